@@ -1,0 +1,143 @@
+"""ctypes bindings of oracle/memc_oracle.c  (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+Every function takes/returns dense NCHW float32 numpy arrays (outputs are float32 for the
+f32 build and float64 for the f64 build) and mirrors one reference CPU entry point:
+
+  filter_interpolation_forward/backward   my_lib.c:904-1079 / 1082-1444
+  flow_projection_forward/backward        my_lib.c:1447-1547 / 1549-1634 (+ fill-hole from
+                                          my_lib_kernel.cu:1742-1836)
+  interpolation_forward/backward          my_lib.c:440-533 / 534-667
+  separable_conv_forward/backward         my_lib.c:250-339 / 340-439
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    """Compile memc_oracle.c (both precisions) with gcc via oracle/Makefile."""
+    want = [os.path.join(_HERE, "liboracle_f32.so"), os.path.join(_HERE, "liboracle_f64.so")]
+    src = os.path.join(_HERE, "memc_oracle.c")
+    stale = force or any(
+        (not os.path.exists(p)) or os.path.getmtime(p) < os.path.getmtime(src) for p in want)
+    if stale:
+        subprocess.run(["make", "-s", "-C", _HERE, "oracle"] + (["-B"] if force else []), check=True)
+    return want
+
+
+def _lib(precision):
+    if precision not in ("f32", "f64"):
+        raise ValueError(precision)
+    if precision not in _LIBS:
+        build()
+        lib = ctypes.CDLL(os.path.join(_HERE, "liboracle_%s.so" % precision))
+        assert lib.oracle_real_bytes() == (4 if precision == "f32" else 8)
+        _LIBS[precision] = lib
+    return _LIBS[precision]
+
+
+def _real(precision):
+    return np.float32 if precision == "f32" else np.float64
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise ValueError("%s: precondition violated (rc=%d)" % (name, rc))
+
+
+def filter_interpolation_forward(in1, flow, filt, precision="f32"):
+    in1, flow, filt = _f32(in1), _f32(flow), _f32(filt)
+    B, C, H, W = in1.shape
+    fs = int(np.sqrt(np.float32(filt.shape[1])))  # my_lib_cuda.c:619-620
+    assert flow.shape == (B, 2, H, W) and filt.shape[0] == B and filt.shape[2:] == (H, W)
+    out = np.zeros((B, C, H, W), dtype=_real(precision))
+    _check(_lib(precision).oracle_filter_interpolation_forward(
+        B, C, H, W, fs, _p(in1), _p(flow), _p(filt), _p(out)), "filter_interpolation_forward")
+    return out
+
+
+def filter_interpolation_backward(in1, flow, filt, gout, precision="f32"):
+    in1, flow, filt, gout = _f32(in1), _f32(flow), _f32(filt), _f32(gout)
+    B, C, H, W = in1.shape
+    fs = int(np.sqrt(np.float32(filt.shape[1])))
+    r = _real(precision)
+    gi1, gi2, gi3 = np.zeros(in1.shape, r), np.zeros(flow.shape, r), np.zeros(filt.shape, r)
+    _check(_lib(precision).oracle_filter_interpolation_backward(
+        B, C, H, W, fs, _p(in1), _p(flow), _p(filt), _p(gout), _p(gi1), _p(gi2), _p(gi3)),
+        "filter_interpolation_backward")
+    return gi1, gi2, gi3
+
+
+def flow_projection_forward(flow, fillhole, precision="f32"):
+    flow = _f32(flow)
+    B, two, H, W = flow.shape
+    assert two == 2
+    count = np.zeros((B, 1, H, W), np.float32)
+    out = np.zeros((B, 2, H, W), _real(precision))
+    _check(_lib(precision).oracle_flow_projection_forward(
+        B, H, W, _p(flow), _p(count), _p(out), int(fillhole)), "flow_projection_forward")
+    return out, count
+
+
+def flow_projection_backward(flow, count, gout, precision="f32"):
+    flow, count, gout = _f32(flow), _f32(count), _f32(gout)
+    B, _, H, W = flow.shape
+    gi = np.zeros(flow.shape, _real(precision))
+    _check(_lib(precision).oracle_flow_projection_backward(
+        B, H, W, _p(flow), _p(count), _p(gout), _p(gi)), "flow_projection_backward")
+    return gi
+
+
+def interpolation_forward(in1, flow, precision="f32"):
+    in1, flow = _f32(in1), _f32(flow)
+    B, C, H, W = in1.shape
+    out = np.zeros(in1.shape, _real(precision))
+    _check(_lib(precision).oracle_interpolation_forward(
+        B, C, H, W, _p(in1), _p(flow), _p(out)), "interpolation_forward")
+    return out
+
+
+def interpolation_backward(in1, flow, gout, precision="f32"):
+    in1, flow, gout = _f32(in1), _f32(flow), _f32(gout)
+    B, C, H, W = in1.shape
+    r = _real(precision)
+    gi1, gi2 = np.zeros(in1.shape, r), np.zeros(flow.shape, r)
+    _check(_lib(precision).oracle_interpolation_backward(
+        B, C, H, W, _p(in1), _p(flow), _p(gout), _p(gi1), _p(gi2)), "interpolation_backward")
+    return gi1, gi2
+
+
+def separable_conv_forward(in1, vert, horiz, precision="f32"):
+    in1, vert, horiz = _f32(in1), _f32(vert), _f32(horiz)
+    B, C, H, W = in1.shape
+    fs = vert.shape[1]
+    out = np.zeros((B, C, H - fs + 1, W - fs + 1), _real(precision))
+    _check(_lib(precision).oracle_separable_conv_forward(
+        B, C, H, W, fs, _p(in1), _p(vert), _p(horiz), _p(out)), "separable_conv_forward")
+    return out
+
+
+def separable_conv_backward(in1, vert, horiz, gout, precision="f32"):
+    in1, vert, horiz, gout = _f32(in1), _f32(vert), _f32(horiz), _f32(gout)
+    B, C, H, W = in1.shape
+    fs = vert.shape[1]
+    r = _real(precision)
+    gi1, gi2, gi3 = np.zeros(in1.shape, r), np.zeros(vert.shape, r), np.zeros(horiz.shape, r)
+    _check(_lib(precision).oracle_separable_conv_backward(
+        B, C, H, W, fs, _p(in1), _p(vert), _p(horiz), _p(gout), _p(gi1), _p(gi2), _p(gi3)),
+        "separable_conv_backward")
+    return gi1, gi2, gi3

@@ -1,0 +1,470 @@
+/*
+ * memc_oracle.c -- CPU restatement of MEMC-Net's per-pixel motion-compensation ops.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path in
+ * memc-net_b200/csrc/.  It may be imported, linked or executed only from tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  The
+ * product path never routes through it (and raises if its CUDA library is missing).
+ *
+ * PARITY PINNING: the reference ships no golden vectors for these ops,
+ * so this restatement is pinned against the reference ITSELF: oracle/Makefile compiles
+ * the reference's own my_package/src/my_lib.c unchanged (against th_stub/TH.h) into
+ * oracle/_ref/libmemc_ref_cpu.so and tests/test_oracle_vs_reference.py requires the
+ * float build of this file to agree with it BIT FOR BIT on seeded inputs; the committed
+ * fixtures under tests/golden/ were generated from that same reference library
+ * (tests/golden/make_golden.py).  Fill-hole has no CPU twin in the reference
+ * (my_lib.c:1539-1543 prints "Not implemented"); it is restated from the CUDA source
+ * my_lib_kernel.cu:1776-1833 and pinned on the GPU box against the reference kernels
+ * recompiled for sm_100a (oracle/_ref/libmemc_ref_gpu.so).
+ *
+ * Two builds (oracle/Makefile): -DORACLE_REAL=float  -> liboracle_f32.so (operation order
+ * of the reference CPU code, no FMA contraction) and -DORACLE_REAL=double ->
+ * liboracle_f64.so (same geometry decisions in fp32, all products and sums in fp64; the
+ * "true value" used to bound fp32 atomic-order noise).
+ *
+ * Layout: every tensor is dense NCHW fp32 (w-stride 1), the only layout the reference's
+ * wrappers accept for these ops besides batch/channel-strided views
+ * (my_lib_cuda.c:642-646).  Outputs are `real` (float or double per build).
+ * Accumulating outputs (gi1/gi3 of FilterInterpolation, count/out of FlowProjection,
+ * gi of FlowProjection backward, gi1 of Interpolation, all SeparableConv grads) are
+ * ADDED into, exactly like the reference, so callers pass zero-filled buffers.
+ *
+ * All functions return 0 on success, -1 on a precondition violation (the reference's
+ * error convention, my_lib_cuda.c:606-617).
+ */
+#include <math.h>
+#include <stddef.h>
+
+#ifndef ORACLE_REAL
+#define ORACLE_REAL float
+#endif
+typedef ORACLE_REAL real;
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int mini(int a, int b) { return a < b ? a : b; }
+
+ORACLE_API int oracle_real_bytes(void) { return (int)sizeof(real); }
+
+/* ------------------------------------------------------------------------------------
+ * FilterInterpolation ("adaptive warp").
+ * Follows my_lib.c:963-1073 (forward) / my_lib_kernel.cu:1121-1214.
+ *
+ * Geometry of one output pixel (h,w) with flow (fx,fy):
+ *   x2 = w + fx, y2 = h + fy                                  (fp32)
+ *   valid  <=>  0 <= x2 <= W-1  &&  0 <= y2 <= H-1  &&  |fx| < W/2  &&  |fy| < H/2
+ *   ix = (int)x2, iy = (int)y2 (truncation; x2,y2 >= 0 so it is floor)
+ *   window origin L = ix + 1 - fs/2, T = iy + 1 - fs/2, size fs x fs
+ *   a tap (j,i) of the window reads image pixel (clamp(j,0,H-1), clamp(i,0,W-1)) and
+ *   filter plane k = (j-T)*fs + (i-L) at the OUTPUT pixel (h,w)
+ *   quadrant of a tap:  top <=> j <= iy,  left <=> i <= ix
+ *   out = (1-a)(1-b) TL + a(1-b) TR + (1-a) b BL + a b BR,  a = x2-ix, b = y2-iy
+ * invalid => out = in1[b,c,h,w]  (my_lib_kernel.cu:1209-1213)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int valid;
+    int ix, iy;      /* truncated target */
+    int L, T;        /* window origin    */
+    float alpha, beta;
+} fi_geom;
+
+static fi_geom fi_geometry(int h, int w, int H, int W, int fs, float fx, float fy)
+{
+    fi_geom g;
+    float x2 = (float)w + fx;
+    float y2 = (float)h + fy;
+    g.valid = (x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1) &&
+               fabsf(fx) < (float)W / 2.0f && fabsf(fy) < (float)H / 2.0f);
+    g.ix = g.iy = g.L = g.T = 0;
+    g.alpha = g.beta = 0.0f;
+    if (g.valid) {
+        g.ix = (int)x2;
+        g.iy = (int)y2;
+        g.L = g.ix + 1 - fs / 2;
+        g.T = g.iy + 1 - fs / 2;
+        g.alpha = x2 - (float)g.ix;
+        g.beta = y2 - (float)g.iy;
+    }
+    return g;
+}
+
+/* the four quadrant sums for one channel; quadrant order/tap order as my_lib.c:994-1040
+ * (rows outer, columns inner inside each quadrant) */
+static void fi_quadrants(const float *img /* [H,W] plane */, const float *filt /* batch base */,
+                         size_t plane, size_t pix, int H, int W, int fs, const fi_geom *g,
+                         real q[4])
+{
+    const int R = g->L + fs, Bm = g->T + fs;
+    for (int qi = 0; qi < 4; ++qi) {
+        const int top = (qi < 2), left = ((qi & 1) == 0);
+        const int j0 = top ? g->T : g->iy + 1, j1 = top ? g->iy : Bm - 1;
+        const int i0 = left ? g->L : g->ix + 1, i1 = left ? g->ix : R - 1;
+        real acc = (real)0;
+        for (int j = j0; j <= j1; ++j) {
+            const int jj = clampi(j, 0, H - 1);
+            for (int i = i0; i <= i1; ++i) {
+                const int ii = clampi(i, 0, W - 1);
+                const int k = (j - g->T) * fs + (i - g->L);
+                acc += (real)img[(size_t)jj * W + ii] * (real)filt[(size_t)k * plane + pix];
+            }
+        }
+        q[qi] = acc;
+    }
+}
+
+ORACLE_API int oracle_filter_interpolation_forward(int B, int C, int H, int W, int fs,
+                                                   const float *in1, const float *flow,
+                                                   const float *filt, real *out)
+{
+    if (B < 0 || C < 0 || H <= 0 || W <= 0 || fs <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *fb = filt + (size_t)b * fs * fs * plane;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const fi_geom g = fi_geometry(h, w, H, W, fs, fx, fy);
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    real *o = out + ((size_t)b * C + c) * plane + pix;
+                    if (!g.valid) { *o = (real)img[pix]; continue; }
+                    real q[4];
+                    fi_quadrants(img, fb, plane, pix, H, W, fs, &g, q);
+                    const real a = (real)g.alpha, bt = (real)g.beta;
+                    /* my_lib.c:1042-1046, left-to-right evaluation */
+                    *o = ((real)1 - a) * ((real)1 - bt) * q[0] + a * ((real)1 - bt) * q[1] +
+                         ((real)1 - a) * bt * q[2] + a * bt * q[3];
+                }
+            }
+    }
+    return 0;
+}
+
+/* Backward, my_lib.c:1151-1439 / my_lib_kernel.cu:1248-1515.
+ * invalid pixel => contributes nothing at all (gi2 is not even written).
+ * gi1 (+=, scatter to the clamped tap), gi3 (+=, own pixel), gi2 (=, own pixel). */
+ORACLE_API int oracle_filter_interpolation_backward(int B, int C, int H, int W, int fs,
+                                                    const float *in1, const float *flow,
+                                                    const float *filt, const float *gout,
+                                                    real *gi1, real *gi2, real *gi3)
+{
+    if (B < 0 || C < 0 || H <= 0 || W <= 0 || fs <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *fb = filt + (size_t)b * fs * fs * plane;
+        real *g3b = gi3 + (size_t)b * fs * fs * plane;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const fi_geom g = fi_geometry(h, w, H, W, fs, fx, fy);
+                if (!g.valid) continue;
+                const real a = (real)g.alpha, bt = (real)g.beta;
+                const int R = g.L + fs, Bm = g.T + fs;
+
+                /* steps 1+3: image and filter gradients (my_lib.c:1189-1253) */
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    real *g1 = gi1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    for (int qi = 0; qi < 4; ++qi) {
+                        const int top = (qi < 2), left = ((qi & 1) == 0);
+                        /* go * {(1-a)|a} * {(1-b)|b}, evaluated left to right */
+                        const real gq = go * (left ? (real)1 - a : a) * (top ? (real)1 - bt : bt);
+                        const int j0 = top ? g.T : g.iy + 1, j1 = top ? g.iy : Bm - 1;
+                        const int i0 = left ? g.L : g.ix + 1, i1 = left ? g.ix : R - 1;
+                        for (int j = j0; j <= j1; ++j) {
+                            const int jj = clampi(j, 0, H - 1);
+                            for (int i = i0; i <= i1; ++i) {
+                                const int ii = clampi(i, 0, W - 1);
+                                const int k = (j - g.T) * fs + (i - g.L);
+                                g1[(size_t)jj * W + ii] += gq * (real)fb[(size_t)k * plane + pix];
+                                g3b[(size_t)k * plane + pix] += gq * (real)img[(size_t)jj * W + ii];
+                            }
+                        }
+                    }
+                }
+
+                /* step 2: flow gradients (my_lib.c:1273-1414).  The reference writes
+                 * gamma = 1 - beta and then uses (1 - gamma), NOT beta: keep that rounding. */
+                real dx = (real)0, dy = (real)0;
+                const real gam_y = (real)1 - bt, gam_x = (real)1 - a;
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    real q[4];
+                    fi_quadrants(img, fb, plane, pix, H, W, fs, &g, q);
+                    real t = (real)0;
+                    t += gam_y * (q[1] - q[0]);
+                    t += ((real)1 - gam_y) * (q[3] - q[2]);
+                    dx += go * t;
+                }
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    real q[4];
+                    fi_quadrants(img, fb, plane, pix, H, W, fs, &g, q);
+                    real t = (real)0;
+                    t += gam_x * (q[2] - q[0]);
+                    t += ((real)1 - gam_x) * (q[3] - q[1]);
+                    dy += go * t;
+                }
+                gi2[((size_t)b * 2 + 0) * plane + pix] = dx;
+                gi2[((size_t)b * 2 + 1) * plane + pix] = dy;
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * FlowProjection: forward splat of -flow to the 4 integer neighbours of p + flow,
+ * count, divide, optional hole fill.
+ *   scatter + average : my_lib.c:1491-1536 (CUDA: my_lib_kernel.cu:1664-1690, 1730-1736)
+ *   fill-hole         : my_lib_kernel.cu:1776-1833 ONLY (no CPU twin in the reference)
+ * `count` is float (integer-valued, exact below 2^24) in both builds, as in the reference.
+ * ---------------------------------------------------------------------------------- */
+static inline int fp_valid(float x2, float y2, int H, int W)
+{
+    return x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1);
+}
+
+ORACLE_API int oracle_flow_projection_forward(int B, int H, int W, const float *flow,
+                                              float *count, real *out, int fillhole)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *fxp = flow + ((size_t)b * 2 + 0) * plane;
+        const float *fyp = flow + ((size_t)b * 2 + 1) * plane;
+        real *ox = out + ((size_t)b * 2 + 0) * plane;
+        real *oy = out + ((size_t)b * 2 + 1) * plane;
+        float *cnt = count + (size_t)b * plane;
+
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const float fx = fxp[(size_t)h * W + w], fy = fyp[(size_t)h * W + w];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                /* a clamped R/Bm makes the same cell appear twice: it is hit twice */
+                for (int k = 0; k < 4; ++k) ox[cell[k]] += -(real)fx;
+                for (int k = 0; k < 4; ++k) oy[cell[k]] += -(real)fy;
+                for (int k = 0; k < 4; ++k) cnt[cell[k]] += 1.0f;
+            }
+
+        for (size_t p = 0; p < plane; ++p) {
+            const float c = cnt[p];
+            if (c > 0.0f) { ox[p] /= (real)c; oy[p] /= (real)c; }
+        }
+
+        if (!fillhole) continue;
+        /* Holes (count <= 0) take the mean of the nearest non-hole to the left, right and
+         * above.  The reference's downward search is `while(down_temp = 0.0f && ...)`
+         * (my_lib_kernel.cu:1799): an assignment, so it never runs and "down" never
+         * contributes.  Holes only read non-hole pixels, so the result is order-free. */
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                if (cnt[(size_t)h * W + w] > 0.0f) continue;
+                int lo = w, ro = w, uo = h;
+                float lt = 0.0f, rt = 0.0f, ut = 0.0f;
+                while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cnt[(size_t)h * W + lo]; }
+                while (rt == 0.0f && ro + 1 <= W - 1) { ++ro; rt = cnt[(size_t)h * W + ro]; }
+                while (ut == 0.0f && uo - 1 >= 0) { --uo; ut = cnt[(size_t)uo * W + w]; }
+                if (lt + rt + ut <= 0.0f) continue; /* nothing found: stays 0 */
+                const real l = lt > 0.0f ? (real)1 : (real)0;
+                const real r = rt > 0.0f ? (real)1 : (real)0;
+                const real u = ut > 0.0f ? (real)1 : (real)0;
+                const real den = l + r + u;
+                real sx = (real)0, sy = (real)0;
+                /* multiply-by-flag then add, in the reference's left/right/up order */
+                if (lt > 0.0f) { sx += ox[(size_t)h * W + lo]; sy += oy[(size_t)h * W + lo]; }
+                if (rt > 0.0f) { sx += ox[(size_t)h * W + ro]; sy += oy[(size_t)h * W + ro]; }
+                if (ut > 0.0f) { sx += ox[(size_t)uo * W + w]; sy += oy[(size_t)uo * W + w]; }
+                ox[(size_t)h * W + w] = sx / den;
+                oy[(size_t)h * W + w] = sy / den;
+            }
+    }
+    return 0;
+}
+
+/* my_lib.c:1590-1629: a gather over the same 4 cells, divided by the saved count;
+ * ignores fill-hole.  gi is added into (reference uses +=). */
+ORACLE_API int oracle_flow_projection_backward(int B, int H, int W, const float *flow,
+                                               const float *count, const float *gout, real *gi)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *cnt = count + (size_t)b * plane;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float *go = gout + ((size_t)b * 2 + ch) * plane;
+                    real *g = gi + ((size_t)b * 2 + ch) * plane + pix;
+                    for (int k = 0; k < 4; ++k) *g += -(real)go[cell[k]] / (real)cnt[cell[k]];
+                }
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Interpolation (plain bilinear backward warp), any channel count (the reference's
+ * InterpolationCh variant is the same code with the channel==3 check removed,
+ * my_lib_cuda.c:490,519).  my_lib.c:480-527 (fwd), 590-660 (bwd).
+ * Note the validity test is x2 < W (not <= W-1) and out-of-range pixels give 0.
+ * ---------------------------------------------------------------------------------- */
+ORACLE_API int oracle_interpolation_forward(int B, int C, int H, int W, const float *in1,
+                                            const float *flow, real *out)
+{
+    if (B < 0 || C < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                const int valid = x2 >= 0.0f && y2 >= 0.0f && x2 < (float)W && y2 < (float)H;
+                int L = 0, T = 0, R = 0, Bm = 0;
+                real a = 0, bt = 0;
+                if (valid) {
+                    L = (int)x2; T = (int)y2;
+                    R = mini(L + 1, W - 1); Bm = mini(T + 1, H - 1);
+                    a = (real)(x2 - (float)L); bt = (real)(y2 - (float)T);
+                }
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    real *o = out + ((size_t)b * C + c) * plane + pix;
+                    if (!valid) { *o = (real)0; continue; }
+                    const real TL = img[(size_t)T * W + L], TR = img[(size_t)T * W + R];
+                    const real BL = img[(size_t)Bm * W + L], BR = img[(size_t)Bm * W + R];
+                    *o = ((real)1 - a) * ((real)1 - bt) * TL + a * ((real)1 - bt) * TR +
+                         ((real)1 - a) * bt * BL + a * bt * BR;
+                }
+            }
+    return 0;
+}
+
+ORACLE_API int oracle_interpolation_backward(int B, int C, int H, int W, const float *in1,
+                                             const float *flow, const float *gout, real *gi1,
+                                             real *gi2)
+{
+    if (B < 0 || C < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!(x2 >= 0.0f && y2 >= 0.0f && x2 < (float)W && y2 < (float)H)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const real a = (real)(x2 - (float)L), bt = (real)(y2 - (float)T);
+                for (int c = 0; c < C; ++c) {
+                    real *g1 = gi1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    g1[(size_t)T * W + L] += go * ((real)1 - a) * ((real)1 - bt);
+                    g1[(size_t)T * W + R] += go * a * ((real)1 - bt);
+                    g1[(size_t)Bm * W + L] += go * ((real)1 - a) * bt;
+                    g1[(size_t)Bm * W + R] += go * a * bt;
+                }
+                /* gamma = Bm - y2 (my_lib.c:622): negative-capable when Bm was clamped */
+                real gam = (real)((float)Bm - y2), dx = (real)0, dy = (real)0;
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    real t = (real)0;
+                    t += gam * ((real)img[(size_t)T * W + R] - (real)img[(size_t)T * W + L]);
+                    t += ((real)1 - gam) * ((real)img[(size_t)Bm * W + R] - (real)img[(size_t)Bm * W + L]);
+                    dx += go * t;
+                }
+                gam = (real)((float)R - x2);
+                for (int c = 0; c < C; ++c) {
+                    const float *img = in1 + ((size_t)b * C + c) * plane;
+                    const real go = (real)gout[((size_t)b * C + c) * plane + pix];
+                    real t = (real)0;
+                    t += gam * ((real)img[(size_t)Bm * W + L] - (real)img[(size_t)T * W + L]);
+                    t += ((real)1 - gam) * ((real)img[(size_t)Bm * W + R] - (real)img[(size_t)T * W + R]);
+                    dy += go * t;
+                }
+                gi2[((size_t)b * 2 + 0) * plane + pix] = dx;
+                gi2[((size_t)b * 2 + 1) * plane + pix] = dy;
+            }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * SeparableConv: per-pixel separable fs x fs local convolution over the valid region.
+ * my_lib.c:312-330 (fwd), 406-430 (bwd).  in1 [B,C,H,W]; vert/horiz [B,fs,Ho,Wo];
+ * out [B,C,Ho,Wo] with Ho = H-fs+1, Wo = W-fs+1.
+ * ---------------------------------------------------------------------------------- */
+ORACLE_API int oracle_separable_conv_forward(int B, int C, int H, int W, int fs,
+                                             const float *in1, const float *vert,
+                                             const float *horiz, real *out)
+{
+    const int Ho = H - fs + 1, Wo = W - fs + 1;
+    if (B < 0 || C < 0 || fs <= 0 || Ho <= 0 || Wo <= 0) return -1;
+    const size_t ip = (size_t)H * W, op = (size_t)Ho * Wo;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < Ho; ++h)
+            for (int w = 0; w < Wo; ++w)
+                for (int c = 0; c < C; ++c) {
+                    real acc = (real)0;
+                    for (int y = 0; y < fs; ++y)
+                        for (int x = 0; x < fs; ++x) {
+                            const real t1 = in1[((size_t)b * C + c) * ip + (size_t)(h + y) * W + (w + x)];
+                            const real t2 = vert[((size_t)b * fs + y) * op + (size_t)h * Wo + w];
+                            const real t3 = horiz[((size_t)b * fs + x) * op + (size_t)h * Wo + w];
+                            acc += t1 * t2 * t3;
+                        }
+                    out[((size_t)b * C + c) * op + (size_t)h * Wo + w] = acc;
+                }
+    return 0;
+}
+
+ORACLE_API int oracle_separable_conv_backward(int B, int C, int H, int W, int fs,
+                                              const float *in1, const float *vert,
+                                              const float *horiz, const float *gout, real *gi1,
+                                              real *gi2, real *gi3)
+{
+    const int Ho = H - fs + 1, Wo = W - fs + 1;
+    if (B < 0 || C < 0 || fs <= 0 || Ho <= 0 || Wo <= 0) return -1;
+    const size_t ip = (size_t)H * W, op = (size_t)Ho * Wo;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < Ho; ++h)
+            for (int w = 0; w < Wo; ++w)
+                for (int c = 0; c < C; ++c) {
+                    const real go = gout[((size_t)b * C + c) * op + (size_t)h * Wo + w];
+                    for (int y = 0; y < fs; ++y)
+                        for (int x = 0; x < fs; ++x) {
+                            const size_t i1 = ((size_t)b * C + c) * ip + (size_t)(h + y) * W + (w + x);
+                            const size_t i2 = ((size_t)b * fs + y) * op + (size_t)h * Wo + w;
+                            const size_t i3 = ((size_t)b * fs + x) * op + (size_t)h * Wo + w;
+                            const real t1 = in1[i1], t2 = vert[i2], t3 = horiz[i3];
+                            gi1[i1] += go * t2 * t3;
+                            gi2[i2] += go * t1 * t3;
+                            gi3[i3] += go * t1 * t2;
+                        }
+                }
+    return 0;
+}
