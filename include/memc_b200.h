@@ -1,0 +1,217 @@
+/*
+ * memc_b200.h -- C ABI of libmemc_b200.so: B200-native (sm_100a) kernels for MEMC-Net's
+ * per-pixel motion-compensation hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) REFERENCE-NAMED LAUNCHERS.  Same names, argument order and error convention as the
+ *      extern "C" launchers the reference declares in my_package/src/my_lib_kernel.h and
+ *      calls from its THC glue my_package/src/my_lib_cuda.c.  A caller written against the
+ *      reference's header (the cffi/THC glue, or a ctypes stub) links
+ *      against libmemc_b200.so instead of my_lib_kernel.o with no source change.
+ *      Contract (identical to the reference):
+ *        - all tensors fp32, 4-D NCHW, w-stride 1; strides are in ELEMENTS (int);
+ *        - the caller owns every buffer and ZERO-FILLS every output / gradient buffer
+ *          before the call; the library allocates nothing and frees nothing;
+ *        - work is enqueued asynchronously on `stream`; no synchronisation;
+ *        - returns 0 on success, -1 on a launch failure or a layout the kernels cannot
+ *          take (w-stride != 1);  `nElement` is accepted and ignored, as in the reference.
+ *      Beyond the reference: batch/channel offsets are computed in 64 bits, so tensors
+ *      above 2^31 elements work as long as each stride fits an int.
+ *
+ *  (2) memc_b200_* EXTENDED ENTRY POINTS.  64-bit strides plus a `flags` word:
+ *        MEMC_B200_OVERWRITE  the library itself produces every element of every output
+ *                             (zero-filling what it scatters into), so the caller may pass
+ *                             uninitialised buffers and skip its memsets;
+ *        MEMC_B200_NO_FAST    force the generic (non-TMA) kernels (used by the tests to
+ *                             cross-check the fast path).
+ *      The Python autograd Functions in memc-net_b200/my_package/functions use these.
+ *
+ * cudaStream_t is passed as an opaque pointer so that this header needs no CUDA include.
+ */
+#ifndef MEMC_B200_H
+#define MEMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef MEMC_B200_STREAM_T
+#define MEMC_B200_STREAM_T
+typedef void *memc_stream_t; /* a cudaStream_t */
+#endif
+
+#if defined(__GNUC__)
+#define MEMC_B200_API __attribute__((visibility("default")))
+#else
+#define MEMC_B200_API
+#endif
+
+#define MEMC_B200_OVERWRITE 1
+#define MEMC_B200_NO_FAST 2
+
+/* ---- library info ------------------------------------------------------------------ */
+MEMC_B200_API int memc_b200_abi_version(void);          /* bumped on any signature change            */
+MEMC_B200_API const char *memc_b200_build_info(void);   /* "sm_100a nvcc <ver> ..."                   */
+/* number of kernel launches (incl. memsets) the library has issued since load, for
+ * bench.py's gpu_launches accounting */
+MEMC_B200_API unsigned long long memc_b200_launch_count(void);
+
+/* ====================================================================================
+ * (1) reference-named launchers
+ * ==================================================================================== */
+
+/* replaces my_lib_kernel.h:133-144 (called from my_lib_cuda.c:651) */
+MEMC_B200_API int FilterInterpolationLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const float *input1, const float *input2, const float *input3, float *output);
+
+/* replaces my_lib_kernel.h:146-158 (called from my_lib_cuda.c:729) */
+MEMC_B200_API int FilterInterpolationLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const float *input1, const float *input2, const float *input3,
+    const float *gradoutput, float *gradinput1, float *gradinput2, float *gradinput3);
+
+/* replaces my_lib_kernel.h:161-171 (called from my_lib_cuda.c:785): scatter -> average ->
+ * (fillhole ? fill-hole : nothing) */
+MEMC_B200_API int FlowProjection_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int fillhole,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const float *input1, float *count, float *output);
+
+/* replaces my_lib_kernel.h:173-187 (called from my_lib_cuda.c:839) */
+MEMC_B200_API int FlowProjection_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const float *input1, const float *count, const float *gradoutput, float *gradinput1);
+
+/* replaces my_lib_kernel.h:67-81 (called from my_lib_cuda.c:402 and, for the Ch variant,
+ * :519) */
+MEMC_B200_API int InterpolationLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const float *input1, const float *input2, float *output);
+
+/* replaces my_lib_kernel.h:83-98 (called from my_lib_cuda.c:462, :579) */
+MEMC_B200_API int InterpolationLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const float *input1, const float *input2, const float *gradoutput,
+    float *gradinput1, float *gradinput2);
+
+/* replace my_lib_kernel.h:101-132: the reference's InterpolationCh kernels are a copy of
+ * the Interpolation ones with no channel restriction; here they are the same code. */
+MEMC_B200_API int InterpolationChLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const float *input1, const float *input2, float *output);
+
+MEMC_B200_API int InterpolationChLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const float *input1, const float *input2, const float *gradoutput,
+    float *gradinput1, float *gradinput2);
+
+/* replaces my_lib_kernel.h:37-48 (called from my_lib_cuda.c:257).  w,h are the INPUT
+ * image extent; the output/filter extent is (h-fs+1) x (w-fs+1). */
+MEMC_B200_API int SeparableConvLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input2, const float *input3, float *output);
+
+/* replaces my_lib_kernel.h:50-64 (called from my_lib_cuda.c:341) */
+MEMC_B200_API int SeparableConvLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input2, const float *input3,
+    const float *gradoutput, float *gradinput1, float *gradinput2, float *gradinput3);
+
+/* ====================================================================================
+ * (2) extended entry points
+ * ==================================================================================== */
+
+/* strides of one NCHW tensor, in elements; the w-stride is implicitly 1 */
+typedef struct memc_strides {
+    int64_t b, c, h;
+} memc_strides;
+
+MEMC_B200_API int memc_b200_filter_interpolation_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_filter, memc_strides s_out,
+    const float *input1, const float *flow, const float *filter, float *output, int flags);
+
+MEMC_B200_API int memc_b200_filter_interpolation_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_filter, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2, memc_strides s_gi3,
+    const float *input1, const float *flow, const float *filter, const float *gradoutput,
+    float *gradinput1, float *gradinput2, float *gradinput3, int flags);
+
+MEMC_B200_API int memc_b200_flow_projection_forward(
+    memc_stream_t stream, int batch, int h, int w, int fillhole,
+    memc_strides s_flow, memc_strides s_count, memc_strides s_out,
+    const float *flow, float *count, float *output, int flags);
+
+MEMC_B200_API int memc_b200_flow_projection_backward(
+    memc_stream_t stream, int batch, int h, int w,
+    memc_strides s_flow, memc_strides s_count, memc_strides s_gout, memc_strides s_gi,
+    const float *flow, const float *count, const float *gradoutput, float *gradinput, int flags);
+
+MEMC_B200_API int memc_b200_interpolation_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_out,
+    const float *input1, const float *flow, float *output, int flags);
+
+MEMC_B200_API int memc_b200_interpolation_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2,
+    const float *input1, const float *flow, const float *gradoutput,
+    float *gradinput1, float *gradinput2, int flags);
+
+MEMC_B200_API int memc_b200_separable_conv_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_vert, memc_strides s_horiz, memc_strides s_out,
+    const float *input1, const float *vertical, const float *horizontal, float *output, int flags);
+
+MEMC_B200_API int memc_b200_separable_conv_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_vert, memc_strides s_horiz, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2, memc_strides s_gi3,
+    const float *input1, const float *vertical, const float *horizontal, const float *gradoutput,
+    float *gradinput1, float *gradinput2, float *gradinput3, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMC_B200_H */

@@ -1,0 +1,63 @@
+"""Build libmemc_b200.so (sm_100a) in-tree with nvcc.
+
+    python memc-net_b200/build.py [--force] [--verbose]
+
+The library lands in memc-net_b200/lib/libmemc_b200.so; it is git-ignored (source-only
+history) but travels to the GPU box with the gpurun snapshot.  nvcc cross-compiles without
+a GPU.  No torch headers are involved: the boundary is a plain C ABI (include/memc_b200.h).
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libmemc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [
+        os.path.join(HERE, "..", "include", "memc_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not (force or _stale()):
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    flags = [f for f in FLAGS if f != "--use_fast_math=false"]
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    for src in sources():
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([NVCC, *flags, "-c", src, "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0 or verbose:
+            sys.stderr.write("== %s ==\n%s\n" % (os.path.basename(src), out))
+        failed |= pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcuda"], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,343 @@
+// filter_interpolation.cu -- FilterInterpolation ("adaptive warp") forward / backward, generic path.
+//
+// Semantics: reference my_package/src/my_lib_kernel.cu:1087-1218 (forward) and :1220-1518
+// (backward); CPU twin my_lib.c:904-1444.  See oracle/memc_oracle.c for the plain-C statement.
+//
+// This file holds the GENERIC kernels: any filter size, any (w-stride-1) strides, no
+// alignment requirements; one output pixel per thread, gathers served by L1.  The TMA /
+// shared-memory fast path for fs = 4 lives in filter_interpolation_tma.cu and falls back
+// here whenever its layout preconditions do not hold.
+//
+// Differences from the legacy kernels (same results):
+//   * the fs*fs filter planes of a pixel are read ONCE into registers (fs = 4) instead of
+//     once per channel;
+//   * backward: gradinput3 / gradinput2 are accumulated in registers and written once (the
+//     legacy code issues 16*C atomics on its own pixel), the four quadrant sums are computed
+//     once instead of three times; only gradinput1 (a true scatter) uses atomics.
+#include "memc_common.cuh"
+
+namespace memc {
+
+struct FiArgs {
+    int B, C, H, W, fs;
+    View in1, flow, filt, out;  // `out` = output (fwd) or gradoutput (bwd)
+    View gi1, gi2, gi3;         // bwd only
+    const float* in1p;
+    const float* flowp;
+    const float* filtp;
+    float* outp;          // fwd
+    const float* goutp;   // bwd
+    float* gi1p;
+    float* gi2p;
+    float* gi3p;
+};
+
+constexpr int BX = 32, BY = 8;
+
+// ------------------------------------------------------------------------------ forward
+template <int FS>
+__global__ void __launch_bounds__(BX* BY) fi_fwd_direct_kernel(const FiArgs p) {
+    const int w = blockIdx.x * BX + threadIdx.x;
+    const int h = blockIdx.y * BY + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || h >= p.H) return;
+    const int fs = FS ? FS : p.fs;
+    const int W = p.W, H = p.H;
+
+    const float* fl = p.flowp + b * p.flow.b + h * p.flow.h + w;
+    const float fx = ldg_stream(fl);
+    const float fy = ldg_stream(fl + p.flow.c);
+    const FiGeom g = fi_geometry(w, h, W, H, fx, fy);
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    float* ob = p.outp + b * p.out.b + h * p.out.h + w;
+
+    if (!g.valid) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
+        const float* src = in1b + h * p.in1.h + w;
+        for (int c = 0; c < p.C; ++c) stg_stream(ob + c * p.out.c, __ldg(src + c * p.in1.c));
+        return;
+    }
+
+    const float* fb = p.filtp + b * p.filt.b + h * p.filt.h + w;
+    const float a = g.alpha, bt = g.beta;
+    const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
+    const float wBL = (1.0f - a) * bt, wBR = a * bt;
+
+    if (FS == 4) {
+        float wg[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) wg[k] = ldg_stream(fb + k * p.filt.c);
+        const int L = g.ix - 1, T = g.iy - 1;
+        int xo[4];
+        int64_t yo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xo[i] = clampi(L + i, 0, W - 1);
+            yo[i] = (int64_t)clampi(T + i, 0, H - 1) * p.in1.h;
+        }
+        for (int c = 0; c < p.C; ++c) {
+            const float* img = in1b + c * p.in1.c;
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    q[(j >> 1) * 2 + (i >> 1)] = fmaf(__ldg(img + yo[j] + xo[i]), wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+            stg_stream(ob + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
+        }
+    } else {
+        const int hf = fs / 2;
+        const int L = g.ix + 1 - hf, T = g.iy + 1 - hf;
+        for (int c = 0; c < p.C; ++c) {
+            const float* img = in1b + c * p.in1.c;
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < fs; ++j) {
+                const float* row = img + (int64_t)clampi(T + j, 0, H - 1) * p.in1.h;
+                for (int i = 0; i < fs; ++i) {
+                    const float t = __ldg(row + clampi(L + i, 0, W - 1)) * __ldg(fb + (j * fs + i) * p.filt.c);
+                    // predicated adds instead of q[dynamic]: keeps q[] in registers
+                    q[0] += (j < hf && i < hf) ? t : 0.f;
+                    q[1] += (j < hf && i >= hf) ? t : 0.f;
+                    q[2] += (j >= hf && i < hf) ? t : 0.f;
+                    q[3] += (j >= hf && i >= hf) ? t : 0.f;
+                }
+            }
+            stg_stream(ob + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- backward
+// OVERWRITE: every element of gi2/gi3 is produced here (zeros for invalid pixels); gi1 has
+// been zero-filled by the launcher.  !OVERWRITE: reference contract, add into gi1/gi3,
+// assign gi2 for valid pixels only.
+template <int FS, bool OVERWRITE>
+__global__ void __launch_bounds__(BX* BY) fi_bwd_direct_kernel(const FiArgs p) {
+    const int w = blockIdx.x * BX + threadIdx.x;
+    const int h = blockIdx.y * BY + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || h >= p.H) return;
+    const int fs = FS ? FS : p.fs;
+    const int W = p.W, H = p.H;
+
+    const float* fl = p.flowp + b * p.flow.b + h * p.flow.h + w;
+    const float fx = ldg_stream(fl);
+    const float fy = ldg_stream(fl + p.flow.c);
+    const FiGeom g = fi_geometry(w, h, W, H, fx, fy);
+
+    float* g2 = p.gi2p + b * p.gi2.b + h * p.gi2.h + w;
+    float* g3 = p.gi3p + b * p.gi3.b + h * p.gi3.h + w;
+
+    if (!g.valid) {  // my_lib_kernel.cu:1256: an invalid pixel contributes nothing
+        if (OVERWRITE) {
+            stg_stream(g2, 0.f);
+            stg_stream(g2 + p.gi2.c, 0.f);
+            for (int k = 0; k < fs * fs; ++k) stg_stream(g3 + k * p.gi3.c, 0.f);
+        }
+        return;
+    }
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    float* g1b = p.gi1p + b * p.gi1.b;
+    const float* go = p.goutp + b * p.out.b + h * p.out.h + w;
+    const float* fb = p.filtp + b * p.filt.b + h * p.filt.h + w;
+    const float a = g.alpha, bt = g.beta;
+    // the reference forms gamma = 1 - beta and then uses (1 - gamma) rather than beta
+    const float gam_y = 1.0f - bt, gam_x = 1.0f - a;
+    float dx = 0.f, dy = 0.f;
+
+    if (FS == 4) {
+        float wg[16], acc3[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            wg[k] = ldg_stream(fb + k * p.filt.c);
+            acc3[k] = 0.f;
+        }
+        const int L = g.ix - 1, T = g.iy - 1;
+        int xo[4];
+        int yc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xo[i] = clampi(L + i, 0, W - 1);
+            yc[i] = clampi(T + i, 0, H - 1);
+        }
+        for (int c = 0; c < p.C; ++c) {
+            const float* img = in1b + c * p.in1.c;
+            float* g1 = g1b + c * p.gi1.c;
+            const float gov = ldg_stream(go + c * p.out.c);
+            const float gq[4] = {gov * (1.0f - a) * (1.0f - bt), gov * a * (1.0f - bt),
+                                 gov * (1.0f - a) * bt, gov * a * bt};
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int qi = (j >> 1) * 2 + (i >> 1);
+                    const float v = __ldg(img + (int64_t)yc[j] * p.in1.h + xo[i]);
+                    red_add(g1 + (int64_t)yc[j] * p.gi1.h + xo[i], gq[qi] * wg[j * 4 + i]);
+                    acc3[j * 4 + i] = fmaf(gq[qi], v, acc3[j * 4 + i]);
+                    q[qi] = fmaf(v, wg[j * 4 + i], q[qi]);
+                }
+            dx = fmaf(gov, gam_y * (q[1] - q[0]) + (1.0f - gam_y) * (q[3] - q[2]), dx);
+            dy = fmaf(gov, gam_x * (q[2] - q[0]) + (1.0f - gam_x) * (q[3] - q[1]), dy);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (OVERWRITE) stg_stream(g3 + k * p.gi3.c, acc3[k]);
+            else g3[k * p.gi3.c] += acc3[k];  // own pixel: no atomic needed
+        }
+    } else {
+        const int hf = fs / 2;
+        const int L = g.ix + 1 - hf, T = g.iy + 1 - hf;
+        // pass A: taps outer, channels inner -> gi3 (one write per tap) and the gi1 scatter
+        for (int j = 0; j < fs; ++j) {
+            const int yc = clampi(T + j, 0, H - 1);
+            for (int i = 0; i < fs; ++i) {
+                const int xc = clampi(L + i, 0, W - 1);
+                const float wk = __ldg(fb + (j * fs + i) * p.filt.c);
+                const float qa = (i >= hf) ? a : 1.0f - a;
+                const float qb = (j >= hf) ? bt : 1.0f - bt;
+                float acc = 0.f;
+                for (int c = 0; c < p.C; ++c) {
+                    const float gq = __ldg(go + c * p.out.c) * qa * qb;
+                    red_add(g1b + c * p.gi1.c + (int64_t)yc * p.gi1.h + xc, gq * wk);
+                    acc = fmaf(gq, __ldg(in1b + c * p.in1.c + (int64_t)yc * p.in1.h + xc), acc);
+                }
+                float* dst = g3 + (j * fs + i) * p.gi3.c;
+                if (OVERWRITE) stg_stream(dst, acc);
+                else *dst += acc;
+            }
+        }
+        // pass B: quadrant sums per channel -> flow gradient
+        for (int c = 0; c < p.C; ++c) {
+            const float* img = in1b + c * p.in1.c;
+            const float gov = __ldg(go + c * p.out.c);
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < fs; ++j) {
+                const float* row = img + (int64_t)clampi(T + j, 0, H - 1) * p.in1.h;
+                for (int i = 0; i < fs; ++i) {
+                    const float t = __ldg(row + clampi(L + i, 0, W - 1)) * __ldg(fb + (j * fs + i) * p.filt.c);
+                    // predicated adds instead of q[dynamic]: keeps q[] in registers
+                    q[0] += (j < hf && i < hf) ? t : 0.f;
+                    q[1] += (j < hf && i >= hf) ? t : 0.f;
+                    q[2] += (j >= hf && i < hf) ? t : 0.f;
+                    q[3] += (j >= hf && i >= hf) ? t : 0.f;
+                }
+            }
+            dx = fmaf(gov, gam_y * (q[1] - q[0]) + (1.0f - gam_y) * (q[3] - q[2]), dx);
+            dy = fmaf(gov, gam_x * (q[2] - q[0]) + (1.0f - gam_x) * (q[3] - q[1]), dy);
+        }
+    }
+    stg_stream(g2, dx);
+    stg_stream(g2 + p.gi2.c, dy);
+}
+
+// fast path (filter_interpolation_tma.cu); returns 1 if it took the call, 0 if not
+// applicable, -1 on error
+int fi_forward_fast(cudaStream_t stream, const FiArgs& a);
+int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool overwrite);
+
+static int fi_forward(cudaStream_t stream, const FiArgs& a, int flags) {
+    if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    if (a.fs <= 0) return -1;
+    if (!(flags & MEMC_B200_NO_FAST)) {
+        const int r = fi_forward_fast(stream, a);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
+    dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
+    if (a.fs == 4) fi_fwd_direct_kernel<4><<<grid, block, 0, stream>>>(a);
+    else fi_fwd_direct_kernel<0><<<grid, block, 0, stream>>>(a);
+    count_launch();
+    return check_launch("FilterInterpolation forward");
+}
+
+static int fi_backward(cudaStream_t stream, const FiArgs& a, int flags) {
+    if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    if (a.fs <= 0) return -1;
+    const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
+    if (ow && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
+    if (!(flags & MEMC_B200_NO_FAST)) {
+        const int r = fi_backward_fast(stream, a, ow);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
+    dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
+    if (a.fs == 4) {
+        if (ow) fi_bwd_direct_kernel<4, true><<<grid, block, 0, stream>>>(a);
+        else fi_bwd_direct_kernel<4, false><<<grid, block, 0, stream>>>(a);
+    } else {
+        if (ow) fi_bwd_direct_kernel<0, true><<<grid, block, 0, stream>>>(a);
+        else fi_bwd_direct_kernel<0, false><<<grid, block, 0, stream>>>(a);
+    }
+    count_launch();
+    return check_launch("FilterInterpolation backward");
+}
+
+}  // namespace memc
+
+using namespace memc;
+
+extern "C" int memc_b200_filter_interpolation_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_filter, memc_strides s_out,
+    const float* input1, const float* flow, const float* filter, float* output, int flags) {
+    FiArgs a{};
+    a.B = batch; a.C = channel; a.H = h; a.W = w; a.fs = filter_size;
+    a.in1 = mk_view(s_in1); a.flow = mk_view(s_flow); a.filt = mk_view(s_filter); a.out = mk_view(s_out);
+    a.in1p = input1; a.flowp = flow; a.filtp = filter; a.outp = output;
+    return fi_forward(stream, a, flags);
+}
+
+extern "C" int memc_b200_filter_interpolation_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_filter, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2, memc_strides s_gi3,
+    const float* input1, const float* flow, const float* filter, const float* gradoutput,
+    float* gradinput1, float* gradinput2, float* gradinput3, int flags) {
+    FiArgs a{};
+    a.B = batch; a.C = channel; a.H = h; a.W = w; a.fs = filter_size;
+    a.in1 = mk_view(s_in1); a.flow = mk_view(s_flow); a.filt = mk_view(s_filter); a.out = mk_view(s_gout);
+    a.gi1 = mk_view(s_gi1); a.gi2 = mk_view(s_gi2); a.gi3 = mk_view(s_gi3);
+    a.in1p = input1; a.flowp = flow; a.filtp = filter; a.goutp = gradoutput;
+    a.gi1p = gradinput1; a.gi2p = gradinput2; a.gi3p = gradinput3;
+    return fi_backward(stream, a, flags);
+}
+
+// Reference-named launchers (my_lib_kernel.h:133-158).  The reference passes only the
+// input strides: output / gradients share input1's (resp. input2's, input3's) batch and
+// channel strides (checked by its wrapper, my_lib_cuda.c:645-646, 719-723) and every
+// tensor uses its source's h-stride (my_lib_kernel.cu:1184, 1283-1286, 1424).
+extern "C" int FilterInterpolationLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement, const int w, const int h, const int channel,
+    const int batch, const int filter_size,
+    const int i1b, const int i1c, const int i1h, const int i1w,
+    const int i2b, const int i2c, const int i2h, const int i2w,
+    const int i3b, const int i3c, const int i3h, const int i3w,
+    const float* input1, const float* input2, const float* input3, float* output) {
+    (void)nElement;
+    if (i1w != 1 || i2w != 1 || i3w != 1) return -1;
+    FiArgs a{};
+    a.B = batch; a.C = channel; a.H = h; a.W = w; a.fs = filter_size;
+    a.in1 = mk_view(i1b, i1c, i1h); a.flow = mk_view(i2b, i2c, i2h); a.filt = mk_view(i3b, i3c, i3h);
+    a.out = a.in1;
+    a.in1p = input1; a.flowp = input2; a.filtp = input3; a.outp = output;
+    return fi_forward(stream, a, 0);
+}
+
+extern "C" int FilterInterpolationLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement, const int w, const int h, const int channel,
+    const int batch, const int filter_size,
+    const int i1b, const int i1c, const int i1h, const int i1w,
+    const int i2b, const int i2c, const int i2h, const int i2w,
+    const int i3b, const int i3c, const int i3h, const int i3w,
+    const float* input1, const float* input2, const float* input3, const float* gradoutput,
+    float* gradinput1, float* gradinput2, float* gradinput3) {
+    (void)nElement;
+    if (i1w != 1 || i2w != 1 || i3w != 1) return -1;
+    FiArgs a{};
+    a.B = batch; a.C = channel; a.H = h; a.W = w; a.fs = filter_size;
+    a.in1 = mk_view(i1b, i1c, i1h); a.flow = mk_view(i2b, i2c, i2h); a.filt = mk_view(i3b, i3c, i3h);
+    a.out = a.in1; a.gi1 = a.in1; a.gi2 = a.flow; a.gi3 = a.filt;
+    a.in1p = input1; a.flowp = input2; a.filtp = input3; a.goutp = gradoutput;
+    a.gi1p = gradinput1; a.gi2p = gradinput2; a.gi3p = gradinput3;
+    return fi_backward(stream, a, 0);
+}

@@ -1,0 +1,47 @@
+// runtime.cu -- library info, launch accounting and the strided zero-fill used by the
+// MEMC_B200_OVERWRITE entry points.
+#include "memc_common.cuh"
+
+namespace memc {
+
+unsigned long long g_launches = 0;
+
+__global__ void __launch_bounds__(256) zero_rows_kernel(float* p, View v, int C, int H, int W) {
+    // grid: (ceil(W/256), H, B*C)
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= W) return;
+    const int bc = blockIdx.z;
+    const int b = bc / C, c = bc - b * C;
+    p[b * v.b + c * v.c + (int64_t)blockIdx.y * v.h + w] = 0.0f;
+}
+
+int zero_fill(cudaStream_t stream, float* p, View v, int B, int C, int H, int W) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    const bool dense = v.h == W && (C == 1 || v.c == (int64_t)H * W) && (B == 1 || v.b == (int64_t)C * H * W);
+    if (dense) {
+        cudaError_t err = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)B * C * H * W, stream);
+        count_launch();
+        if (err != cudaSuccess) {
+            fprintf(stderr, "memc_b200: memset failed: %s\n", cudaGetErrorString(err));
+            return -1;
+        }
+        return 0;
+    }
+    dim3 grid((W + 255) / 256, H, B * C);
+    zero_rows_kernel<<<grid, 256, 0, stream>>>(p, v, C, H, W);
+    count_launch();
+    return check_launch("zero_fill");
+}
+
+}  // namespace memc
+
+extern "C" int memc_b200_abi_version(void) { return 1; }
+
+#define MEMC_STR2(x) #x
+#define MEMC_STR(x) MEMC_STR2(x)
+extern "C" const char* memc_b200_build_info(void) {
+    return "libmemc_b200 sm_100a nvcc " MEMC_STR(__CUDACC_VER_MAJOR__) "." MEMC_STR(__CUDACC_VER_MINOR__) "." MEMC_STR(
+        __CUDACC_VER_BUILD__) " built " __DATE__;
+}
+
+extern "C" unsigned long long memc_b200_launch_count(void) { return memc::g_launches; }

@@ -1,0 +1,68 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names.
+
+All generators take a `torch.Generator` seed and a device and are deterministic per
+(seed, shape).  They are used by bench.py and by the tests so that both run the same data.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _gen(seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    return g
+
+
+def smooth_flow(B, H, W, sigma, seed=0, device="cpu", jitter=0.25):
+    """Low-res N(0, sigma^2) field at (H/16, W/16) bilinearly upsampled, plus per-pixel
+    N(0, jitter^2): smooth motion with fractional positions everywhere."""
+    g = _gen(seed, device)
+    lh, lw = max(2, H // 16), max(2, W // 16)
+    low = torch.randn(B, 2, lh, lw, generator=g, device=device) * sigma
+    flow = F.interpolate(low, size=(H, W), mode="bilinear", align_corners=True)
+    flow = flow + torch.randn(B, 2, H, W, generator=g, device=device) * jitter
+    return flow.contiguous()
+
+
+def uniform_flow(B, H, W, amplitude, seed=0, device="cpu"):
+    g = _gen(seed, device)
+    return ((torch.rand(B, 2, H, W, generator=g, device=device) * 2 - 1) * amplitude).contiguous()
+
+
+def radial_flow(B, H, W, gain, device="cpu"):
+    """flow = gain * (centre - p): gain ~0.9 makes nearly every pixel splat into a few
+    hundred cells (atomic contention); a negative gain diverges and tears large holes."""
+    ys = torch.arange(H, device=device, dtype=torch.float32).view(1, 1, H, 1)
+    xs = torch.arange(W, device=device, dtype=torch.float32).view(1, 1, 1, W)
+    fx = gain * ((W - 1) / 2.0 - xs).expand(B, 1, H, W)
+    fy = gain * ((H - 1) / 2.0 - ys).expand(B, 1, H, W)
+    return torch.cat([fx, fy], dim=1).contiguous()
+
+
+def image(B, C, H, W, seed=0, device="cpu"):
+    return torch.rand(B, C, H, W, generator=_gen(seed, device), device=device)
+
+
+def softmax_filter(B, fs, H, W, seed=0, device="cpu"):
+    """Per-pixel kernels that are positive and sum to 1 over the fs*fs taps."""
+    return torch.softmax(torch.randn(B, fs * fs, H, W, generator=_gen(seed, device), device=device), dim=1)
+
+
+def gaussian_filter(B, fs, H, W, seed=0, device="cpu", scale=0.25):
+    return torch.randn(B, fs * fs, H, W, generator=_gen(seed, device), device=device) * scale
+
+
+def grad_like(t, seed=0):
+    return torch.randn(t.shape, generator=_gen(seed, t.device), device=t.device)
+
+
+def filter_interpolation_case(B, C, H, W, fs=4, sigma=None, seed=0, device="cpu"):
+    """(input1, flow, filter, gradoutput) for FilterInterpolation; sigma defaults to the
+    SURVEY's 4 px @720p / 6 px @1080p scaled by height."""
+    if sigma is None:
+        sigma = 6.0 * H / 1080.0 if H >= 900 else 4.0 * max(H, 64) / 720.0
+    in1 = image(B, C, H, W, seed, device)
+    flow = smooth_flow(B, H, W, sigma, seed + 1, device)
+    filt = softmax_filter(B, fs, H, W, seed + 2, device)
+    gout = grad_like(in1, seed + 3)
+    return in1, flow, filt, gout

@@ -1,0 +1,60 @@
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN CPU code.
+
+Run where /root/reference exists:   python tests/golden/make_golden.py
+It builds oracle/_ref/libmemc_ref_cpu.so (my_package/src/my_lib.c compiled unchanged against
+oracle/th_stub/TH.h, see oracle/Makefile), feeds it the seeded inputs of tests/cases.py and
+stores inputs + reference outputs.  Fill-hole has no CPU implementation in the reference
+(my_lib.c:1539-1543), so flow-projection fixtures are scatter+average only; the fill-hole
+fixture is produced on the GPU box by tests/golden/make_golden_gpu.py from the reference
+CUDA kernels.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from tests.cases import fi_case, flow_case, sepconv_case  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref.build()
+    assert ref.available_cpu(), "reference CPU library could not be built"
+    for name, (B, C, H, W, fs, sigma, seed) in {
+            "fi_rgb_fs4": (2, 3, 16, 20, 4, 3.0, 100),
+            "fi_c5_fs5": (1, 5, 12, 14, 5, 2.0, 101),
+            "fi_fs2": (1, 2, 9, 11, 2, 1.5, 102),
+            "fi_fs6_wild": (1, 3, 14, 14, 6, 20.0, 103)}.items():
+        in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed)
+        out = ref.cpu_filter_interpolation_forward(in1, flow, filt)
+        g1, g2, g3 = ref.cpu_filter_interpolation_backward(in1, flow, filt, gout)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="filter_interpolation", in1=in1, flow=flow,
+                            filt=filt, gout=gout, out=out, g1=g1, g2=g2, g3=g3)
+    for name, (B, H, W, sigma, seed) in {"fp_small": (2, 12, 16, 3.0, 110), "fp_wild": (1, 10, 10, 15.0, 111)}.items():
+        flow = flow_case(B, H, W, sigma, seed)
+        out, count = ref.cpu_flow_projection_forward(flow)
+        gout = np.random.default_rng(seed).standard_normal(flow.shape).astype(np.float32)
+        gi = ref.cpu_flow_projection_backward(flow, count, gout)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="flow_projection", flow=flow, out=out,
+                            count=count, gout=gout, gi=gi)
+    for name, (B, C, H, W, sigma, seed) in {"ip_rgb": (2, 3, 12, 16, 3.0, 120), "ip_c7": (1, 7, 9, 13, 2.0, 121)}.items():
+        in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed)
+        out = ref.cpu_interpolation_forward(in1, flow)
+        g1, g2 = ref.cpu_interpolation_backward(in1, flow, gout)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="interpolation", in1=in1, flow=flow, gout=gout,
+                            out=out, g1=g1, g2=g2)
+    for name, (B, C, H, W, fs, seed) in {"sc_fs4": (2, 3, 12, 15, 4, 130), "sc_fs3": (1, 3, 8, 8, 3, 131)}.items():
+        in1, v, hz, gout = sepconv_case(B, C, H, W, fs, seed)
+        out = ref.cpu_separable_conv_forward(in1, v, hz)
+        g1, g2, g3 = ref.cpu_separable_conv_backward(in1, v, hz, gout)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="separable_conv", in1=in1, vert=v, horiz=hz,
+                            gout=gout, out=out, g1=g1, g2=g2, g3=g3)
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()

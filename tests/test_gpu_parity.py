@@ -1,0 +1,369 @@
+"""GPU parity tests proper (run on the B200 box):  libmemc_b200.so, called through the C ABI
+(reference-named launchers, extended entry points, and the autograd Functions / Modules that
+sit on them) against
+
+  * the CPU oracle (oracle/memc_oracle.c, pinned bit-exactly to the reference's my_lib.c),
+    f32 and f64 builds, on the same seeded inputs, incl. the edge cases of tests/cases.py;
+  * the reference's OWN CUDA kernels recompiled for sm_100a (oracle/_ref/libmemc_ref_gpu.so),
+    when that binary travelled with the snapshot.
+
+Tolerance (north_star): <= 1e-5 max-abs fp32 against the reference's kernels, written as
+TOL below.  Outputs that are sums of float atomics (gradinput1, FlowProjection output) are
+order-dependent even in the reference; they are compared with the f64 oracle using
+TOL * max(1, max|expected|) and `count` (integer-valued) exactly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu, ref
+from tests.cases import fi_case, flow_case, sepconv_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.detach().cpu().numpy()
+
+
+def close(got, exp, tol=TOL, what=""):
+    got = host(got) if isinstance(got, torch.Tensor) else got
+    exp = np.asarray(exp, dtype=np.float64)
+    scale = max(1.0, float(np.abs(exp).max())) if exp.size else 1.0
+    err = float(np.abs(got.astype(np.float64) - exp).max()) if exp.size else 0.0
+    assert err <= tol * scale, "%s: max-abs err %.3e > %.1e * %.3g" % (what, err, tol, scale)
+    return err
+
+
+@pytest.fixture(scope="module")
+def L(built_lib):
+    from memc_b200 import lib
+    lib.load()
+    assert torch.cuda.is_available()
+    return lib
+
+
+FI_SHAPES = [  # B, C, H, W, fs, sigma
+    (1, 3, 64, 64, 4, 3.0), (3, 3, 64, 64, 4, 3.0), (2, 3, 37, 53, 4, 8.0), (1, 5, 20, 31, 5, 2.0),
+    (1, 2, 16, 16, 2, 1.0), (1, 3, 24, 24, 6, 40.0), (1, 64, 16, 24, 4, 2.0), (1, 1, 1, 1, 4, 0.0),
+    (2, 3, 96, 128, 4, 4.0), (1, 3, 128, 256, 4, 20.0), (1, 64, 64, 128, 4, 3.0), (1, 3, 70, 260, 4, 1.0),
+]
+
+
+# ------------------------------------------------------------------- FilterInterpolation
+@pytest.mark.parametrize("shape", FI_SHAPES)
+@pytest.mark.parametrize("no_fast", [False, True])
+def test_filter_interpolation_modules_vs_oracle(L, shape, no_fast, monkeypatch):
+    """Through the public API (Module -> Function -> extended C ABI, OVERWRITE mode)."""
+    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+    if no_fast:  # force the generic kernels to cross-check the fast path
+        monkeypatch.setattr(L, "OVERWRITE", L.OVERWRITE | L.NO_FAST)
+    B, C, H, W, fs, sigma = shape
+    in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed=sum(shape[:5]))
+    t1, t2, t3 = dev(in1).requires_grad_(), dev(flow).requires_grad_(), dev(filt).requires_grad_()
+    out = FilterInterpolationModule()(t1, t2, t3)
+    close(out, cpu.filter_interpolation_forward(in1, flow, filt), what="out vs f32 oracle")
+    close(out, cpu.filter_interpolation_forward(in1, flow, filt, "f64"), what="out vs f64 oracle")
+    g1, g2, g3 = torch.autograd.grad(out, (t1, t2, t3), dev(gout))
+    e1, e2, e3 = cpu.filter_interpolation_backward(in1, flow, filt, gout, "f64")
+    close(g1, e1, what="gradinput1"), close(g2, e2, what="gradinput2"), close(g3, e3, what="gradinput3")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 37, 53, 4, 8.0), (1, 5, 20, 31, 5, 2.0), (2, 3, 96, 128, 4, 4.0)])
+def test_filter_interpolation_named_abi_reference_contract(L, shape):
+    """Reference-named FFI functions: caller zero-fills; gi1/gi3 are ADDED into, gi2 is
+    ASSIGNED for valid pixels only (my_lib_kernel.cu:1283-1286, 1424, 1495)."""
+    import my_package._ext.my_lib as my_lib
+    B, C, H, W, fs, sigma = shape
+    in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed=5)
+    t1, t2, t3, tg = dev(in1), dev(flow), dev(filt), dev(gout)
+    out = torch.zeros_like(t1)
+    assert my_lib.FilterInterpolationLayer_gpu_forward(t1, t2, t3, out) == 0
+    close(out, cpu.filter_interpolation_forward(in1, flow, filt, "f64"), what="out")
+    e1, e2, e3 = cpu.filter_interpolation_backward(in1, flow, filt, gout, "f64")
+    for prefill in (0.0, 1.0):
+        g1, g2, g3 = (torch.full_like(t, prefill) for t in (t1, t2, t3))
+        assert my_lib.FilterInterpolationLayer_gpu_backward(t1, t2, t3, tg, g1, g2, g3) == 0
+        close(g1, e1 + prefill, what="gi1 (+=)")
+        close(g3, e3 + prefill, what="gi3 (+=)")
+        # invalid pixels keep the prefill in gi2: e2 is 0 there, valid ones are overwritten
+        x2 = np.arange(W, dtype=np.float32)[None, None, :] + flow[:, 0]
+        y2 = np.arange(H, dtype=np.float32)[None, :, None] + flow[:, 1]
+        with np.errstate(invalid="ignore"):
+            valid = ((x2 >= 0) & (y2 >= 0) & (x2 <= W - 1) & (y2 <= H - 1) &
+                     (np.abs(flow[:, 0]) < np.float32(W) / 2) & (np.abs(flow[:, 1]) < np.float32(H) / 2))
+        exp2 = np.where(valid[:, None], e2, prefill)
+        close(g2, exp2, what="gi2 (= for valid only)")
+
+
+def test_filter_interpolation_strided_views_and_stream(L):
+    """b/c-strided views (the reference accepts them, my_lib_cuda.c:624-646) on a side stream."""
+    import my_package._ext.my_lib as my_lib
+    B, C, H, W = 2, 3, 40, 48
+    in1, flow, filt, gout = fi_case(B, C, H, W, 4, 3.0, seed=17)
+    big1 = torch.zeros(B + 1, C + 2, H, W, device="cuda")
+    bigo = torch.zeros_like(big1)
+    v1, vo = big1[1:, 1:1 + C], bigo[1:, 1:1 + C]
+    v1.copy_(dev(in1))
+    bigf = torch.zeros(B, 20, H, W, device="cuda")
+    vf = bigf[:, 2:18]
+    vf.copy_(dev(filt))
+    t2 = dev(flow)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        assert my_lib.FilterInterpolationLayer_gpu_forward(v1, t2, vf, vo) == 0
+    s.synchronize()
+    close(vo, cpu.filter_interpolation_forward(in1, flow, filt, "f64"), what="strided out")
+    assert float(bigo[0].abs().max()) == 0.0 and float(bigo[:, 0].abs().max()) == 0.0  # nothing spilled
+
+
+@pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
+@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 4, 4.0), (1, 64, 64, 128, 4, 3.0), (1, 5, 20, 31, 5, 2.0),
+                                   (1, 3, 128, 256, 4, 20.0)])
+def test_filter_interpolation_vs_reference_cuda_kernels(L, shape):
+    """north_star bar: <= 1e-5 max-abs fp32 vs the reference's own CUDA kernels, same inputs."""
+    import my_package._ext.my_lib as my_lib
+    B, C, H, W, fs, sigma = shape
+    in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed=23)
+    t1, t2, t3, tg = dev(in1), dev(flow), dev(filt), dev(gout)
+    r_out = ref.gpu_filter_interpolation_forward(t1, t2, t3)
+    out = torch.zeros_like(t1)
+    assert my_lib.FilterInterpolationLayer_gpu_forward(t1, t2, t3, out) == 0
+    close(out, host(r_out), what="out vs reference CUDA")
+    r1, r2, r3 = ref.gpu_filter_interpolation_backward(t1, t2, t3, tg)
+    g1, g2, g3 = torch.zeros_like(t1), torch.zeros_like(t2), torch.zeros_like(t3)
+    assert my_lib.FilterInterpolationLayer_gpu_backward(t1, t2, t3, tg, g1, g2, g3) == 0
+    close(g1, host(r1), what="gi1 vs reference CUDA")
+    close(g2, host(r2), what="gi2 vs reference CUDA")
+    close(g3, host(r3), what="gi3 vs reference CUDA")
+
+
+def test_filter_interpolation_720p_vs_oracle(L):
+    """One full 1280x720 frame (BASELINE.json configs[1] geometry) against the f64 oracle."""
+    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+    from memc_b200 import synth
+    B, C, H, W = 1, 3, 720, 1280
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, seed=3, device="cuda")
+    t1.requires_grad_(), t2.requires_grad_(), t3.requires_grad_()
+    out = FilterInterpolationModule()(t1, t2, t3)
+    g1, g2, g3 = torch.autograd.grad(out, (t1, t2, t3), tg)
+    in1, flow, filt, gout = host(t1), host(t2), host(t3), host(tg)
+    close(out, cpu.filter_interpolation_forward(in1, flow, filt, "f64"), what="720p out")
+    e1, e2, e3 = cpu.filter_interpolation_backward(in1, flow, filt, gout, "f64")
+    close(g1, e1, what="720p gi1"), close(g2, e2, what="720p gi2"), close(g3, e3, what="720p gi3")
+
+
+# ------------------------------------------------------------------------ FlowProjection
+FP_SHAPES = [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0), (2, 96, 160, 6.0), (1, 70, 260, 1.0)]
+
+
+@pytest.mark.parametrize("shape", FP_SHAPES)
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_flow_projection_vs_oracle(L, shape, fillhole):
+    from my_package.functions.FlowProjectionLayer import FlowProjectionLayer
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=31)
+    layer = FlowProjectionLayer(requires_grad=not fillhole)
+    t = dev(flow).requires_grad_(not fillhole)
+    out = layer(t)
+    eo, ec = cpu.flow_projection_forward(flow, fillhole, "f64")
+    assert np.array_equal(host(layer.count), ec), "count must be exact"
+    close(out, eo, what="FlowProjection out")
+    if not fillhole:
+        gout = np.random.default_rng(3).standard_normal(flow.shape).astype(np.float32)
+        (gi,) = torch.autograd.grad(out, (t,), dev(gout))
+        close(gi, cpu.flow_projection_backward(flow, ec, gout, "f64"), what="FlowProjection gi")
+
+
+def test_flow_projection_named_abi_reference_contract(L):
+    import my_package._ext.my_lib as my_lib
+    B, H, W = 2, 48, 64
+    flow = flow_case(B, H, W, 5.0, seed=37)
+    t = dev(flow)
+    for fillhole in (0, 1):
+        count, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.FlowProjectionLayer_gpu_forward(t, count, out, fillhole) == 0
+        eo, ec = cpu.flow_projection_forward(flow, fillhole, "f64")
+        assert np.array_equal(host(count), ec)
+        close(out, eo, what="named FlowProjection fwd fillhole=%d" % fillhole)
+    gout = np.random.default_rng(4).standard_normal(flow.shape).astype(np.float32)
+    for prefill in (0.0, 1.0):  # the reference kernel does `gradinput1[...] += ...` (my_lib_kernel.cu:1879)
+        gi = torch.full_like(t, prefill)
+        assert my_lib.FlowProjectionLayer_gpu_backward(t, count, dev(gout), gi) == 0
+        e = cpu.flow_projection_backward(flow, ec, gout, "f64")
+        x2 = np.arange(W, dtype=np.float32)[None, None, :] + flow[:, 0]
+        y2 = np.arange(H, dtype=np.float32)[None, :, None] + flow[:, 1]
+        with np.errstate(invalid="ignore"):
+            valid = (x2 >= 0) & (y2 >= 0) & (x2 <= W - 1) & (y2 <= H - 1)
+        close(gi, np.where(valid[:, None], e + prefill, prefill), what="named FlowProjection bwd")
+
+
+@pytest.mark.parametrize("kind", ["contention", "divergent", "uniform"])
+def test_flow_projection_regimes(L, kind):
+    """The three BASELINE.json configs[2] regimes at a size the oracle finishes quickly."""
+    from my_package.functions.FlowProjectionLayer import FlowProjectionLayer
+    from memc_b200 import synth
+    B, H, W = 2, 270, 480
+    if kind == "contention":
+        t = synth.radial_flow(B, H, W, 0.9, device="cuda")
+    elif kind == "divergent":
+        t = synth.radial_flow(B, H, W, -0.5, device="cuda")
+    else:
+        t = synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda")
+    layer = FlowProjectionLayer(requires_grad=False)
+    out = layer(t)
+    eo, ec = cpu.flow_projection_forward(host(t), 1, "f64")
+    assert np.array_equal(host(layer.count), ec)
+    # thousands of addends of magnitude ~100 px land on one cell in the contention case: the
+    # fp32 atomic order noise scales with sum|addend| * eps, so bound by TOL * max|sum|/count...
+    close(out, eo, tol=5e-5 if kind == "contention" else TOL, what=kind)
+
+
+@pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_flow_projection_vs_reference_cuda_kernels(L, fillhole):
+    import my_package._ext.my_lib as my_lib
+    from memc_b200 import synth
+    B, H, W = 2, 180, 320
+    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -0.5, device="cuda")):
+        r_out, r_count = ref.gpu_flow_projection_forward(t, fillhole)
+        count, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.FlowProjectionLayer_gpu_forward(t, count, out, fillhole) == 0
+        assert torch.equal(count, r_count)
+        close(out, host(r_out), what="FlowProjection vs reference CUDA (fillhole=%d)" % fillhole)
+        gout = torch.randn_like(t)
+        gi = torch.zeros_like(t)
+        assert my_lib.FlowProjectionLayer_gpu_backward(t, count, gout, gi) == 0
+        close(gi, host(ref.gpu_flow_projection_backward(t, r_count, gout)), what="FlowProjection bwd vs reference CUDA")
+
+
+def test_flow_projection_fillhole_follows_requires_grad(L):
+    """FlowProjectionModule(input.requires_grad): holes are filled only when no grad is
+    required (reference FlowProjectionLayer.py:15) -- callers use torch.no_grad()."""
+    from my_package.modules.FlowProjectionModule import FlowProjectionModule
+    from memc_b200 import synth
+    t = synth.radial_flow(1, 64, 96, -0.5, device="cuda")
+    filled = FlowProjectionModule(False)(t)
+    unfilled = FlowProjectionModule(True)(t)
+    eo1, _ = cpu.flow_projection_forward(host(t), 1, "f64")
+    eo0, _ = cpu.flow_projection_forward(host(t), 0, "f64")
+    close(filled, eo1), close(unfilled, eo0)
+    assert np.abs(eo1 - eo0).max() > 0.1
+
+
+# ------------------------------------------------------------------------- Interpolation
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0), (1, 3, 1, 1, 0.0),
+                                   (2, 3, 96, 160, 5.0)])
+def test_interpolation_vs_oracle(L, shape):
+    from my_package.modules.InterpolationModule import InterpolationModule
+    B, C, H, W, sigma = shape
+    in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed=41)
+    t1, t2 = dev(in1).requires_grad_(), dev(flow).requires_grad_()
+    out = InterpolationModule()(t1, t2)
+    close(out, cpu.interpolation_forward(in1, flow, "f64"), what="Interpolation out")
+    g1, g2 = torch.autograd.grad(out, (t1, t2), dev(gout))
+    e1, e2 = cpu.interpolation_backward(in1, flow, gout, "f64")
+    close(g1, e1, what="Interpolation gi1"), close(g2, e2, what="Interpolation gi2")
+
+
+def test_interpolation_named_abi_and_reference_cuda(L):
+    import my_package._ext.my_lib as my_lib
+    B, C, H, W = 2, 3, 60, 84
+    in1, flow, _, gout = fi_case(B, C, H, W, 4, 4.0, seed=43)
+    t1, t2, tg = dev(in1), dev(flow), dev(gout)
+    out = torch.zeros_like(t1)
+    assert my_lib.InterpolationLayer_gpu_forward(t1, t2, out) == 0
+    close(out, cpu.interpolation_forward(in1, flow, "f64"))
+    g1, g2 = torch.zeros_like(t1), torch.zeros_like(t2)
+    assert my_lib.InterpolationLayer_gpu_backward(t1, t2, tg, g1, g2) == 0
+    e1, e2 = cpu.interpolation_backward(in1, flow, gout, "f64")
+    close(g1, e1), close(g2, e2)
+    # Ch variant: any channel count
+    in5 = np.random.default_rng(1).random((B, 5, H, W), dtype=np.float32)
+    o5 = torch.zeros(B, 5, H, W, device="cuda")
+    assert my_lib.InterpolationLayer_gpu_forward(dev(in5), t2, o5) == -1  # C != 3 rejected (my_lib_cuda.c:373)
+    assert my_lib.InterpolationChLayer_gpu_forward(dev(in5), t2, o5) == 0
+    close(o5, cpu.interpolation_forward(in5, flow, "f64"))
+    if ref.available_gpu():
+        close(out, host(ref.gpu_interpolation_forward(t1, t2)), what="vs reference CUDA fwd")
+        r1, r2 = ref.gpu_interpolation_backward(t1, t2, tg)
+        close(g1, host(r1), what="vs reference CUDA gi1"), close(g2, host(r2), what="vs reference CUDA gi2")
+
+
+# ------------------------------------------------------------------------- SeparableConv
+@pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3), (1, 3, 4, 4, 4), (2, 3, 64, 96, 4)])
+def test_separable_conv_vs_oracle(L, shape):
+    from my_package.functions.SeparableConvLayer import SeparableConvLayer
+    B, C, H, W, fs = shape
+    in1, v, hz, gout = sepconv_case(B, C, H, W, fs, seed=47)
+    t1, t2, t3 = dev(in1).requires_grad_(), dev(v).requires_grad_(), dev(hz).requires_grad_()
+    out = SeparableConvLayer(fs)(t1, t2, t3)
+    close(out, cpu.separable_conv_forward(in1, v, hz, "f64"), what="SeparableConv out")
+    g1, g2, g3 = torch.autograd.grad(out, (t1, t2, t3), dev(gout))
+    e1, e2, e3 = cpu.separable_conv_backward(in1, v, hz, gout, "f64")
+    close(g1, e1, what="SeparableConv gi1"), close(g2, e2, what="gi2"), close(g3, e3, what="gi3")
+
+
+def test_separable_conv_named_abi_and_reference_cuda(L):
+    import my_package._ext.my_lib as my_lib
+    B, C, H, W, fs = 2, 3, 40, 56, 4
+    in1, v, hz, gout = sepconv_case(B, C, H, W, fs, seed=53)
+    t1, t2, t3, tg = dev(in1), dev(v), dev(hz), dev(gout)
+    out = torch.zeros(B, C, H - fs + 1, W - fs + 1, device="cuda")
+    assert my_lib.SeparableConvLayer_gpu_forward(t1, t2, t3, out) == 0
+    close(out, cpu.separable_conv_forward(in1, v, hz, "f64"))
+    e1, e2, e3 = cpu.separable_conv_backward(in1, v, hz, gout, "f64")
+    for prefill in (0.0, 1.0):  # reference: atomicAdd into all three (my_lib_kernel.cu:376-381)
+        g1, g2, g3 = (torch.full_like(t, prefill) for t in (t1, t2, t3))
+        assert my_lib.SeparableConvLayer_gpu_backward(t1, t2, t3, tg, g1, g2, g3) == 0
+        close(g1, e1 + prefill), close(g2, e2 + prefill), close(g3, e3 + prefill)
+    if ref.available_gpu():
+        close(out, host(ref.gpu_separable_conv_forward(t1, t2, t3)), what="vs reference CUDA fwd")
+        r1, r2, r3 = ref.gpu_separable_conv_backward(t1, t2, t3, tg)
+        g1, g2, g3 = (torch.zeros_like(t) for t in (t1, t2, t3))
+        assert my_lib.SeparableConvLayer_gpu_backward(t1, t2, t3, tg, g1, g2, g3) == 0
+        close(g1, host(r1)), close(g2, host(r2)), close(g3, host(r3))
+
+
+# ------------------------------------------------------------------------------ goldens
+def test_cuda_path_matches_golden_fixtures(L):
+    """The committed reference-made vectors (tests/golden) through the CUDA path."""
+    import glob
+    import os
+    import my_package._ext.my_lib as my_lib
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))):
+        z = np.load(path)
+        op = str(z["op"])
+        if op == "filter_interpolation":
+            t1, t2, t3 = dev(z["in1"]), dev(z["flow"]), dev(z["filt"])
+            out = torch.zeros_like(t1)
+            assert my_lib.FilterInterpolationLayer_gpu_forward(t1, t2, t3, out) == 0
+            close(out, z["out"], what=path)
+            g1, g2, g3 = torch.zeros_like(t1), torch.zeros_like(t2), torch.zeros_like(t3)
+            assert my_lib.FilterInterpolationLayer_gpu_backward(t1, t2, t3, dev(z["gout"]), g1, g2, g3) == 0
+            close(g1, z["g1"], what=path), close(g2, z["g2"], what=path), close(g3, z["g3"], what=path)
+        elif op == "flow_projection":
+            t = dev(z["flow"])
+            fh = int(z["fillhole"]) if "fillhole" in z.files else 0
+            count, out = torch.zeros(t.shape[0], 1, *t.shape[2:], device="cuda"), torch.zeros_like(t)
+            assert my_lib.FlowProjectionLayer_gpu_forward(t, count, out, fh) == 0
+            assert np.array_equal(host(count), z["count"])
+            close(out, z["out"], what=path)
+        elif op == "interpolation":
+            t1, t2 = dev(z["in1"]), dev(z["flow"])
+            out = torch.zeros_like(t1)
+            fn = my_lib.InterpolationLayer_gpu_forward if t1.shape[1] == 3 else my_lib.InterpolationChLayer_gpu_forward
+            assert fn(t1, t2, out) == 0
+            close(out, z["out"], what=path)
+        elif op == "separable_conv":
+            t1, t2, t3 = dev(z["in1"]), dev(z["vert"]), dev(z["horiz"])
+            out = torch.zeros(*z["out"].shape, device="cuda")
+            assert my_lib.SeparableConvLayer_gpu_forward(t1, t2, t3, out) == 0
+            close(out, z["out"], what=path)

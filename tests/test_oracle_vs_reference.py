@@ -1,0 +1,85 @@
+"""Pins oracle/memc_oracle.c (our restatement) to the reference's OWN CPU code.
+
+oracle/_ref/libmemc_ref_cpu.so is my_package/src/my_lib.c compiled unchanged (oracle/Makefile);
+the float build of the oracle must agree with it BIT FOR BIT on seeded inputs, including the
+edge cases of tests/cases.py.  Skipped where oracle/_ref is absent (it is built wherever
+/root/reference exists and travels with the repo snapshot); the committed fixtures under
+tests/golden/ (test_golden.py) carry the same pin everywhere.
+"""
+import numpy as np
+import pytest
+
+from oracle import cpu, ref
+from tests.cases import fi_case, flow_case, sepconv_case
+
+needs_ref = pytest.mark.skipif(not ref.available_cpu(), reason="oracle/_ref/libmemc_ref_cpu.so not built")
+
+FI_SHAPES = [  # B, C, H, W, fs, sigma
+    (1, 3, 64, 64, 4, 3.0),    # BASELINE.json configs[0]
+    (3, 3, 64, 64, 4, 3.0),
+    (2, 3, 37, 53, 4, 8.0),    # ragged
+    (1, 5, 20, 31, 5, 2.0),    # odd filter size, C != 3
+    (1, 2, 16, 16, 2, 1.0),
+    (1, 3, 24, 24, 6, 40.0),   # mostly out-of-range flow
+    (1, 64, 16, 24, 4, 2.0),   # MEMC_Net_star context channels
+    (1, 1, 1, 1, 4, 0.0),      # degenerate 1x1
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", FI_SHAPES)
+def test_filter_interpolation_bit_exact(shape):
+    B, C, H, W, fs, sigma = shape
+    in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed=hash(shape) % 1000)
+    assert np.array_equal(cpu.filter_interpolation_forward(in1, flow, filt),
+                          ref.cpu_filter_interpolation_forward(in1, flow, filt))
+    for a, b in zip(cpu.filter_interpolation_backward(in1, flow, filt, gout),
+                    ref.cpu_filter_interpolation_backward(in1, flow, filt, gout)):
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0)])
+def test_flow_projection_bit_exact(shape):
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=11)
+    out, count = cpu.flow_projection_forward(flow, fillhole=0)
+    rout, rcount = ref.cpu_flow_projection_forward(flow)
+    assert np.array_equal(count, rcount) and np.array_equal(out, rout)
+    gout = np.random.default_rng(5).standard_normal(flow.shape).astype(np.float32)
+    assert np.array_equal(cpu.flow_projection_backward(flow, count, gout),
+                          ref.cpu_flow_projection_backward(flow, count, gout))
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0)])
+def test_interpolation_bit_exact(shape):
+    B, C, H, W, sigma = shape
+    in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed=7)
+    assert np.array_equal(cpu.interpolation_forward(in1, flow), ref.cpu_interpolation_forward(in1, flow))
+    for a, b in zip(cpu.interpolation_backward(in1, flow, gout), ref.cpu_interpolation_backward(in1, flow, gout)):
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3)])
+def test_separable_conv_bit_exact(shape):
+    B, C, H, W, fs = shape
+    in1, v, hz, gout = sepconv_case(B, C, H, W, fs, seed=3)
+    assert np.array_equal(cpu.separable_conv_forward(in1, v, hz), ref.cpu_separable_conv_forward(in1, v, hz))
+    for a, b in zip(cpu.separable_conv_backward(in1, v, hz, gout),
+                    ref.cpu_separable_conv_backward(in1, v, hz, gout)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 37, 53, 4, 5.0), (1, 64, 16, 24, 4, 2.0)])
+def test_f64_build_agrees_with_f32(shape):
+    """The f64 build makes the same geometric decisions, so it differs only by rounding."""
+    B, C, H, W, fs, sigma = shape
+    in1, flow, filt, gout = fi_case(B, C, H, W, fs, sigma, seed=1)
+    o32 = cpu.filter_interpolation_forward(in1, flow, filt, "f32")
+    o64 = cpu.filter_interpolation_forward(in1, flow, filt, "f64")
+    assert o64.dtype == np.float64 and np.abs(o32 - o64).max() < 2e-6
+    for a, b in zip(cpu.filter_interpolation_backward(in1, flow, filt, gout, "f32"),
+                    cpu.filter_interpolation_backward(in1, flow, filt, gout, "f64")):
+        assert np.abs(a - b).max() < 1e-4 * max(1.0, np.abs(b).max())
