@@ -24,7 +24,10 @@
  *                             (zero-filling what it scatters into), so the caller may pass
  *                             uninitialised buffers and skip its memsets;
  *        MEMC_B200_NO_FAST    force the generic (non-TMA) kernels (used by the tests to
- *                             cross-check the fast path).
+ *                             cross-check the fast path);
+ *        MEMC_B200_NO_ZERO    with OVERWRITE: the caller has already zero-filled the
+ *                             scatter targets (gradinput1 / count+output); lets bench.py
+ *                             time the kernel apart from the memset.
  *      The Python autograd Functions in memc-net_b200/my_package/functions use these.
  *
  * cudaStream_t is passed as an opaque pointer so that this header needs no CUDA include.
@@ -51,6 +54,7 @@ typedef void *memc_stream_t; /* a cudaStream_t */
 
 #define MEMC_B200_OVERWRITE 1
 #define MEMC_B200_NO_FAST 2
+#define MEMC_B200_NO_ZERO 4
 
 /* ---- library info ------------------------------------------------------------------ */
 MEMC_B200_API int memc_b200_abi_version(void);          /* bumped on any signature change            */

@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcuda"], check=True)
+    subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs], check=True)
     return LIB
 
 

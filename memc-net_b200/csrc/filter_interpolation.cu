@@ -255,7 +255,7 @@ static int fi_backward(cudaStream_t stream, const FiArgs& a, int flags) {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     if (a.fs <= 0) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
-    if (ow && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
+    if (ow && !(flags & MEMC_B200_NO_ZERO) && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {
         const int r = fi_backward_fast(stream, a, ow);
         if (r != 0) return r < 0 ? -1 : 0;

@@ -145,7 +145,7 @@ static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
         const int r = fp_forward_fast(stream, a, ow);
         if (r != 0) return r < 0 ? -1 : 0;
     }
-    if (ow) {
+    if (ow && !(flags & MEMC_B200_NO_ZERO)) {
         if (zero_fill(stream, a.countp, a.count, a.B, 1, a.H, a.W) != 0) return -1;
         if (zero_fill(stream, a.outp, a.out, a.B, 2, a.H, a.W) != 0) return -1;
     }

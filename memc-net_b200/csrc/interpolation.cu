@@ -102,7 +102,7 @@ static int ip_forward(cudaStream_t stream, const IpArgs& a, int flags) {
 static int ip_backward(cudaStream_t stream, const IpArgs& a, int flags) {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
-    if (ow && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
+    if (ow && !(flags & MEMC_B200_NO_ZERO) && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
     dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
     if (ow) ip_bwd_kernel<true><<<grid, block, 0, stream>>>(a);
     else ip_bwd_kernel<false><<<grid, block, 0, stream>>>(a);

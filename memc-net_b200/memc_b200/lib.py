@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmemc_b200.so")
 
 OVERWRITE = 1  # MEMC_B200_OVERWRITE
 NO_FAST = 2    # MEMC_B200_NO_FAST
+NO_ZERO = 4    # MEMC_B200_NO_ZERO
 
 _lib = None
 

@@ -39,6 +39,19 @@ def radial_flow(B, H, W, gain, device="cpu"):
     return torch.cat([fx, fy], dim=1).contiguous()
 
 
+def tear_flow(B, H, W, amplitude, seed=0, device="cpu", jitter=0.25):
+    """Two motion layers pulling apart: the left half moves left and the right half moves right
+    by `amplitude`, the top half up and the bottom half down -> a cross of holes 2*amplitude wide
+    in the projected flow (the fill-hole stress case: long searches, whole columns empty)."""
+    g = _gen(seed, device)
+    xs = torch.arange(W, device=device, dtype=torch.float32).view(1, 1, 1, W)
+    ys = torch.arange(H, device=device, dtype=torch.float32).view(1, 1, H, 1)
+    fx = torch.where(xs < W / 2.0, -float(amplitude), float(amplitude)).expand(B, 1, H, W)
+    fy = torch.where(ys < H / 2.0, -float(amplitude), float(amplitude)).expand(B, 1, H, W)
+    flow = torch.cat([fx, fy], dim=1) + torch.randn(B, 2, H, W, generator=g, device=device) * jitter
+    return flow.contiguous()
+
+
 def image(B, C, H, W, seed=0, device="cpu"):
     return torch.rand(B, C, H, W, generator=_gen(seed, device), device=device)
 

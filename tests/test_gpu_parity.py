@@ -205,7 +205,7 @@ def test_flow_projection_named_abi_reference_contract(L):
         close(gi, np.where(valid[:, None], e + prefill, prefill), what="named FlowProjection bwd")
 
 
-@pytest.mark.parametrize("kind", ["contention", "divergent", "uniform"])
+@pytest.mark.parametrize("kind", ["contention", "divergent", "uniform", "tear"])
 def test_flow_projection_regimes(L, kind):
     """The three BASELINE.json configs[2] regimes at a size the oracle finishes quickly."""
     from my_package.functions.FlowProjectionLayer import FlowProjectionLayer
@@ -214,7 +214,9 @@ def test_flow_projection_regimes(L, kind):
     if kind == "contention":
         t = synth.radial_flow(B, H, W, 0.9, device="cuda")
     elif kind == "divergent":
-        t = synth.radial_flow(B, H, W, -0.5, device="cuda")
+        t = synth.radial_flow(B, H, W, -1.5, device="cuda")   # targets 2.5 px apart: lattice of holes
+    elif kind == "tear":
+        t = synth.tear_flow(B, H, W, 20.0, seed=4, device="cuda")
     else:
         t = synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda")
     layer = FlowProjectionLayer(requires_grad=False)
@@ -232,7 +234,8 @@ def test_flow_projection_vs_reference_cuda_kernels(L, fillhole):
     import my_package._ext.my_lib as my_lib
     from memc_b200 import synth
     B, H, W = 2, 180, 320
-    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -0.5, device="cuda")):
+    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -1.5, device="cuda"),
+              synth.tear_flow(B, H, W, 12.0, seed=3, device="cuda")):
         r_out, r_count = ref.gpu_flow_projection_forward(t, fillhole)
         count, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
         assert my_lib.FlowProjectionLayer_gpu_forward(t, count, out, fillhole) == 0
@@ -249,7 +252,7 @@ def test_flow_projection_fillhole_follows_requires_grad(L):
     required (reference FlowProjectionLayer.py:15) -- callers use torch.no_grad()."""
     from my_package.modules.FlowProjectionModule import FlowProjectionModule
     from memc_b200 import synth
-    t = synth.radial_flow(1, 64, 96, -0.5, device="cuda")
+    t = synth.tear_flow(1, 64, 96, 6.0, device="cuda")
     filled = FlowProjectionModule(False)(t)
     unfilled = FlowProjectionModule(True)(t)
     eo1, _ = cpu.flow_projection_forward(host(t), 1, "f64")

@@ -133,7 +133,7 @@ def main():
         flows = {"smooth": synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"),
                  "uniform": synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda"),
                  "contention": synth.radial_flow(B, H, W, 0.9, device="cuda"),
-                 "divergent": synth.radial_flow(B, H, W, -0.5, device="cuda")}
+                 "tear": synth.tear_flow(B, H, W, 24.0, seed=3, device="cuda")}
         for kind, flow in flows.items():
             count = torch.empty(B, 1, H, W, device="cuda")
             out = torch.empty_like(flow)

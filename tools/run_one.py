@@ -1,0 +1,32 @@
+"""Launch one op a few times (for ncu captures).   python tools/run_one.py fi_fwd|fi_bwd|fp_fwd|... [B] [flags]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "memc-net_b200")):
+    sys.path.insert(0, p)
+from memc_b200 import lib, synth  # noqa: E402
+from tools.kbench import fi_calls, S, P  # noqa: E402
+
+op = sys.argv[1]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else lib.OVERWRITE
+C = int(os.environ.get("C", "3"))
+H, W = int(os.environ.get("H", "1080")), int(os.environ.get("W", "1920"))
+lib.load()
+if op in ("fi_fwd", "fi_bwd"):
+    _, fwd, bwd = fi_calls(B, C, H, W, flags)
+    for _ in range(3):
+        (fwd if op == "fi_fwd" else bwd)()
+elif op == "fp_fwd":
+    kind = os.environ.get("FLOW", "smooth")
+    flow = {"smooth": lambda: synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"),
+            "uniform": lambda: synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda"),
+            "contention": lambda: synth.radial_flow(B, H, W, 0.9, device="cuda")}[kind]()
+    count, out = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(flow)
+    for _ in range(3):
+        lib.call("memc_b200_flow_projection_forward", lib.stream_ptr(flow), B, H, W, 1, S(flow), S(count), S(out),
+                 P(flow), P(count), P(out), flags)
+torch.cuda.synchronize()
