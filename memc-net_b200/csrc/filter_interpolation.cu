@@ -14,23 +14,10 @@
 //   * backward: gradinput3 / gradinput2 are accumulated in registers and written once (the
 //     legacy code issues 16*C atomics on its own pixel), the four quadrant sums are computed
 //     once instead of three times; only gradinput1 (a true scatter) uses atomics.
-#include "memc_common.cuh"
+#include "filter_interpolation.cuh"
 
 namespace memc {
 
-struct FiArgs {
-    int B, C, H, W, fs;
-    View in1, flow, filt, out;  // `out` = output (fwd) or gradoutput (bwd)
-    View gi1, gi2, gi3;         // bwd only
-    const float* in1p;
-    const float* flowp;
-    const float* filtp;
-    float* outp;          // fwd
-    const float* goutp;   // bwd
-    float* gi1p;
-    float* gi2p;
-    float* gi3p;
-};
 
 constexpr int BX = 32, BY = 8;
 
@@ -231,11 +218,6 @@ __global__ void __launch_bounds__(BX* BY) fi_bwd_direct_kernel(const FiArgs p) {
     stg_stream(g2, dx);
     stg_stream(g2 + p.gi2.c, dy);
 }
-
-// fast path (filter_interpolation_tma.cu); returns 1 if it took the call, 0 if not
-// applicable, -1 on error
-int fi_forward_fast(cudaStream_t stream, const FiArgs& a);
-int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool overwrite);
 
 static int fi_forward(cudaStream_t stream, const FiArgs& a, int flags) {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;

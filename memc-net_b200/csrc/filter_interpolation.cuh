@@ -1,0 +1,27 @@
+// filter_interpolation.cuh -- argument block shared by the generic and the TMA kernels.
+#pragma once
+#include "memc_common.cuh"
+
+namespace memc {
+
+struct FiArgs {
+    int B, C, H, W, fs;
+    View in1, flow, filt, out;  // `out` = output (fwd) or gradoutput (bwd)
+    View gi1, gi2, gi3;         // bwd only
+    const float* in1p;
+    const float* flowp;
+    const float* filtp;
+    float* outp;          // fwd
+    const float* goutp;   // bwd
+    float* gi1p;
+    float* gi2p;
+    float* gi3p;
+    int dbg;              // development switches (MEMC_TMA_DBG), 0 in production
+};
+
+// fast path (filter_interpolation_tma.cu): returns 1 if it took the call, 0 if its layout
+// preconditions do not hold (the caller then runs the generic kernels), -1 on error
+int fi_forward_fast(cudaStream_t stream, const FiArgs& a);
+int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool overwrite);
+
+}  // namespace memc

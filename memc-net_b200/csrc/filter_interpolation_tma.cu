@@ -1,8 +1,538 @@
-// filter_interpolation_tma.cu -- fs = 4 fast path of FilterInterpolation (placeholder:
-// reports "not applicable" so every call takes the generic kernels).
-#include "memc_common.cuh"
+// filter_interpolation_tma.cu -- fs = 4 fast path of FilterInterpolation for sm_100a.
+//
+// Same arithmetic as the generic kernels (filter_interpolation.cu; reference
+// my_lib_kernel.cu:1087-1518), different data movement.  The generic kernel is bound by
+// memory-level parallelism: every byte in flight is pinned to a register of a resident thread
+// (Little's law: ~64 KB must be in flight per SM to saturate HBM3e) and by L1 wavefronts (a
+// warp-wide gather of 32 neighbouring pixels straddles two 128-byte lines).  Here one elected
+// thread per CTA hands the tile to the TMA engine and the taps are served from shared memory:
+//
+//   tile   = TW x TH output pixels of one frame (warp-wide row segments of 32 pixels)
+//   TMA 1  flow   box (TW,TH,2)   -> smem  } issued first, no dependence on anything
+//   TMA 2  filter box (TW,TH,16)  -> smem  } (forward; backward reads the filter into registers)
+//   ...    threads read the flow, compute the integer target of every pixel and reduce the
+//          tile's bounding box of source windows (data dependent!)
+//   TMA 3  image  box (SW,SH,C) at that origin -> smem   (clamped taps stay inside the image;
+//          whatever the box misses is fetched with plain loads -- always correct)
+//   ...    filter taps and image taps come from shared memory (row pitch SW = k*32 words, so
+//          the bank of a tap depends on its column only); results leave through coalesced STG.
+//   backward additionally accumulates gradinput1 in a shared-memory box congruent with the
+//   image box and flushes it with ONE TMA reduce-add per tile (UTMAREDG, performed by the L2).
+//
+// Several CTAs share an SM so that one computes while the others' loads are in flight.
+// Layout preconditions (else the caller falls back to the generic kernel): fs == 4, C <= 4,
+// W % 4 == 0, 16-byte aligned bases and strides (TMA), H >= SH, W >= SW.
+//
+// Measured TMA constraint (B200, driver 580): the innermost tile coordinate must be a multiple
+// of 16 bytes (an unaligned c0 raises "illegal instruction"), hence the box origin x is rounded
+// down to a multiple of 4 pixels.
+#include "filter_interpolation.cuh"
+#include "tma_utils.cuh"
+#include <stdlib.h>
+
 namespace memc {
-struct FiArgs;
-int fi_forward_fast(cudaStream_t, const FiArgs&) { return 0; }
-int fi_backward_fast(cudaStream_t, const FiArgs&, bool) { return 0; }
+
+namespace {
+
+constexpr int CB = 4;  // max channels staged per box
+
+// TW x TH output tile, SW x SH image box, NT threads, MINB resident CTAs per SM (launch bound)
+template <int TW_, int TH_, int SW_, int SH_, int NT_, int MINB_>
+struct Cfg {
+    static constexpr int TW = TW_, TH = TH_, SW = SW_, SH = SH_, NT = NT_, MINB = MINB_;
+    static constexpr int SEGS = TW / 32;      // 32-pixel row segments per tile row
+    static constexpr int PPT = TW * TH / NT;  // pixels per thread
+    static_assert(TW % 32 == 0 && SW % 32 == 0 && (TW * TH) % NT == 0 && NT % 32 == 0, "bad tile config");
+};
+
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// shared-memory carve-up (byte offsets from a 128-byte aligned base)
+struct Layout {
+    int off_flow, off_a, off_bar, off_img, off_acc, total;
+};
+template <class K>
+__host__ __device__ constexpr Layout make_layout(int C, int planes_a, bool with_acc) {
+    Layout l{};
+    l.off_a = 0;  // filter (fwd) / gradoutput (bwd) tile
+    l.off_flow = planes_a * K::TH * K::TW * 4;
+    l.off_bar = l.off_flow + 2 * K::TH * K::TW * 4;
+    l.off_img = (l.off_bar + 64 + 127) & ~127;
+    l.off_acc = l.off_img + C * K::SH * K::SW * 4;
+    l.total = with_acc ? l.off_acc + C * K::SH * K::SW * 4 : l.off_acc;
+    return l;
+}
+
+// pixel k of this thread inside the tile: a warp always owns a 32-pixel row segment
+template <class K>
+__device__ __forceinline__ void tile_pixel(int k, int lane, int warp, int& xl, int& yl) {
+    const int seg = warp + k * (K::NT / 32);
+    yl = seg / K::SEGS;
+    xl = lane + 32 * (seg % K::SEGS);
+}
+
+// bounding box of the source windows over the tile's valid pixels -> box origin (bx, by)
+template <class K>
+__device__ __forceinline__ bool tile_box(const float* s_flow, int* s_bb, int x0, int y0, int W, int H, int lane,
+                                         int warp, int& bx, int& by) {
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < K::PPT; ++k) {
+        int xl, yl;
+        tile_pixel<K>(k, lane, warp, xl, yl);
+        const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * K::TW + xl], s_flow[(K::TH + yl) * K::TW + xl]);
+        if (g.valid && x0 + xl < W && y0 + yl < H) {
+            mnx = min(mnx, g.ix); mxx = max(mxx, g.ix);
+            mny = min(mny, g.iy); mxy = max(mxy, g.iy);
+        }
+    }
+    mnx = warp_min(mnx); mxx = warp_max(mxx); mny = warp_min(mny); mxy = warp_max(mxy);
+    if (lane == 0 && mnx <= mxx) {
+        atomicMin(&s_bb[0], mnx); atomicMax(&s_bb[1], mxx);
+        atomicMin(&s_bb[2], mny); atomicMax(&s_bb[3], mxy);
+    }
+    __syncthreads();
+    const bool any_valid = s_bb[0] <= s_bb[1];
+    // windows span [min ix - 1, max ix + 2]; taps are clamped into the image, so the origin is
+    // clamped too; a span wider than the box centres the box; x is rounded down to 4 (TMA)
+    bx = s_bb[0] - 1;
+    by = s_bb[2] - 1;
+    const int need_w = s_bb[1] - s_bb[0] + 4 + 3, need_h = s_bb[3] - s_bb[2] + 4;
+    if (need_w > K::SW) bx += (need_w - K::SW) / 2;
+    if (need_h > K::SH) by += (need_h - K::SH) / 2;
+    bx = max(0, min(bx, W - K::SW)) & ~3;  // W >= SW and W % 4 == 0 are launch preconditions
+    by = max(0, min(by, H - K::SH));       // H >= SH is a launch precondition
+    return any_valid;
+}
+
+// ====================================================================================
+// forward
+// ====================================================================================
+template <int C, class K>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                  const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);  // TMA: 128-byte boxes
+    constexpr Layout lay = make_layout<K>(C, 16, false);
+    const float* s_filt = reinterpret_cast<const float*>(sm + lay.off_a);     // [16][TH][TW]
+    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);  // [2][TH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 filter, 2 image
+    int* s_bb = reinterpret_cast<int*>(bars + 3);
+    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);    // [C][SH][SW]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H;
+
+    if (tid == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::mbar_init(&bars[2], 1);
+        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_a, &m_filt, x0, y0, 0, b, &bars[1]);
+    }
+
+    tma::mbar_wait(&bars[0], 0, 1);
+    int bx, by;
+    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
+    const bool skip_img = (p.dbg & 4) != 0;  // development switch: serve every tap from global
+    if (skip_img) { bx = -100000; by = -100000; }
+    if (tid == 0 && any_valid && !skip_img) {
+        tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
+        tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
+    }
+    tma::mbar_wait(&bars[1], 0, 2);
+    if (any_valid && !skip_img) tma::mbar_wait(&bars[2], 0, 3);
+
+    const float* in1b = p.in1p + b * p.in1.b;
+#pragma unroll
+    for (int k = 0; k < K::PPT; ++k) {
+        int xl, yl;
+        tile_pixel<K>(k, lane, warp, xl, yl);
+        const int x = x0 + xl, y = y0 + yl;
+        if (x >= W || y >= H) continue;
+        float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+        // geometry is recomputed from the staged flow (cheaper than keeping it live in registers)
+        const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+        if (!g.valid) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                stg_stream(outp + c * p.out.c, __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x));
+            continue;
+        }
+        const float a = g.alpha, bt = g.beta;
+        const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
+        const float wBL = (1.0f - a) * bt, wBR = a * bt;
+        const int L = g.ix - 1, T = g.iy - 1;
+        const int lx = L - bx, ly = T - by;
+        const float* wcol = s_filt + yl * TW + xl;  // plane stride TH*TW
+        const bool fast = (L >= 0) && (L + 3 <= W - 1) && (T >= 0) && (T + 3 <= H - 1) &&
+                          (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
+        if (fast) {
+            float wg[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) wg[t] = wcol[t * TH * TW];
+            const float* base = s_img + ly * SW + lx;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        q[(j >> 1) * 2 + (i >> 1)] =
+                            fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+                stg_stream(outp + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
+            }
+        } else {  // window touches the image border or leaves the staged box: rare, kept compact
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const float* img = in1b + c * p.in1.c;
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll 1
+                for (int t = 0; t < 16; ++t) {
+                    const int j = t >> 2, i = t & 3;
+                    const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
+                    const int ux = cx - bx, uy = cy - by;
+                    const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+                    const float v = in_box ? s_img[c * SH * SW + uy * SW + ux] : __ldg(img + (int64_t)cy * p.in1.h + cx);
+                    const float wt = wcol[t * TH * TW];  // same fmaf chain as the fast path / generic kernel
+                    q0 = (j < 2 && i < 2) ? fmaf(v, wt, q0) : q0;
+                    q1 = (j < 2 && i >= 2) ? fmaf(v, wt, q1) : q1;
+                    q2 = (j >= 2 && i < 2) ? fmaf(v, wt, q2) : q2;
+                    q3 = (j >= 2 && i >= 2) ? fmaf(v, wt, q3) : q3;
+                }
+                stg_stream(outp + c * p.out.c, wTL * q0 + wTR * q1 + wBL * q2 + wBR * q3);
+            }
+        }
+    }
+}
+
+// ====================================================================================
+// backward
+// ====================================================================================
+// TMA stages flow, gradoutput and the image box; the 16 filter planes of a pixel are read
+// straight into registers (coalesced streaming loads; the next pixel's loads are issued before
+// the current pixel is processed); gradinput3 / gradinput2 leave through coalesced streaming
+// stores.  gradinput1 -- the scatter -- is accumulated in a SHARED-MEMORY box congruent with the
+// image box and flushed once per tile with a TMA reduce-add, instead of 16*C global float
+// atomics per pixel (~1 L2 reduction sector per pixel instead of ~26, ncu in profiles/).
+template <int C, bool OVERWRITE, class K>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_gout,
+                  const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_gi1,
+                  const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, NT = K::NT, PPT = K::PPT;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    constexpr Layout lay = make_layout<K>(C, C, true);
+    const float* s_gout = reinterpret_cast<const float*>(sm + lay.off_a);     // [C][TH][TW]
+    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);  // [2][TH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 gout, 2 image
+    int* s_bb = reinterpret_cast<int*>(bars + 3);
+    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);
+    float* s_acc = reinterpret_cast<float*>(sm + lay.off_acc);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H;
+
+    if (tid == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::mbar_init(&bars[2], 1);
+        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], C * TH * TW * 4);
+        tma::load_4d(sm + lay.off_a, &m_gout, x0, y0, 0, b, &bars[1]);
+    }
+
+    // filter planes of my first pixel: issued now, consumed after the staging waits
+    const float* filt_b = p.filtp + b * p.filt.b;
+    float wnext[16];
+    {
+        int xl, yl;
+        tile_pixel<K>(0, lane, warp, xl, yl);
+        const float* fp = filt_b + (int64_t)min(y0 + yl, H - 1) * p.filt.h + min(x0 + xl, W - 1);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) wnext[t] = ldg_stream(fp + t * p.filt.c);
+    }
+    // zero the accumulation box while the loads fly
+    {
+        float4* a4 = reinterpret_cast<float4*>(s_acc);
+        for (int i = tid; i < C * SH * SW / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    tma::mbar_wait(&bars[0], 0, 11);
+    int bx, by;
+    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);  // syncs: box is zeroed
+    if (tid == 0 && any_valid) {
+        tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
+        tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
+    }
+    tma::mbar_wait(&bars[1], 0, 12);
+    if (any_valid) tma::mbar_wait(&bars[2], 0, 13);
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    float* g1b = p.gi1p + b * p.gi1.b;
+#pragma unroll 1
+    for (int k = 0; k < PPT; ++k) {
+        int xl, yl;
+        tile_pixel<K>(k, lane, warp, xl, yl);
+        const int x = x0 + xl, y = y0 + yl;
+        float wg[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) wg[t] = wnext[t];
+        if (k + 1 < PPT) {  // prefetch the next pixel's filter planes
+            int xn, yn;
+            tile_pixel<K>(k + 1, lane, warp, xn, yn);
+            const float* fp = filt_b + (int64_t)min(y0 + yn, H - 1) * p.filt.h + min(x0 + xn, W - 1);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) wnext[t] = ldg_stream(fp + t * p.filt.c);
+        }
+        if (x >= W || y >= H) continue;
+        float* g2 = p.gi2p + b * p.gi2.b + (int64_t)y * p.gi2.h + x;
+        float* g3 = p.gi3p + b * p.gi3.b + (int64_t)y * p.gi3.h + x;
+        const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+        if (!g.valid) {  // my_lib_kernel.cu:1256: an invalid pixel contributes nothing
+            if (OVERWRITE) {
+                stg_stream(g2, 0.f);
+                stg_stream(g2 + p.gi2.c, 0.f);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) stg_stream(g3 + t * p.gi3.c, 0.f);
+            }
+            continue;
+        }
+        const float a = g.alpha, bt = g.beta;
+        const float gam_y = 1.0f - bt, gam_x = 1.0f - a;  // the reference uses (1 - gamma), not beta
+        const int L = g.ix - 1, T = g.iy - 1;
+        const int lx = L - bx, ly = T - by;
+        const bool fast = (L >= 0) && (L + 3 <= W - 1) && (T >= 0) && (T + 3 <= H - 1) &&
+                          (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
+        float acc3[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc3[t] = 0.f;
+        float dx = 0.f, dy = 0.f;
+        if (fast) {
+            const int boff = ly * SW + lx;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float gov = s_gout[(c * TH + yl) * TW + xl];
+                const float gq[4] = {gov * (1.0f - a) * (1.0f - bt), gov * a * (1.0f - bt),
+                                     gov * (1.0f - a) * bt, gov * a * bt};
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int qi = (j >> 1) * 2 + (i >> 1), t = j * 4 + i;
+                        const int o = boff + c * SH * SW + j * SW + i;
+                        const float v = s_img[o];
+                        atomicAdd(&s_acc[o], gq[qi] * wg[t]);
+                        acc3[t] = fmaf(gq[qi], v, acc3[t]);
+                        q[qi] = fmaf(v, wg[t], q[qi]);
+                    }
+                dx = fmaf(gov, gam_y * (q[1] - q[0]) + (1.0f - gam_y) * (q[3] - q[2]), dx);
+                dy = fmaf(gov, gam_x * (q[2] - q[0]) + (1.0f - gam_x) * (q[3] - q[1]), dy);
+            }
+        } else {  // border / outside the staged box: per-tap clamping, global fallbacks
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const float* img = in1b + c * p.in1.c;
+                float* g1 = g1b + c * p.gi1.c;
+                const float gov = s_gout[(c * TH + yl) * TW + xl];
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int j = t >> 2, i = t & 3;
+                    const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
+                    const int ux = cx - bx, uy = cy - by;
+                    const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+                    const int o = c * SH * SW + uy * SW + ux;
+                    const float v = in_box ? s_img[o] : __ldg(img + (int64_t)cy * p.in1.h + cx);
+                    const float gq = gov * ((i >= 2) ? a : 1.0f - a) * ((j >= 2) ? bt : 1.0f - bt);
+                    if (in_box) atomicAdd(&s_acc[o], gq * wg[t]);
+                    else red_add(g1 + (int64_t)cy * p.gi1.h + cx, gq * wg[t]);
+                    acc3[t] = fmaf(gq, v, acc3[t]);
+                    q0 = (j < 2 && i < 2) ? fmaf(v, wg[t], q0) : q0;
+                    q1 = (j < 2 && i >= 2) ? fmaf(v, wg[t], q1) : q1;
+                    q2 = (j >= 2 && i < 2) ? fmaf(v, wg[t], q2) : q2;
+                    q3 = (j >= 2 && i >= 2) ? fmaf(v, wg[t], q3) : q3;
+                }
+                dx = fmaf(gov, gam_y * (q1 - q0) + (1.0f - gam_y) * (q3 - q2), dx);
+                dy = fmaf(gov, gam_x * (q2 - q0) + (1.0f - gam_x) * (q3 - q1), dy);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            if (OVERWRITE) stg_stream(g3 + t * p.gi3.c, acc3[t]);
+            else g3[t * p.gi3.c] += acc3[t];  // own pixel: no atomic needed
+        }
+        stg_stream(g2, dx);
+        stg_stream(g2 + p.gi2.c, dy);
+    }
+
+    // ---- flush the accumulation box: one TMA reduce-add per tile (clipped to the image by the TMA)
+    tma::fence_proxy_async();  // generic-proxy writes to s_acc -> visible to the async proxy
+    __syncthreads();
+    if (tid == 0 && any_valid) {
+        tma::reduce_add_4d(&m_gi1, bx, by, 0, b, s_acc);
+        tma::bulk_commit();
+        tma::bulk_wait_read_all();  // shared memory must stay alive until the TMA has read it
+    }
+}
+
+// ------------------------------------------------------------------------------- launch
+bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m) {
+    if (!tma::make_map_nchw(&m[0], a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, TH, 2,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return false;
+    if (!bwd) {
+        if (!tma::make_map_nchw(&m[1], a.filtp, a.B, 16, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, TW, TH, 16,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+            return false;
+    } else {
+        if (!tma::make_map_nchw(&m[1], a.goutp, a.B, a.C, a.H, a.W, a.out.b, a.out.c, a.out.h, TW, TH, a.C,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+            return false;
+        if (!tma::make_map_nchw(&m[3], a.gi1p, a.B, a.C, a.H, a.W, a.gi1.b, a.gi1.c, a.gi1.h, SW, SH, a.C,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE))
+            return false;
+    }
+    return tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, SW, SH, a.C,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+template <int C, class K>
+int launch_fwd(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[4];
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    static bool configured = false;  // per template instance
+    constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_fwd_tma_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        configured = true;
+    }
+    dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
+    fi_fwd_tma_kernel<C, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a);
+    count_launch();
+    return check_launch("FilterInterpolation forward (TMA)") == 0 ? 1 : -1;
+}
+
+template <int C, bool OW, class K>
+int launch_bwd(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[4];
+    if (!make_maps(a, true, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    static bool configured = false;
+    constexpr size_t smem = (size_t)make_layout<K>(C, C, true).total + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_bwd_tma_kernel<C, OW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        configured = true;
+    }
+    dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
+    fi_bwd_tma_kernel<C, OW, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], m[3], a);
+    count_launch();
+    return check_launch("FilterInterpolation backward (TMA)") == 0 ? 1 : -1;
+}
+
+// tile configurations.  *_DEFAULT is what production uses; the others are selectable with
+// MEMC_FI_FWD_CFG / MEMC_FI_BWD_CFG (C == 3 only) for tools/kbench.py sweeps.
+//                  TW  TH  SW  SH   NT  MINB
+using FwdA = Cfg<64, 16, 96, 32, 512, 2>;  // 110 KB: 2 CTAs / SM
+using FwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  61 KB: 3 CTAs / SM
+using FwdC = Cfg<32, 16, 64, 40, 256, 3>;  //  67 KB: 3 CTAs / SM
+using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
+using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
+using FWD_DEFAULT = FwdA;
+using BwdA = Cfg<64, 16, 96, 32, 256, 2>;  //  94 KB: 2 CTAs / SM
+using BwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  59 KB: 3 CTAs / SM
+using BwdC = Cfg<64, 8, 96, 24, 256, 3>;   //  65 KB: 3 CTAs / SM
+using BwdD = Cfg<32, 8, 64, 24, 128, 5>;   //  41 KB: 5 CTAs / SM
+using BWD_DEFAULT = BwdA;
+
+int env_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+}  // namespace
+
+int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
+    FiArgs a = a_in;
+    a.dbg = env_int("MEMC_TMA_DBG");
+    if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
+    if (a.C == 3) {
+        switch (env_int("MEMC_FI_FWD_CFG")) {
+            case 1: return launch_fwd<3, FwdA>(stream, a);
+            case 2: return launch_fwd<3, FwdB>(stream, a);
+            case 3: return launch_fwd<3, FwdC>(stream, a);
+            case 4: return launch_fwd<3, FwdD>(stream, a);
+            case 5: return launch_fwd<3, FwdE>(stream, a);
+            default: return launch_fwd<3, FWD_DEFAULT>(stream, a);
+        }
+    }
+    switch (a.C) {
+        case 1: return launch_fwd<1, FWD_DEFAULT>(stream, a);
+        case 2: return launch_fwd<2, FWD_DEFAULT>(stream, a);
+        case 4: return launch_fwd<4, FWD_DEFAULT>(stream, a);
+    }
+    return 0;
+}
+
+int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {
+    FiArgs a = a_in;
+    a.dbg = env_int("MEMC_TMA_DBG");
+    if (a.dbg & 8) return 0;  // development: generic backward
+    if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
+    if (a.C == 3 && ow) {
+        switch (env_int("MEMC_FI_BWD_CFG")) {
+            case 1: return launch_bwd<3, true, BwdA>(stream, a);
+            case 2: return launch_bwd<3, true, BwdB>(stream, a);
+            case 3: return launch_bwd<3, true, BwdC>(stream, a);
+            case 4: return launch_bwd<3, true, BwdD>(stream, a);
+            default: return launch_bwd<3, true, BWD_DEFAULT>(stream, a);
+        }
+    }
+    switch (a.C) {
+        case 1: return ow ? launch_bwd<1, true, BWD_DEFAULT>(stream, a) : launch_bwd<1, false, BWD_DEFAULT>(stream, a);
+        case 2: return ow ? launch_bwd<2, true, BWD_DEFAULT>(stream, a) : launch_bwd<2, false, BWD_DEFAULT>(stream, a);
+        case 3: return launch_bwd<3, false, BWD_DEFAULT>(stream, a);
+        case 4: return ow ? launch_bwd<4, true, BWD_DEFAULT>(stream, a) : launch_bwd<4, false, BWD_DEFAULT>(stream, a);
+    }
+    return 0;
+}
+
 }  // namespace memc

@@ -1,0 +1,133 @@
+// tma_utils.cuh -- thin inline-PTX wrappers around the sm_100a async-copy machinery used
+// by the fast paths: mbarrier, cp.async.bulk.tensor (TMA tile loads, SASS UTMALDG) and
+// cp.reduce.async.bulk.tensor (TMA reduce-add stores, SASS UTMAREDG), plus the host-side
+// tensor-map encoder obtained through cudaGetDriverEntryPoint (no link-time libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace memc {
+namespace tma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+// make freshly initialised barriers visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// order generic-proxy accesses to shared memory before subsequent async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a lost transaction becomes a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        if (spin > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0)
+                printf("memc_b200: mbarrier %d timed out in block (%d,%d,%d) thread %d\n", tag, blockIdx.x,
+                       blockIdx.y, blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// 4-D tile load global -> shared, completion signalled on `bar` (complete_tx::bytes)
+__device__ __forceinline__ void load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                        uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+// 4-D tile reduce-add shared -> global (element-wise atomic add performed by the L2), bulk-group completion
+__device__ __forceinline__ void reduce_add_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                              const void* smem_src) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group"
+        " [%0, {%1, %2, %3, %4}], [%5];" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+        : "memory");
+}
+// 4-D tile store shared -> global
+__device__ __forceinline__ void store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, const void* smem_src) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group"
+        " [%0, {%1, %2, %3, %4}], [%5];" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk groups have finished READING shared memory (safe to reuse / exit)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// fp32 NCHW tensor [B,C,H,W] with element strides (b,c,h,1) -> rank-4 tiled map, box (bw,bh,bc,1).
+// Returns false when the layout cannot be described (alignment / size limits).
+inline bool make_map_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int W, int64_t sb, int64_t sc,
+                          int64_t sh, int bw, int bh, int bc, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+    // a size-1 dimension's stride is irrelevant: substitute a legal one
+    if (H == 1) sh = W;
+    if (C == 1) sc = (int64_t)H * sh;
+    if (B == 1) sb = (int64_t)C * sc;
+    if (sh % 4 || sc % 4 || sb % 4) return false;  // strides must be multiples of 16 bytes
+    if (sh < W || sc <= 0 || sb <= 0) return false;
+    if (bw > 256 || bh > 256 || bc > 256 || (bw * 4) % 16) return false;
+    const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)sh * 4, (cuuint64_t)sc * 4, (cuuint64_t)sb * 4};
+    for (int i = 0; i < 3; ++i)
+        if (gstr[i] >= (1ull << 40)) return false;
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tma
+}  // namespace memc

@@ -53,6 +53,7 @@ FI_SHAPES = [  # B, C, H, W, fs, sigma
     (1, 3, 64, 64, 4, 3.0), (3, 3, 64, 64, 4, 3.0), (2, 3, 37, 53, 4, 8.0), (1, 5, 20, 31, 5, 2.0),
     (1, 2, 16, 16, 2, 1.0), (1, 3, 24, 24, 6, 40.0), (1, 64, 16, 24, 4, 2.0), (1, 1, 1, 1, 4, 0.0),
     (2, 3, 96, 128, 4, 4.0), (1, 3, 128, 256, 4, 20.0), (1, 64, 64, 128, 4, 3.0), (1, 3, 70, 260, 4, 1.0),
+    (2, 3, 37, 100, 4, 2.0), (1, 4, 50, 196, 4, 6.0), (1, 1, 33, 96, 4, 1.5), (1, 2, 130, 132, 4, 60.0),
 ]
 
 
@@ -143,6 +144,23 @@ def test_filter_interpolation_vs_reference_cuda_kernels(L, shape):
     close(g1, host(r1), what="gi1 vs reference CUDA")
     close(g2, host(r2), what="gi2 vs reference CUDA")
     close(g3, host(r3), what="gi3 vs reference CUDA")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0)])
+def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
+    """The TMA path stages data differently but performs the SAME fp32 operations in the same
+    order as the generic kernel, so the two must agree bit for bit (forward)."""
+    from memc_b200 import synth
+    B, C, H, W, sigma = shape
+    t1, t2, t3, _ = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=9, device="cuda")
+    outs = []
+    for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
+        o = torch.empty_like(t1)
+        L.call("memc_b200_filter_interpolation_forward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(o), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(o), flags)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_filter_interpolation_720p_vs_oracle(L):
