@@ -102,6 +102,11 @@ __device__ __forceinline__ bool tile_box(const float* s_flow, int* s_bb, int x0,
     }
     __syncthreads();
     const bool any_valid = s_bb[0] <= s_bb[1];
+    if (!any_valid) {  // nothing to stage: any legal origin will do
+        bx = 0;
+        by = 0;
+        return false;
+    }
     // windows span [min ix - 1, max ix + 2]; taps are clamped into the image, so the origin is
     // clamped too; a span wider than the box centres the box; x is rounded down to 4 (TMA)
     bx = s_bb[0] - 1;
@@ -117,51 +122,13 @@ __device__ __forceinline__ bool tile_box(const float* s_flow, int* s_bb, int x0,
 // ====================================================================================
 // forward
 // ====================================================================================
+// all pixels of one staged tile: shared by the one-tile-per-CTA and the persistent kernels
 template <int C, class K>
-__global__ void __launch_bounds__(K::NT, K::MINB)
-fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                  const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+__device__ __forceinline__ void fwd_compute_tile(const FiArgs& p, const float* s_filt, const float* s_flow,
+                                                 const float* s_img, int x0, int y0, int b, int bx, int by, int lane,
+                                                 int warp) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);  // TMA: 128-byte boxes
-    constexpr Layout lay = make_layout<K>(C, 16, false);
-    const float* s_filt = reinterpret_cast<const float*>(sm + lay.off_a);     // [16][TH][TW]
-    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);  // [2][TH][TW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 filter, 2 image
-    int* s_bb = reinterpret_cast<int*>(bars + 3);
-    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);    // [C][SH][SW]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
     const int W = p.W, H = p.H;
-
-    if (tid == 0) {
-        tma::mbar_init(&bars[0], 1);
-        tma::mbar_init(&bars[1], 1);
-        tma::mbar_init(&bars[2], 1);
-        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
-        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
-        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
-        tma::load_4d(sm + lay.off_a, &m_filt, x0, y0, 0, b, &bars[1]);
-    }
-
-    tma::mbar_wait(&bars[0], 0, 1);
-    int bx, by;
-    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
-    const bool skip_img = (p.dbg & 4) != 0;  // development switch: serve every tap from global
-    if (skip_img) { bx = -100000; by = -100000; }
-    if (tid == 0 && any_valid && !skip_img) {
-        tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
-        tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
-    }
-    tma::mbar_wait(&bars[1], 0, 2);
-    if (any_valid && !skip_img) tma::mbar_wait(&bars[2], 0, 3);
-
     const float* in1b = p.in1p + b * p.in1.b;
 #pragma unroll
     for (int k = 0; k < K::PPT; ++k) {
@@ -226,30 +193,20 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     }
 }
 
-// ====================================================================================
-// backward
-// ====================================================================================
-// TMA stages flow, gradoutput and the image box; the 16 filter planes of a pixel are read
-// straight into registers (coalesced streaming loads; the next pixel's loads are issued before
-// the current pixel is processed); gradinput3 / gradinput2 leave through coalesced streaming
-// stores.  gradinput1 -- the scatter -- is accumulated in a SHARED-MEMORY box congruent with the
-// image box and flushed once per tile with a TMA reduce-add, instead of 16*C global float
-// atomics per pixel (~1 L2 reduction sector per pixel instead of ~26, ncu in profiles/).
-template <int C, bool OVERWRITE, class K>
+
+template <int C, class K>
 __global__ void __launch_bounds__(K::NT, K::MINB)
-fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_gout,
-                  const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_gi1,
-                  const FiArgs p) {
-    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, NT = K::NT, PPT = K::PPT;
+fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                  const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    constexpr Layout lay = make_layout<K>(C, C, true);
-    const float* s_gout = reinterpret_cast<const float*>(sm + lay.off_a);     // [C][TH][TW]
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);  // TMA: 128-byte boxes
+    constexpr Layout lay = make_layout<K>(C, 16, false);
+    const float* s_filt = reinterpret_cast<const float*>(sm + lay.off_a);     // [16][TH][TW]
     const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);  // [2][TH][TW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 gout, 2 image
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 filter, 2 image
     int* s_bb = reinterpret_cast<int*>(bars + 3);
-    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);
-    float* s_acc = reinterpret_cast<float*>(sm + lay.off_acc);
+    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);    // [C][SH][SW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
@@ -266,53 +223,219 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     if (tid == 0) {
         tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
         tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
-        tma::mbar_expect_tx(&bars[1], C * TH * TW * 4);
-        tma::load_4d(sm + lay.off_a, &m_gout, x0, y0, 0, b, &bars[1]);
+        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_a, &m_filt, x0, y0, 0, b, &bars[1]);
     }
 
-    // filter planes of my first pixel: issued now, consumed after the staging waits
-    const float* filt_b = p.filtp + b * p.filt.b;
-    float wnext[16];
-    {
-        int xl, yl;
-        tile_pixel<K>(0, lane, warp, xl, yl);
-        const float* fp = filt_b + (int64_t)min(y0 + yl, H - 1) * p.filt.h + min(x0 + xl, W - 1);
-#pragma unroll
-        for (int t = 0; t < 16; ++t) wnext[t] = ldg_stream(fp + t * p.filt.c);
-    }
-    // zero the accumulation box while the loads fly
-    {
-        float4* a4 = reinterpret_cast<float4*>(s_acc);
-        for (int i = tid; i < C * SH * SW / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    tma::mbar_wait(&bars[0], 0, 11);
+    tma::mbar_wait(&bars[0], 0, 1);
     int bx, by;
-    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);  // syncs: box is zeroed
-    if (tid == 0 && any_valid) {
+    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
+    const bool skip_img = (p.dbg & 4) != 0;  // development switch: serve every tap from global
+    if (skip_img) { bx = -100000; by = -100000; }
+    if (tid == 0 && any_valid && !skip_img) {
         tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
         tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
     }
-    tma::mbar_wait(&bars[1], 0, 12);
-    if (any_valid) tma::mbar_wait(&bars[2], 0, 13);
+    tma::mbar_wait(&bars[1], 0, 2);
+    if (any_valid && !skip_img) tma::mbar_wait(&bars[2], 0, 3);
 
+    fwd_compute_tile<C, K>(p, s_filt, s_flow, s_img, x0, y0, b, bx, by, lane, warp);
+}
+
+bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m);  // m[5]
+
+// ------------------------------------------------------------------------------------
+// persistent forward: each CTA walks tiles blockIdx.x, blockIdx.x + grid, ... (raster order,
+// so concurrently running CTAs work on neighbouring tiles and share image rows in L2) with a
+// two-stage ring for (filter tile, image box) and a three-slot ring for the flow tile.  The
+// flow of tile i+2 and the filter/image of tile i+1 are in flight while tile i is computed:
+// the dependent chain flow -> bounding box -> image box is off the critical path.
+// ------------------------------------------------------------------------------------
+template <class K>
+__host__ __device__ constexpr int persist_smem(int C) {
+    return 2 * (16 * K::TH * K::TW * 4 + C * K::SH * K::SW * 4) + 3 * (2 * K::TH * K::TW * 4) + 256;
+}
+
+template <int C, class K>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_fwd_persist_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                      const __grid_constant__ CUtensorMap m_img, const FiArgs p, const int tiles_x,
+                      const int tiles_y, const int n_tiles) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    constexpr int FILT_B = 16 * TH * TW * 4, IMG_B = C * SH * SW * 4, FLOW_B = 2 * TH * TW * 4;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    unsigned char* const sm_filt0 = sm;                      // 2 stages, FILT_B apart
+    unsigned char* const sm_img0 = sm + 2 * FILT_B;          // 2 stages, IMG_B apart
+    unsigned char* const sm_flow = sm + 2 * FILT_B + 2 * IMG_B;  // 3 slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_flow + 3 * FLOW_B);  // [0,1] filter, [2,3] image, [4,5,6] flow
+    int* s_bb = reinterpret_cast<int*>(bars + 8);                        // 2 x 4 (double buffered)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+    if (n == 0) return;
+    const int W = p.W, H = p.H;
+    const int per_frame = tiles_x * tiles_y;
+
+    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
+        const int t = (int)blockIdx.x + i * G;
+        b = t / per_frame;
+        const int r = t - b * per_frame;
+        const int ty = r / tiles_x;
+        x0 = (r - ty * tiles_x) * TW;
+        y0 = ty * TH;
+    };
+    auto issue_flow = [&](int i) {  // thread 0 only
+        int x0, y0, b;
+        tile_origin(i, x0, y0, b);
+        uint64_t* bar = &bars[4 + i % 3];
+        tma::mbar_expect_tx(bar, FLOW_B);
+        tma::load_4d(sm_flow + (i % 3) * FLOW_B, &m_flow, x0, y0, 0, b, bar);
+    };
+    auto issue_stage = [&](int i, int bx, int by) {  // thread 0 only: filter tile + image box of tile i
+        int x0, y0, b;
+        tile_origin(i, x0, y0, b);
+        const int st = i & 1;
+        tma::mbar_expect_tx(&bars[st], FILT_B);
+        tma::load_4d(sm_filt0 + st * FILT_B, &m_filt, x0, y0, 0, b, &bars[st]);
+        tma::mbar_expect_tx(&bars[2 + st], IMG_B);
+        tma::load_4d(sm_img0 + st * IMG_B, &m_img, bx, by, 0, b, &bars[2 + st]);
+    };
+
+    if (tid == 0) {
+        for (int k = 0; k < 7; ++k) tma::mbar_init(&bars[k], 1);
+        for (int k = 0; k < 8; ++k) s_bb[k] = (k & 1) ? INT_MIN : INT_MAX;  // {min,max,min,max} x 2
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue_flow(0);
+        if (n > 1) issue_flow(1);
+    }
+    // box of tile 0
+    int bx_cur, by_cur;
+    {
+        int x0, y0, b;
+        tile_origin(0, x0, y0, b);
+        tma::mbar_wait(&bars[4], 0, 21);
+        tile_box<K>(reinterpret_cast<const float*>(sm_flow), s_bb, x0, y0, W, H, lane, warp, bx_cur, by_cur);
+        if (tid == 0) issue_stage(0, bx_cur, by_cur);
+    }
+
+    for (int i = 0; i < n; ++i) {
+        int bx_next = 0, by_next = 0;
+        if (i + 1 < n) {  // (A) look ahead: box of tile i+1, launch its loads, and the flow of tile i+2
+            int x0, y0, b;
+            tile_origin(i + 1, x0, y0, b);
+            tma::mbar_wait(&bars[4 + (i + 1) % 3], ((i + 1) / 3) & 1, 22);
+            tile_box<K>(reinterpret_cast<const float*>(sm_flow + ((i + 1) % 3) * FLOW_B), s_bb + 4 * ((i + 1) & 1), x0,
+                        y0, W, H, lane, warp, bx_next, by_next);
+            if (tid == 0) {
+                tma::fence_proxy_async();  // stage (i+1)&1 / flow slot (i+2)%3 were last READ by generic loads
+                issue_stage(i + 1, bx_next, by_next);
+                if (i + 2 < n) issue_flow(i + 2);
+            }
+        }
+        // (B) compute tile i
+        {
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            const int st = i & 1;
+            tma::mbar_wait(&bars[st], (i >> 1) & 1, 23);
+            tma::mbar_wait(&bars[2 + st], (i >> 1) & 1, 24);
+            fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm_filt0 + st * FILT_B),
+                                   reinterpret_cast<const float*>(sm_flow + (i % 3) * FLOW_B),
+                                   reinterpret_cast<const float*>(sm_img0 + st * IMG_B), x0, y0, b, bx_cur, by_cur,
+                                   lane, warp);
+        }
+        // (R) recycle the bounding-box scratch of tile i (used again by tile i+2), then close the iteration:
+        // after this barrier nobody reads stage i&1 or flow slot i%3 any more.
+        if (tid == 0) {
+            int* bb = s_bb + 4 * (i & 1);
+            bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;
+        }
+        __syncthreads();
+        bx_cur = bx_next;
+        by_cur = by_next;
+    }
+}
+
+template <int C, class K>
+int launch_fwd_persist(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[5];
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    static int configured = 0, n_sm = 0;
+    constexpr size_t smem = (size_t)persist_smem<K>(C) + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_fwd_persist_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        configured = 1;
+    }
+    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
+    if (n_tiles > 0x7fffffffLL) return 0;
+    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
+    fi_fwd_persist_kernel<C, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
+    count_launch();
+    return check_launch("FilterInterpolation forward (persistent TMA)") == 0 ? 1 : -1;
+}
+
+// ====================================================================================
+// backward
+// ====================================================================================
+// TMA stages flow, gradoutput, the 16 filter planes and the image box of a tile; gradinput3 /
+// gradinput2 leave through coalesced streaming stores.  gradinput1 -- the scatter -- is
+// accumulated in a SHARED-MEMORY box congruent with the image box and flushed once per tile with
+// a TMA reduce-add (~1 L2 reduction sector per pixel instead of ~26 with per-tap global atomics).
+//
+// Shared memory has no native fp32 atomic add on sm_100a (atomicAdd(float*) on shared compiles
+// to an ATOMS.CAST.SPIN compare-and-swap loop, measured ~25 cycles per tap); it does have a
+// native fire-and-forget int32 add (ATOMS.ADD).  The box is therefore accumulated in FIXED
+// POINT with a per-tile power-of-two scale:
+//     M     = max over the tile's valid pixels of  max_c|gradoutput_c| * max_t|filter_t|
+//             (every contribution is gq * w with |gq| <= |gradoutput_c|, so |contribution| <= M)
+//     Kb    = TW*TH: a box cell receives at most one (unclamped) tap per pixel of the tile;
+//             border-clamped taps, which could pile up on one cell, bypass the box (global red)
+//     scale = 2^e, the largest power of two with  M * Kb * 2^e < 2^31   (no overflow possible)
+// Each contribution is rounded to a multiple of 2^-e <= M * Kb * 2^-30: for a 32x8 tile that is
+// M * 2^-22, about the fp32 ulp of M, i.e. the absolute precision of adding into an fp32
+// accumulator of magnitude M -- and unlike float atomics the tile's sum is order-independent.
+// If M is not finite (NaN / Inf gradients) the tile falls back to the float CAS path so that
+// NaN/Inf propagate exactly as in the reference.
+template <class K>
+__host__ __device__ constexpr Layout make_bwd_layout(int C) {
+    Layout l{};
+    l.off_a = 16 * K::TH * K::TW * 4;                   // gradoutput tile (filter tile sits at 0)
+    l.off_flow = l.off_a + C * K::TH * K::TW * 4;
+    l.off_bar = l.off_flow + 2 * K::TH * K::TW * 4;
+    l.off_img = (l.off_bar + 64 + 127) & ~127;
+    l.off_acc = l.off_img + C * K::SH * K::SW * 4;
+    l.total = l.off_acc + C * K::SH * K::SW * 4;
+    return l;
+}
+
+template <int C, bool OVERWRITE, bool INT_ACC, class K>
+__device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s_filt, const float* s_gout,
+                                                 const float* s_flow, const float* s_img, float* s_acc, float scale,
+                                                 int x0, int y0, int b, int bx, int by, int lane, int warp) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    const int W = p.W, H = p.H;
     const float* in1b = p.in1p + b * p.in1.b;
     float* g1b = p.gi1p + b * p.gi1.b;
+    int* s_acci = reinterpret_cast<int*>(s_acc);
 #pragma unroll 1
-    for (int k = 0; k < PPT; ++k) {
+    for (int k = 0; k < K::PPT; ++k) {
         int xl, yl;
         tile_pixel<K>(k, lane, warp, xl, yl);
         const int x = x0 + xl, y = y0 + yl;
-        float wg[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) wg[t] = wnext[t];
-        if (k + 1 < PPT) {  // prefetch the next pixel's filter planes
-            int xn, yn;
-            tile_pixel<K>(k + 1, lane, warp, xn, yn);
-            const float* fp = filt_b + (int64_t)min(y0 + yn, H - 1) * p.filt.h + min(x0 + xn, W - 1);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) wnext[t] = ldg_stream(fp + t * p.filt.c);
-        }
         if (x >= W || y >= H) continue;
         float* g2 = p.gi2p + b * p.gi2.b + (int64_t)y * p.gi2.h + x;
         float* g3 = p.gi3p + b * p.gi3.b + (int64_t)y * p.gi3.h + x;
@@ -332,70 +455,196 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
         const int lx = L - bx, ly = T - by;
         const bool fast = (L >= 0) && (L + 3 <= W - 1) && (T >= 0) && (T + 3 <= H - 1) &&
                           (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
-        float acc3[16];
+        // Taps outer, channels inner: gradinput3[t] is complete after its channel loop and is
+        // stored at once (no 16-register accumulator array), the filter tap is read when needed.
+        float gov[C], gq[C][4], q[C][4];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc3[t] = 0.f;
-        float dx = 0.f, dy = 0.f;
+        for (int c = 0; c < C; ++c) {
+            gov[c] = s_gout[(c * TH + yl) * TW + xl];
+            gq[c][0] = gov[c] * (1.0f - a) * (1.0f - bt);
+            gq[c][1] = gov[c] * a * (1.0f - bt);
+            gq[c][2] = gov[c] * (1.0f - a) * bt;
+            gq[c][3] = gov[c] * a * bt;
+            q[c][0] = q[c][1] = q[c][2] = q[c][3] = 0.f;
+        }
+        const float* wcol = s_filt + yl * TW + xl;  // plane stride TH*TW
         if (fast) {
-            const int boff = ly * SW + lx;
+            // one window row per iteration, NOT unrolled across rows: keeps ~12 loads in flight
+            // instead of 64 and the kernel at <= 64 registers (more resident warps)
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const bool top = j < 2;
+                const int roff = (ly + j) * SW + lx;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float gov = s_gout[(c * TH + yl) * TW + xl];
-                const float gq[4] = {gov * (1.0f - a) * (1.0f - bt), gov * a * (1.0f - bt),
-                                     gov * (1.0f - a) * bt, gov * a * bt};
-                float q[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < 4; ++i) {
+                    const int h = i >> 1;
+                    const float w = wcol[(j * 4 + i) * TH * TW];
+                    float a3 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int qi = (j >> 1) * 2 + (i >> 1), t = j * 4 + i;
-                        const int o = boff + c * SH * SW + j * SW + i;
+                    for (int c = 0; c < C; ++c) {
+                        const int o = roff + c * SH * SW + i;
                         const float v = s_img[o];
-                        atomicAdd(&s_acc[o], gq[qi] * wg[t]);
-                        acc3[t] = fmaf(gq[qi], v, acc3[t]);
-                        q[qi] = fmaf(v, wg[t], q[qi]);
+                        const float gsel = top ? gq[c][h] : gq[c][2 + h];
+                        if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn(gsel * w * scale));
+                        else atomicAdd(&s_acc[o], gsel * w);
+                        a3 = fmaf(gsel, v, a3);
+                        const float nq = fmaf(v, w, top ? q[c][h] : q[c][2 + h]);
+                        q[c][h] = top ? nq : q[c][h];
+                        q[c][2 + h] = top ? q[c][2 + h] : nq;
                     }
-                dx = fmaf(gov, gam_y * (q[1] - q[0]) + (1.0f - gam_y) * (q[3] - q[2]), dx);
-                dy = fmaf(gov, gam_x * (q[2] - q[0]) + (1.0f - gam_x) * (q[3] - q[1]), dy);
+                    float* dst = g3 + (int64_t)(j * 4 + i) * p.gi3.c;
+                    if (OVERWRITE) stg_stream(dst, a3);
+                    else *dst += a3;  // own pixel: no atomic needed
+                }
             }
         } else {  // border / outside the staged box: per-tap clamping, global fallbacks
 #pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-                const float* img = in1b + c * p.in1.c;
-                float* g1 = g1b + c * p.gi1.c;
-                const float gov = s_gout[(c * TH + yl) * TW + xl];
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            for (int t = 0; t < 16; ++t) {
+                const int j = t >> 2, i = t & 3;
+                const bool top = j < 2;
+                const int h = i >> 1;
+                const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
+                const int ux = cx - bx, uy = cy - by;
+                const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+                // clamped taps pile up on border cells (up to 9 of one pixel on a corner): they go
+                // straight to global memory so that a box cell receives at most ONE tap per pixel
+                const bool to_box = in_box && cx == L + i && cy == T + j;
+                const float w = wcol[t * TH * TW];
+                float a3 = 0.f;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const int j = t >> 2, i = t & 3;
-                    const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
-                    const int ux = cx - bx, uy = cy - by;
-                    const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+                for (int c = 0; c < C; ++c) {
                     const int o = c * SH * SW + uy * SW + ux;
-                    const float v = in_box ? s_img[o] : __ldg(img + (int64_t)cy * p.in1.h + cx);
-                    const float gq = gov * ((i >= 2) ? a : 1.0f - a) * ((j >= 2) ? bt : 1.0f - bt);
-                    if (in_box) atomicAdd(&s_acc[o], gq * wg[t]);
-                    else red_add(g1 + (int64_t)cy * p.gi1.h + cx, gq * wg[t]);
-                    acc3[t] = fmaf(gq, v, acc3[t]);
-                    q0 = (j < 2 && i < 2) ? fmaf(v, wg[t], q0) : q0;
-                    q1 = (j < 2 && i >= 2) ? fmaf(v, wg[t], q1) : q1;
-                    q2 = (j >= 2 && i < 2) ? fmaf(v, wg[t], q2) : q2;
-                    q3 = (j >= 2 && i >= 2) ? fmaf(v, wg[t], q3) : q3;
+                    const float v = in_box ? s_img[o] : __ldg(in1b + c * p.in1.c + (int64_t)cy * p.in1.h + cx);
+                    const float gsel = (i >= 2) ? (top ? gq[c][1] : gq[c][3]) : (top ? gq[c][0] : gq[c][2]);
+                    if (to_box) {
+                        if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn(gsel * w * scale));
+                        else atomicAdd(&s_acc[o], gsel * w);
+                    } else {
+                        red_add(g1b + c * p.gi1.c + (int64_t)cy * p.gi1.h + cx, gsel * w);
+                    }
+                    a3 = fmaf(gsel, v, a3);
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const bool mine = (qq == (top ? 0 : 2) + h);
+                        q[c][qq] = mine ? fmaf(v, w, q[c][qq]) : q[c][qq];
+                    }
                 }
-                dx = fmaf(gov, gam_y * (q1 - q0) + (1.0f - gam_y) * (q3 - q2), dx);
-                dy = fmaf(gov, gam_x * (q2 - q0) + (1.0f - gam_x) * (q3 - q1), dy);
+                if (OVERWRITE) stg_stream(g3 + t * p.gi3.c, a3);
+                else g3[t * p.gi3.c] += a3;
             }
         }
+        float dx = 0.f, dy = 0.f;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            if (OVERWRITE) stg_stream(g3 + t * p.gi3.c, acc3[t]);
-            else g3[t * p.gi3.c] += acc3[t];  // own pixel: no atomic needed
+        for (int c = 0; c < C; ++c) {
+            dx = fmaf(gov[c], gam_y * (q[c][1] - q[c][0]) + (1.0f - gam_y) * (q[c][3] - q[c][2]), dx);
+            dy = fmaf(gov[c], gam_x * (q[c][2] - q[c][0]) + (1.0f - gam_x) * (q[c][3] - q[c][1]), dy);
         }
         stg_stream(g2, dx);
         stg_stream(g2 + p.gi2.c, dy);
     }
+}
+
+template <int C, bool OVERWRITE, class K>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_gout,
+                  const __grid_constant__ CUtensorMap m_filt, const __grid_constant__ CUtensorMap m_img,
+                  const __grid_constant__ CUtensorMap m_gi1, const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, NT = K::NT;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    constexpr Layout lay = make_bwd_layout<K>(C);
+    const float* s_filt = reinterpret_cast<const float*>(sm);                 // [16][TH][TW]
+    const float* s_gout = reinterpret_cast<const float*>(sm + lay.off_a);     // [C][TH][TW]
+    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);  // [2][TH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);           // 0 flow, 1 gout, 2 filter, 3 image
+    int* s_bb = reinterpret_cast<int*>(bars + 4);
+    unsigned* s_maxbits = reinterpret_cast<unsigned*>(s_bb + 4);
+    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);
+    float* s_acc = reinterpret_cast<float*>(sm + lay.off_acc);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H;
+
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) tma::mbar_init(&bars[k], 1);
+        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        *s_maxbits = 0u;
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], C * TH * TW * 4);
+        tma::load_4d(sm + lay.off_a, &m_gout, x0, y0, 0, b, &bars[1]);
+        tma::mbar_expect_tx(&bars[2], 16 * TH * TW * 4);
+        tma::load_4d(sm, &m_filt, x0, y0, 0, b, &bars[2]);
+    }
+    // zero the accumulation box while the loads fly (int 0 and float 0 share the bit pattern)
+    {
+        float4* a4 = reinterpret_cast<float4*>(s_acc);
+        for (int i = tid; i < C * SH * SW / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    tma::mbar_wait(&bars[0], 0, 11);
+    int bx, by;
+    const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);  // syncs: box is zeroed
+    if (tid == 0 && any_valid) {
+        tma::mbar_expect_tx(&bars[3], C * SH * SW * 4);
+        tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[3]);
+    }
+    tma::mbar_wait(&bars[1], 0, 12);
+    tma::mbar_wait(&bars[2], 0, 13);
+
+    // ---- per-tile fixed-point scale
+    float mloc = 0.f;
+#pragma unroll
+    for (int k = 0; k < K::PPT; ++k) {
+        int xl, yl;
+        tile_pixel<K>(k, lane, warp, xl, yl);
+        const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+        if (g.valid && x0 + xl < W && y0 + yl < H) {
+            float mg = 0.f, mw = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mg = fmaxf_nan(mg, fabsf(s_gout[(c * TH + yl) * TW + xl]));
+#pragma unroll
+            for (int t = 0; t < 16; ++t) mw = fmaxf_nan(mw, fabsf(s_filt[(t * TH + yl) * TW + xl]));
+            mloc = fmaxf_nan(mloc, mg * mw);
+        }
+    }
+    {   // non-negative floats (and NaN, which sorts above +Inf) order like their bit patterns
+        unsigned mb = __float_as_uint(mloc);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        if (lane == 0 && mb) atomicMax(s_maxbits, mb);
+    }
+    __syncthreads();
+    const float M = __uint_as_float(*s_maxbits);
+    const bool finite = *s_maxbits < 0x7f800000u;
+    float scale = 0.f, inv_scale = 0.f;
+    if (finite && M > 0.f) {
+        int ex;
+        frexpf(M, &ex);  // M < 2^ex
+        constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;  // ceil(log2(TW*TH))
+        int e = 31 - ex - LOG2_PX;
+        e = max(-120, min(e, 120));
+        scale = ldexpf(1.0f, e);
+        inv_scale = ldexpf(1.0f, -e);
+    }
+    if (any_valid) tma::mbar_wait(&bars[3], 0, 14);
+
+    if (scale > 0.f)
+        bwd_compute_tile<C, OVERWRITE, true, K>(p, s_filt, s_gout, s_flow, s_img, s_acc, scale, x0, y0, b, bx, by, lane, warp);
+    else
+        bwd_compute_tile<C, OVERWRITE, false, K>(p, s_filt, s_gout, s_flow, s_img, s_acc, 1.0f, x0, y0, b, bx, by, lane, warp);
 
     // ---- flush the accumulation box: one TMA reduce-add per tile (clipped to the image by the TMA)
+    __syncthreads();
+    if (scale > 0.f) {  // fixed point -> fp32 in place
+        int* ai = reinterpret_cast<int*>(s_acc);
+        for (int i = tid; i < C * SH * SW; i += NT) s_acc[i] = (float)ai[i] * inv_scale;
+    }
     tma::fence_proxy_async();  // generic-proxy writes to s_acc -> visible to the async proxy
     __syncthreads();
     if (tid == 0 && any_valid) {
@@ -421,6 +670,9 @@ bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtens
         if (!tma::make_map_nchw(&m[3], a.gi1p, a.B, a.C, a.H, a.W, a.gi1.b, a.gi1.c, a.gi1.h, SW, SH, a.C,
                                 CU_TENSOR_MAP_L2_PROMOTION_NONE))
             return false;
+        if (!tma::make_map_nchw(&m[4], a.filtp, a.B, 16, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, TW, TH, 16,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+            return false;
     }
     return tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, SW, SH, a.C,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -429,7 +681,7 @@ bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtens
 template <int C, class K>
 int launch_fwd(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[4];
+    CUtensorMap m[5];
     if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
     static bool configured = false;  // per template instance
     constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
@@ -450,10 +702,10 @@ int launch_fwd(cudaStream_t stream, const FiArgs& a) {
 template <int C, bool OW, class K>
 int launch_bwd(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[4];
+    CUtensorMap m[5];
     if (!make_maps(a, true, K::TW, K::TH, K::SW, K::SH, m)) return 0;
     static bool configured = false;
-    constexpr size_t smem = (size_t)make_layout<K>(C, C, true).total + 128;
+    constexpr size_t smem = (size_t)make_bwd_layout<K>(C).total + 128;
     if (!configured) {
         if (cudaFuncSetAttribute(fi_bwd_tma_kernel<C, OW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess) {
@@ -463,7 +715,7 @@ int launch_bwd(cudaStream_t stream, const FiArgs& a) {
         configured = true;
     }
     dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
-    fi_bwd_tma_kernel<C, OW, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], m[3], a);
+    fi_bwd_tma_kernel<C, OW, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[4], m[2], m[3], a);
     count_launch();
     return check_launch("FilterInterpolation backward (TMA)") == 0 ? 1 : -1;
 }
@@ -476,11 +728,17 @@ using FwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  61 KB: 3 CTAs / SM
 using FwdC = Cfg<32, 16, 64, 40, 256, 3>;  //  67 KB: 3 CTAs / SM
 using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
 using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
+using FwdF = Cfg<32, 8, 64, 24, 256, 5>;   //  37 KB: 5 CTAs / SM, 1 px / thread (<= 51 registers)
+using FwdG = Cfg<32, 16, 64, 32, 512, 3>;  //  61 KB: 3 CTAs / SM, 1 px / thread (<= 42 registers)
+using FwdP1 = Cfg<32, 16, 64, 40, 256, 1>;  // persistent, 137 KB: 1 CTA / SM
+using FwdP2 = Cfg<32, 8, 64, 22, 128, 3>;   // persistent,  73 KB: 3 CTAs / SM
+using FwdP3 = Cfg<64, 16, 96, 28, 512, 1>;  // persistent, 215 KB: 1 CTA / SM
+using FwdP4 = Cfg<32, 16, 64, 32, 256, 1>;  // persistent, 125 KB: 1 CTA / SM
 using FWD_DEFAULT = FwdA;
-using BwdA = Cfg<64, 16, 96, 32, 256, 2>;  //  94 KB: 2 CTAs / SM
-using BwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  59 KB: 3 CTAs / SM
-using BwdC = Cfg<64, 8, 96, 24, 256, 3>;   //  65 KB: 3 CTAs / SM
-using BwdD = Cfg<32, 8, 64, 24, 128, 5>;   //  41 KB: 5 CTAs / SM
+using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
+using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
+using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
+using BwdD = Cfg<32, 16, 64, 32, 512, 2>;  //  91 KB: 2 CTAs / SM, 1 px / thread
 using BWD_DEFAULT = BwdA;
 
 int env_int(const char* name) {
@@ -501,6 +759,12 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 3: return launch_fwd<3, FwdC>(stream, a);
             case 4: return launch_fwd<3, FwdD>(stream, a);
             case 5: return launch_fwd<3, FwdE>(stream, a);
+            case 6: return launch_fwd_persist<3, FwdP1>(stream, a);
+            case 7: return launch_fwd_persist<3, FwdP2>(stream, a);
+            case 8: return launch_fwd_persist<3, FwdP3>(stream, a);
+            case 9: return launch_fwd_persist<3, FwdP4>(stream, a);
+            case 10: return launch_fwd<3, FwdF>(stream, a);
+            case 11: return launch_fwd<3, FwdG>(stream, a);
             default: return launch_fwd<3, FWD_DEFAULT>(stream, a);
         }
     }

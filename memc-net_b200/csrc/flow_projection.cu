@@ -4,20 +4,10 @@
 // Semantics: reference my_package/src/my_lib_kernel.cu:1630-1694 (scatter), :1696-1739
 // (average), :1742-1836 (fill-hole), :1837-1901 (backward), sequenced as in the launcher
 // :1905-1992.  CPU twin my_lib.c:1447-1634 (no fill-hole there).
-#include "memc_common.cuh"
+#include "flow_projection.cuh"
 
 namespace memc {
 
-struct FpArgs {
-    int B, H, W, fillhole;
-    View flow, count, out;  // out = output (fwd) / gradoutput (bwd)
-    View gi;                // bwd
-    const float* flowp;
-    float* countp;          // fwd: written; bwd: read
-    float* outp;
-    const float* goutp;
-    float* gip;
-};
 
 constexpr int BX = 32, BY = 8;
 
@@ -135,14 +125,31 @@ __global__ void __launch_bounds__(BX* BY) fp_bwd_kernel(const FpArgs p) {
     *gy = sy;
 }
 
-// fast path (flow_projection_fast.cu); 1 = handled, 0 = not applicable, -1 = error
-int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite);
+// average (+ fill-hole) over frames [b0, b0 + nb) of `a` -- also used by the fast path
+int fp_average_fill(cudaStream_t stream, const FpArgs& a, int b0, int nb, bool do_average) {
+    FpArgs f = a;
+    f.flowp = a.flowp + b0 * a.flow.b;
+    f.countp = a.countp + b0 * a.count.b;
+    f.outp = a.outp + b0 * a.out.b;
+    dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, nb);
+    if (do_average) {
+        fp_average_kernel<<<grid, block, 0, stream>>>(f);
+        count_launch();
+        if (check_launch("FlowProjection average")) return -1;
+    }
+    if (a.fillhole) {
+        fp_fillhole_kernel<<<grid, block, 0, stream>>>(f);
+        count_launch();
+        if (check_launch("FlowProjection fill-hole")) return -1;
+    }
+    return 0;
+}
 
 static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return 0;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     if (!(flags & MEMC_B200_NO_FAST)) {
-        const int r = fp_forward_fast(stream, a, ow);
+        const int r = fp_forward_fast(stream, a, ow, (flags & MEMC_B200_NO_ZERO) != 0);
         if (r != 0) return r < 0 ? -1 : 0;
     }
     if (ow && !(flags & MEMC_B200_NO_ZERO)) {

@@ -1,0 +1,24 @@
+// flow_projection.cuh -- argument block shared by the generic and the fast FlowProjection paths.
+#pragma once
+#include "memc_common.cuh"
+
+namespace memc {
+
+struct FpArgs {
+    int B, H, W, fillhole;
+    View flow, count, out;  // out = output (fwd) / gradoutput (bwd)
+    View gi;                // bwd
+    const float* flowp;
+    float* countp;          // fwd: written; bwd: read
+    float* outp;
+    const float* goutp;
+    float* gip;
+};
+
+// fast path (flow_projection_fast.cu): 1 = handled, 0 = layout preconditions not met (caller
+// runs the generic kernels), -1 = error
+int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero);
+// average (+ fill-hole) over frames [b0, b0 + nb) with the generic kernels (flow_projection.cu)
+int fp_average_fill(cudaStream_t stream, const FpArgs& a, int b0, int nb, bool do_average);
+
+}  // namespace memc

@@ -71,6 +71,8 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) { __stcs(reinter
 __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// max that PROPAGATES NaN (fmaxf drops it): used to detect non-finite tiles
+__device__ __forceinline__ float fmaxf_nan(float a, float b) { return (a != a || b != b) ? a + b : fmaxf(a, b); }
 
 // Geometry of the adaptive warp at one output pixel; decisions in fp32 exactly as the
 // reference (my_lib_kernel.cu:1126-1138): truncation, validity incl. |flow| < extent/2.

@@ -30,21 +30,25 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait may suspend the thread in hardware for up to this many ns before reporting "not
+// yet": waiting warps then stop competing for issue slots with the warps that compute
+// (without the hint ~40 % of the executed instructions of the first version were wait spins).
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a lost transaction becomes a trap (launch error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 22)) {
+        if (spin > (1u << 20)) {
             if ((threadIdx.x & 31) == 0)
                 printf("memc_b200: mbarrier %d timed out in block (%d,%d,%d) thread %d\n", tag, blockIdx.x,
                        blockIdx.y, blockIdx.z, threadIdx.x);

@@ -163,6 +163,31 @@ def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
     assert torch.equal(outs[0], outs[1])
 
 
+def test_filter_interpolation_backward_propagates_nonfinite_gradients(L):
+    """The fast backward accumulates gradinput1 in per-tile fixed point; a tile whose gradients
+    are not finite must fall back to float accumulation so NaN/Inf land where the reference
+    puts them (same NaN mask as the generic kernel, which mirrors the reference arithmetic)."""
+    from memc_b200 import synth
+    B, C, H, W = 1, 3, 96, 160
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, sigma=2.0, seed=11, device="cuda")
+    tg[0, 1, 40, 70] = float("nan")
+    tg[0, 0, 10, 20] = float("inf")
+    res = []
+    for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
+        g1, g2, g3 = torch.empty_like(t1), torch.empty_like(t2), torch.empty_like(t3)
+        L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(tg), L.strides_of(g1), L.strides_of(g2),
+               L.strides_of(g3), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(tg), L.ptr(g1), L.ptr(g2), L.ptr(g3), flags)
+        res.append((g1, g2, g3))
+    torch.cuda.synchronize()
+    for fast, gen in zip(*res):
+        assert torch.equal(torch.isnan(fast), torch.isnan(gen))
+        assert torch.equal(torch.isinf(fast), torch.isinf(gen))
+        ok = torch.isfinite(gen)
+        assert float((fast[ok] - gen[ok]).abs().max()) <= 1e-5
+    assert bool(torch.isnan(res[0][0]).any()) and bool(torch.isinf(res[0][0]).any())
+
+
 def test_filter_interpolation_720p_vs_oracle(L):
     """One full 1280x720 frame (BASELINE.json configs[1] geometry) against the f64 oracle."""
     from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
