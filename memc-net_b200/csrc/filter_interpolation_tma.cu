@@ -119,6 +119,12 @@ __device__ __forceinline__ bool tile_box(const float* s_flow, int* s_bb, int x0,
     return any_valid;
 }
 
+// development-only phase timestamps (thread 0 of the first 256 CTAs, first 8 tiles each)
+__device__ __forceinline__ void prof_mark(const FiArgs& p, int tile_i, int k) {
+    if (p.prof && threadIdx.x == 0 && blockIdx.x < 256 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0 && tile_i < 8)
+        p.prof[((long long)blockIdx.x * 8 + tile_i) * 6 + k] = clock64();
+}
+
 // ====================================================================================
 // forward
 // ====================================================================================
@@ -220,6 +226,7 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
         tma::fence_barrier_init();
     }
     __syncthreads();
+    prof_mark(p, 0, 0);
     if (tid == 0) {
         tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
         tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
@@ -228,8 +235,10 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     }
 
     tma::mbar_wait(&bars[0], 0, 1);
+    prof_mark(p, 0, 1);
     int bx, by;
     const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
+    prof_mark(p, 0, 2);
     const bool skip_img = (p.dbg & 4) != 0;  // development switch: serve every tap from global
     if (skip_img) { bx = -100000; by = -100000; }
     if (tid == 0 && any_valid && !skip_img) {
@@ -238,8 +247,10 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     }
     tma::mbar_wait(&bars[1], 0, 2);
     if (any_valid && !skip_img) tma::mbar_wait(&bars[2], 0, 3);
+    prof_mark(p, 0, 3);
 
     fwd_compute_tile<C, K>(p, s_filt, s_flow, s_img, x0, y0, b, bx, by, lane, warp);
+    prof_mark(p, 0, 4);
 }
 
 bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m);  // m[5]
@@ -386,6 +397,137 @@ int launch_fwd_persist(cudaStream_t stream, const FiArgs& a) {
     fi_fwd_persist_kernel<C, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
     count_launch();
     return check_launch("FilterInterpolation forward (persistent TMA)") == 0 ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------
+// persistent-lite forward: like the one-tile-per-CTA kernel (same smem budget, so the same
+// number of CTAs per SM), but every CTA walks tiles blockIdx.x, +grid, ... and PREFETCHES the
+// small flow tile (optionally also the filter tile) of its next tile while it computes the
+// current one.  The dependent chain per tile shrinks from
+//     launch -> flow (HBM latency) -> bounding box -> image box (L2/HBM latency) -> compute
+// to  bounding box -> image box -> compute.
+// ------------------------------------------------------------------------------------
+template <class K>
+__host__ __device__ constexpr int pl_smem(int C, bool pf) {
+    return (pf ? 2 : 1) * 16 * K::TH * K::TW * 4 + 2 * (2 * K::TH * K::TW * 4) + C * K::SH * K::SW * 4 + 256;
+}
+
+template <int C, class K, bool PF>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_fwd_pl_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                 const __grid_constant__ CUtensorMap m_img, const FiArgs p, const int tiles_x, const int tiles_y,
+                 const int n_tiles) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    constexpr int FILT_B = 16 * TH * TW * 4, IMG_B = C * SH * SW * 4, FLOW_B = 2 * TH * TW * 4;
+    constexpr int NF = PF ? 2 : 1;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    unsigned char* const sm_filt = sm;                               // NF slots
+    unsigned char* const sm_flow = sm + NF * FILT_B;                 // 2 slots
+    unsigned char* const sm_img = sm_flow + 2 * FLOW_B;              // 1 slot
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_img + IMG_B);    // [0,1] flow, [2,3] filter, [4] image
+    int* s_bb = reinterpret_cast<int*>(bars + 6);                    // 2 x 4
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+    if (n == 0) return;
+    const int W = p.W, H = p.H;
+    const int per_frame = tiles_x * tiles_y;
+    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
+        const int t = (int)blockIdx.x + i * G;
+        b = t / per_frame;
+        const int r = t - b * per_frame;
+        const int ty = r / tiles_x;
+        x0 = (r - ty * tiles_x) * TW;
+        y0 = ty * TH;
+    };
+    auto issue_flow = [&](int i) {  // thread 0
+        int x0, y0, b;
+        tile_origin(i, x0, y0, b);
+        tma::mbar_expect_tx(&bars[i & 1], FLOW_B);
+        tma::load_4d(sm_flow + (i & 1) * FLOW_B, &m_flow, x0, y0, 0, b, &bars[i & 1]);
+    };
+    auto issue_filt = [&](int i) {  // thread 0
+        int x0, y0, b;
+        tile_origin(i, x0, y0, b);
+        const int sl = PF ? (i & 1) : 0;
+        tma::mbar_expect_tx(&bars[2 + sl], FILT_B);
+        tma::load_4d(sm_filt + sl * FILT_B, &m_filt, x0, y0, 0, b, &bars[2 + sl]);
+    };
+
+    if (tid == 0) {
+        for (int k = 0; k < 5; ++k) tma::mbar_init(&bars[k], 1);
+        for (int k = 0; k < 8; ++k) s_bb[k] = (k & 1) ? INT_MIN : INT_MAX;
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue_flow(0);
+        if (PF) issue_filt(0);
+    }
+    for (int i = 0; i < n; ++i) {
+        int x0, y0, b;
+        tile_origin(i, x0, y0, b);
+        if (tid == 0) {
+            tma::fence_proxy_async();  // the slots refilled below were last read by generic loads
+            if (i + 1 < n) {
+                issue_flow(i + 1);
+                if (PF) issue_filt(i + 1);
+            }
+            if (!PF) issue_filt(i);
+        }
+        prof_mark(p, i, 0);
+        tma::mbar_wait(&bars[i & 1], (i >> 1) & 1, 41);
+        prof_mark(p, i, 1);
+        const float* s_flow = reinterpret_cast<const float*>(sm_flow + (i & 1) * FLOW_B);
+        int bx, by;
+        tile_box<K>(s_flow, s_bb + 4 * (i & 1), x0, y0, W, H, lane, warp, bx, by);
+        prof_mark(p, i, 2);
+        if (tid == 0) {
+            tma::mbar_expect_tx(&bars[4], IMG_B);
+            tma::load_4d(sm_img, &m_img, bx, by, 0, b, &bars[4]);
+        }
+        const int fsl = PF ? (i & 1) : 0;
+        tma::mbar_wait(&bars[2 + fsl], PF ? ((i >> 1) & 1) : (i & 1), 42);
+        tma::mbar_wait(&bars[4], i & 1, 43);
+        prof_mark(p, i, 3);
+        fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm_filt + fsl * FILT_B), s_flow,
+                               reinterpret_cast<const float*>(sm_img), x0, y0, b, bx, by, lane, warp);
+        prof_mark(p, i, 4);
+        if (tid == 0) {
+            int* bb = s_bb + 4 * (i & 1);
+            bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;
+        }
+        __syncthreads();
+    }
+}
+
+template <int C, class K, bool PF>
+int launch_fwd_pl(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[5];
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    static int configured = 0, n_sm = 0;
+    constexpr size_t smem = (size_t)pl_smem<K>(C, PF) + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_fwd_pl_kernel<C, K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        configured = 1;
+    }
+    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
+    if (n_tiles > 0x7fffffffLL) return 0;
+    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
+    fi_fwd_pl_kernel<C, K, PF><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
+    count_launch();
+    return check_launch("FilterInterpolation forward (persistent-lite TMA)") == 0 ? 1 : -1;
 }
 
 // ====================================================================================
@@ -730,11 +872,15 @@ using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
 using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
 using FwdF = Cfg<32, 8, 64, 24, 256, 5>;   //  37 KB: 5 CTAs / SM, 1 px / thread (<= 51 registers)
 using FwdG = Cfg<32, 16, 64, 32, 512, 3>;  //  61 KB: 3 CTAs / SM, 1 px / thread (<= 42 registers)
+using FwdL1 = Cfg<32, 8, 64, 24, 128, 5>;   // persistent-lite,  39 KB: 5 CTAs / SM
+using FwdL2 = Cfg<32, 8, 64, 24, 128, 4>;   // persistent-lite + filter prefetch, 55 KB: 4 CTAs / SM
+using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs / SM
+using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
 using FwdP1 = Cfg<32, 16, 64, 40, 256, 1>;  // persistent, 137 KB: 1 CTA / SM
 using FwdP2 = Cfg<32, 8, 64, 22, 128, 3>;   // persistent,  73 KB: 3 CTAs / SM
 using FwdP3 = Cfg<64, 16, 96, 28, 512, 1>;  // persistent, 215 KB: 1 CTA / SM
 using FwdP4 = Cfg<32, 16, 64, 32, 256, 1>;  // persistent, 125 KB: 1 CTA / SM
-using FWD_DEFAULT = FwdA;
+using FWD_DEFAULT = FwdE;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
 using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
 using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
@@ -748,25 +894,62 @@ int env_int(const char* name) {
 
 }  // namespace
 
+// development: phase timeline of the forward kernels (MEMC_TMA_DBG & 64); prints cycle averages
+static void prof_report(cudaStream_t stream, long long* dev) {
+    cudaStreamSynchronize(stream);
+    static long long host[256 * 8 * 6];
+    cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
+    const char* names[5] = {"start->flow landed", "bbox", "->filter+image landed", "compute", "(next tile start)"};
+    for (int t = 0; t < 8; ++t) {
+        double sum[5] = {0, 0, 0, 0, 0};
+        int n = 0;
+        for (int c = 0; c < 256; ++c) {
+            const long long* e = host + (c * 8 + t) * 6;
+            if (!e[0] || !e[4]) continue;
+            for (int k = 0; k < 4; ++k) sum[k] += (double)(e[k + 1] - e[k]);
+            if (t + 1 < 8 && e[6]) sum[4] += (double)(e[6] - e[4]);
+            ++n;
+        }
+        if (!n) continue;
+        fprintf(stderr, "memc_b200 prof tile#%d (n=%d):", t, n);
+        for (int k = 0; k < 5; ++k) fprintf(stderr, "  %s %.0f cyc", names[k], sum[k] / n);
+        fprintf(stderr, "\n");
+    }
+}
+
 int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
     FiArgs a = a_in;
     a.dbg = env_int("MEMC_TMA_DBG");
+    if (a.dbg & 64) {
+        static long long* dev = nullptr;
+        if (!dev) cudaMalloc(reinterpret_cast<void**>(&dev), 256 * 8 * 6 * sizeof(long long));
+        cudaMemsetAsync(dev, 0, 256 * 8 * 6 * sizeof(long long), stream);
+        a.prof = dev;
+    }
     if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
     if (a.C == 3) {
+        int r = 0;
         switch (env_int("MEMC_FI_FWD_CFG")) {
-            case 1: return launch_fwd<3, FwdA>(stream, a);
-            case 2: return launch_fwd<3, FwdB>(stream, a);
-            case 3: return launch_fwd<3, FwdC>(stream, a);
-            case 4: return launch_fwd<3, FwdD>(stream, a);
-            case 5: return launch_fwd<3, FwdE>(stream, a);
-            case 6: return launch_fwd_persist<3, FwdP1>(stream, a);
-            case 7: return launch_fwd_persist<3, FwdP2>(stream, a);
-            case 8: return launch_fwd_persist<3, FwdP3>(stream, a);
-            case 9: return launch_fwd_persist<3, FwdP4>(stream, a);
-            case 10: return launch_fwd<3, FwdF>(stream, a);
-            case 11: return launch_fwd<3, FwdG>(stream, a);
-            default: return launch_fwd<3, FWD_DEFAULT>(stream, a);
+            case 1: r = launch_fwd<3, FwdA>(stream, a); break;
+            case 2: r = launch_fwd<3, FwdB>(stream, a); break;
+            case 3: r = launch_fwd<3, FwdC>(stream, a); break;
+            case 4: r = launch_fwd<3, FwdD>(stream, a); break;
+            case 5: r = launch_fwd<3, FwdE>(stream, a); break;
+            case 6: r = launch_fwd_persist<3, FwdP1>(stream, a); break;
+            case 7: r = launch_fwd_persist<3, FwdP2>(stream, a); break;
+            case 8: r = launch_fwd_persist<3, FwdP3>(stream, a); break;
+            case 9: r = launch_fwd_persist<3, FwdP4>(stream, a); break;
+            case 10: r = launch_fwd<3, FwdF>(stream, a); break;
+            case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
+            case 13: r = launch_fwd_pl<3, FwdL2, true>(stream, a); break;
+            case 14: r = launch_fwd_pl<3, FwdL3, false>(stream, a); break;
+            case 15: r = launch_fwd_pl<3, FwdL4, false>(stream, a); break;
+            case 16: r = launch_fwd_pl<3, FwdL3, true>(stream, a); break;
+            case 11: r = launch_fwd<3, FwdG>(stream, a); break;
+            default: r = launch_fwd<3, FWD_DEFAULT>(stream, a); break;
         }
+        if (a.prof && r == 1) prof_report(stream, a.prof);
+        return r;
     }
     switch (a.C) {
         case 1: return launch_fwd<1, FWD_DEFAULT>(stream, a);

@@ -12,8 +12,8 @@
 //         -fx / -fy are accumulated in fixed point with a per-tile power-of-two scale
 //         2^e, M * (TW*TH) * 2^e < 2^31 (a cell receives at most one unclamped hit per pixel;
 //         border-clamped duplicate hits bypass the box) -- order independent within the tile;
-//   TMA   two reduce-adds (output box, count box) flush the tile: ~1 L2 reduction sector per
-//         pixel instead of ~6.6.  Targets outside the box fall back to global atomics.
+//   ...   the touched part of the box is flushed with 128-bit vector reductions (4 cells each,
+//         all-zero vectors skipped).  Targets outside the box fall back to global atomics.
 //
 // The frames are processed ONE AT A TIME (memset -> splat -> average -> fill-hole per frame): a
 // frame's count+output planes (25 MB at 1080p) then stay L2-resident between the passes instead
@@ -43,8 +43,7 @@ __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
 }
 
 __global__ void __launch_bounds__(NT, 4)
-fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_out,
-                const __grid_constant__ CUtensorMap m_count, const FpArgs p, const int b) {
+fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, const int b) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,37 +160,162 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constan
             }
     }
     __syncthreads();
-    {   // fixed point -> fp32 in place
-        float* bf = reinterpret_cast<float*>(&s.box[0][0][0]);
-        const int* bi = &s.box[0][0][0];
-        for (int i = tid; i < 2 * BOX; i += NT) bf[i] = (float)bi[i] * inv_scale;
-        for (int i = 2 * BOX + tid; i < 3 * BOX; i += NT) bf[i] = (float)bi[i];
-    }
-    tma::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-        tma::reduce_add_4d(&m_out, bx, by, 0, b, &s.box[0][0][0]);
-        tma::reduce_add_4d(&m_count, bx, by, 0, b, &s.box[2][0][0]);
-        tma::bulk_commit();
-        tma::bulk_wait_read_all();
+    // ---- flush: only the cells the tile actually hit (their bounding box, clipped to the staged
+    // box), four cells per 128-bit vector reduction (REDG.E.ADD.F32x4), all-zero vectors skipped.
+    // (A dense TMA reduce-add of the whole box is wasteful here: when flows converge, thousands of
+    // tiles would all add mostly-zero boxes onto the same few sectors.)
+    {
+        const int cx0 = max(s.bb[0], bx) - bx, cx1 = min(s.bb[1] + 1, bx + SW - 1) - bx;
+        const int cy0 = max(s.bb[2], by) - by, cy1 = min(s.bb[3] + 1, by + SH - 1) - by;
+        if (cx0 <= cx1 && cy0 <= cy1) {
+            const int v0 = cx0 >> 2, nv = (cx1 >> 2) - v0 + 1, nr = cy1 - cy0 + 1;
+            for (int i = tid; i < 3 * nr * nv; i += NT) {
+                const int pl = i / (nr * nv), r = i - pl * nr * nv;
+                const int uy = cy0 + r / nv, ux = (v0 + r % nv) << 2;
+                const int4 q = *reinterpret_cast<const int4*>(&s.box[pl][uy][ux]);
+                if ((q.x | q.y | q.z | q.w) == 0) continue;
+                const float sc = pl == 2 ? 1.0f : inv_scale;
+                const float4 v = make_float4((float)q.x * sc, (float)q.y * sc, (float)q.z * sc, (float)q.w * sc);
+                float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) +
+                             (int64_t)(by + uy) * (pl == 2 ? p.count.h : p.out.h) + bx + ux;
+                atomicAdd(reinterpret_cast<float4*>(dst), v);
+            }
+        }
     }
 }
 
-// out /= count where count > 0, four pixels per thread (128-bit accesses)
-__global__ void __launch_bounds__(256) fp_average4_kernel(float* __restrict__ out, const float* __restrict__ count,
-                                                          int64_t out_c, int64_t n4) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n4) return;
-    const float4 c = reinterpret_cast<const float4*>(count)[i];
-    float4* px = reinterpret_cast<float4*>(out) + i;
-    float4* py = reinterpret_cast<float4*>(out + out_c) + i;
-    float4 vx = *px, vy = *py;
-    if (c.x > 0.f) { vx.x /= c.x; vy.x /= c.x; }
-    if (c.y > 0.f) { vx.y /= c.y; vy.y /= c.y; }
-    if (c.z > 0.f) { vx.z /= c.z; vy.z /= c.z; }
-    if (c.w > 0.f) { vx.w /= c.w; vy.w /= c.w; }
-    *px = vx;
-    *py = vy;
+// ------------------------------------------------------------------------------------
+// average + occupancy bit masks.  One CTA = one 32 x 32 pixel block, warp r = row r:
+//   out /= count where count > 0 (my_lib_kernel.cu:1730-1736), and
+//   rowmask[b][y][x/32]  bit (x%32) = count[b][y][x] > 0      (32 pixels of a row per word)
+//   colmask[b][y/32][x]  bit (y%32) = count[b][y][x] > 0      (32 pixels of a column per word)
+// The masks turn fill-hole's per-pixel linear walks (O(W) loads when holes are large: the
+// legacy kernel needs 30 ms per 16 frames when the flow converges and most of the frame is a
+// hole) into a few word loads plus clz / ffs -- with exactly the same result.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict__ out, const float* __restrict__ count,
+                                                              unsigned* __restrict__ rowmask, unsigned* __restrict__ colmask,
+                                                              int W, int H, int Wt, int Ht, int64_t out_c) {
+    __shared__ unsigned rw[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // 8 warps x 4 rows = the block's 32 rows
+        const int r = warp + 8 * k, y = blockIdx.y * 32 + r;
+        float c = 0.f;
+        if (x < W && y < H) {
+            const int64_t o = (int64_t)y * W + x;
+            c = count[o];
+            if (c > 0.f) {
+                out[o] = out[o] / c;
+                out[out_c + o] = out[out_c + o] / c;
+            }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, c > 0.f);
+        if (lane == 0) {
+            rw[r] = word;
+            if (y < H) rowmask[(int64_t)y * Wt + blockIdx.x] = word;
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && x < W) {  // column words, stored [y/32][x] so that a warp's loads coalesce
+        unsigned col = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) col |= ((rw[k] >> lane) & 1u) << k;
+        colmask[(int64_t)blockIdx.y * W + x] = col;
+    }
+}
+
+// fill-hole with the masks: identical semantics to flow_projection.cu's fp_fillhole_kernel
+// (nearest counted pixel to the left, right and above; never below, my_lib_kernel.cu:1799).
+// The word walks fetch four words per step (independent loads) and stop at the first hit.
+__global__ void __launch_bounds__(256) fp_fillhole_mask_kernel(float* __restrict__ out, const unsigned* __restrict__ rowmask,
+                                                               const unsigned* __restrict__ colmask, int W, int H, int Wt,
+                                                               int Ht, int64_t out_b, int64_t out_c) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const unsigned* rm = rowmask + ((int64_t)b * H + y) * Wt;
+    const int wi0 = x >> 5, bit = x & 31;
+    const unsigned word = rm[wi0];
+    if ((word >> bit) & 1u) return;  // counted pixel: not a hole
+    int lo = -1, ro = -1, uo = -1;
+    {   // left: highest set bit below x
+        unsigned m = word & ((1u << bit) - 1u);
+        int wi = wi0;
+        while (m == 0u && wi > 0) {
+            unsigned w4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w4[k] = (wi - 1 - k >= 0) ? rm[wi - 1 - k] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m == 0u && wi > 0) { --wi; m = w4[k]; }
+        }
+        if (m) lo = wi * 32 + 31 - __clz(m);
+    }
+    {   // right: lowest set bit above x
+        unsigned m = bit == 31 ? 0u : (word & ~((2u << bit) - 1u));
+        int wi = wi0;
+        while (m == 0u && wi < Wt - 1) {
+            unsigned w4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w4[k] = (wi + 1 + k <= Wt - 1) ? rm[wi + 1 + k] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m == 0u && wi < Wt - 1) { ++wi; m = w4[k]; }
+        }
+        if (m) ro = wi * 32 + __ffs(m) - 1;
+    }
+    {   // up: highest set bit above y in column x (colmask is [y/32][x])
+        const unsigned* cm = colmask + (int64_t)b * Ht * W + x;
+        int hi = y >> 5;
+        unsigned m = cm[(int64_t)hi * W] & ((1u << (y & 31)) - 1u);
+        while (m == 0u && hi > 0) {
+            unsigned w4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w4[k] = (hi - 1 - k >= 0) ? cm[(int64_t)(hi - 1 - k) * W] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m == 0u && hi > 0) { --hi; m = w4[k]; }
+        }
+        if (m) uo = hi * 32 + 31 - __clz(m);
+    }
+    if (lo < 0 && ro < 0 && uo < 0) return;  // nothing found: stays 0
+    float* ox = out + (int64_t)b * out_b;
+    float* oy = ox + out_c;
+    float sx = 0.f, sy = 0.f, den = 0.f;
+    const int64_t row = (int64_t)y * W;
+    if (lo >= 0) { sx += ox[row + lo]; sy += oy[row + lo]; den += 1.f; }
+    if (ro >= 0) { sx += ox[row + ro]; sy += oy[row + ro]; den += 1.f; }
+    if (uo >= 0) { sx += ox[(int64_t)uo * W + x]; sy += oy[(int64_t)uo * W + x]; den += 1.f; }
+    ox[row + x] = sx / den;
+    oy[row + x] = sy / den;
+}
+
+// Library-owned stream-ordered memory pool for the occupancy masks (the only scratch memory the
+// library ever allocates).  A private pool with a high release threshold keeps the blocks
+// cached across calls; the device's default pool would hand them back to the OS at every
+// synchronisation (measured: 2 ms per call).  One pool per device, created on first use.
+cudaMemPool_t scratch_pool() {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = pool;
+    }
+    return pools[dev];
 }
 
 }  // namespace
@@ -204,15 +328,9 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     if (a.out.h != a.W || a.out.c != plane || a.count.h != a.W) return 0;
     if ((reinterpret_cast<uintptr_t>(a.outp) & 15u) || (reinterpret_cast<uintptr_t>(a.countp) & 15u)) return 0;
     if (a.out.b % 4 || a.count.b % 4) return 0;
-    CUtensorMap m_flow, m_out, m_count;
+    CUtensorMap m_flow;
     if (!tma::make_map_nchw(&m_flow, a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, TH, 2,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
-        return 0;
-    if (!tma::make_map_nchw(&m_out, a.outp, a.B, 2, a.H, a.W, a.out.b, a.out.c, a.out.h, SW, SH, 2,
-                            CU_TENSOR_MAP_L2_PROMOTION_NONE))
-        return 0;
-    if (!tma::make_map_nchw(&m_count, a.countp, a.B, 1, a.H, a.W, a.count.b, plane, a.count.h, SW, SH, 1,
-                            CU_TENSOR_MAP_L2_PROMOTION_NONE))
         return 0;
     static bool configured = false;
     const size_t smem = sizeof(Smem) + 128;
@@ -224,22 +342,43 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
         configured = true;
     }
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
-    const int64_t n4 = plane / 4;
-    for (int b = 0; b < a.B; ++b) {
+    // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
+    const int Wt = (a.W + 31) / 32, Ht = (a.H + 31) / 32;
+    const size_t n_row = (size_t)a.B * a.H * Wt, n_col = (size_t)a.B * a.W * Ht;
+    unsigned* masks = nullptr;
+    cudaMemPool_t pool = scratch_pool();
+    if (!pool || cudaMallocFromPoolAsync(reinterpret_cast<void**>(&masks), (n_row + n_col) * sizeof(unsigned), pool,
+                                         stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    unsigned* rowmask = masks;
+    unsigned* colmask = masks + n_row;
+    const dim3 mgrid(Wt, Ht, 1);
+    int rc = 1;
+    for (int b = 0; b < a.B && rc == 1; ++b) {
         float* outb = a.outp + (int64_t)b * a.out.b;
         float* cntb = a.countp + (int64_t)b * a.count.b;
         if (overwrite && !no_zero) {
-            if (cudaMemsetAsync(outb, 0, sizeof(float) * 2 * plane, stream) != cudaSuccess) return -1;
-            if (cudaMemsetAsync(cntb, 0, sizeof(float) * plane, stream) != cudaSuccess) return -1;
+            if (cudaMemsetAsync(outb, 0, sizeof(float) * 2 * plane, stream) != cudaSuccess) rc = -1;
+            if (cudaMemsetAsync(cntb, 0, sizeof(float) * plane, stream) != cudaSuccess) rc = -1;
             count_launch(2);
         }
-        fp_splat_kernel<<<grid, NT, smem, stream>>>(m_flow, m_out, m_count, a, b);
-        fp_average4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(outb, cntb, a.out.c, n4);
+        fp_splat_kernel<<<grid, NT, smem, stream>>>(m_flow, a, b);
+        fp_average_mask_kernel<<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
+                                                           colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
         count_launch(2);
-        if (check_launch("FlowProjection splat/average (fast)")) return -1;
-        if (a.fillhole && fp_average_fill(stream, a, b, 1, false) != 0) return -1;
+        if (check_launch("FlowProjection splat/average (fast)")) rc = -1;
     }
-    return 1;
+    // fill-hole once over the whole batch (it only needs the masks and the averaged output)
+    if (rc == 1 && a.fillhole) {
+        const dim3 fgrid(Wt, (a.H + 7) / 8, a.B);
+        fp_fillhole_mask_kernel<<<fgrid, 256, 0, stream>>>(a.outp, rowmask, colmask, a.W, a.H, Wt, Ht, a.out.b, a.out.c);
+        count_launch();
+        if (check_launch("FlowProjection fill-hole (masks)")) rc = -1;
+    }
+    cudaFreeAsync(masks, stream);
+    return rc;
 }
 
 }  // namespace memc

@@ -13,11 +13,12 @@ def _gen(seed, device):
     return g
 
 
-def smooth_flow(B, H, W, sigma, seed=0, device="cpu", jitter=0.25):
-    """Low-res N(0, sigma^2) field at (H/16, W/16) bilinearly upsampled, plus per-pixel
-    N(0, jitter^2): smooth motion with fractional positions everywhere."""
+def smooth_flow(B, H, W, sigma, seed=0, device="cpu", jitter=0.25, grid=16):
+    """Low-res N(0, sigma^2) field at (H/grid, W/grid) bilinearly upsampled, plus per-pixel
+    N(0, jitter^2): smooth motion with fractional positions everywhere.  grid=16 is the
+    SURVEY's benchmark field (flow gradient ~0.5 px/px: rather rough); larger grids are smoother."""
     g = _gen(seed, device)
-    lh, lw = max(2, H // 16), max(2, W // 16)
+    lh, lw = max(2, H // grid), max(2, W // grid)
     low = torch.randn(B, 2, lh, lw, generator=g, device=device) * sigma
     flow = F.interpolate(low, size=(H, W), mode="bilinear", align_corners=True)
     flow = flow + torch.randn(B, 2, H, W, generator=g, device=device) * jitter
@@ -69,13 +70,13 @@ def grad_like(t, seed=0):
     return torch.randn(t.shape, generator=_gen(seed, t.device), device=t.device)
 
 
-def filter_interpolation_case(B, C, H, W, fs=4, sigma=None, seed=0, device="cpu"):
+def filter_interpolation_case(B, C, H, W, fs=4, sigma=None, seed=0, device="cpu", grid=16):
     """(input1, flow, filter, gradoutput) for FilterInterpolation; sigma defaults to the
     SURVEY's 4 px @720p / 6 px @1080p scaled by height."""
     if sigma is None:
         sigma = 6.0 * H / 1080.0 if H >= 900 else 4.0 * max(H, 64) / 720.0
     in1 = image(B, C, H, W, seed, device)
-    flow = smooth_flow(B, H, W, sigma, seed + 1, device)
+    flow = smooth_flow(B, H, W, sigma, seed + 1, device, grid=grid)
     filt = softmax_filter(B, fs, H, W, seed + 2, device)
     gout = grad_like(in1, seed + 3)
     return in1, flow, filt, gout

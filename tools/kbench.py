@@ -63,8 +63,8 @@ def P(t):
     return lib.ptr(t)
 
 
-def fi_calls(B, C, H, W, flags):
-    in1, flow, filt, gout = synth.filter_interpolation_case(B, C, H, W, seed=0, device="cuda")
+def fi_calls(B, C, H, W, flags, grid=16):
+    in1, flow, filt, gout = synth.filter_interpolation_case(B, C, H, W, seed=0, device="cuda", grid=grid)
     out = torch.empty_like(in1)
     g1, g2, g3 = torch.empty_like(in1), torch.empty_like(flow), torch.empty_like(filt)
     st = lib.stream_ptr(in1)
@@ -126,6 +126,16 @@ def main():
                 row("FI bwd %s B%d C%d %dx%d" % (tag, B, C, W, H), px, (3 * C + 36) * 4, tb, trb)
                 del in1, flow, filt, gout
                 torch.cuda.empty_cache()
+
+    if only is None or "fismooth" in only:
+        # the same op on smoother motion fields (flow gradient ~0.5 / 0.12 / 0.03 px per px)
+        B, C, H, W = 4, 3, 1080, 1920
+        for grid in (16, 64, 256):
+            (in1, flow, filt, gout), fwd, bwd = fi_calls(B, C, H, W, lib.OVERWRITE, grid=grid)
+            row("FI fwd fast B4 C3 1080p flow-grid %d" % grid, B * H * W, 96, timeit(fwd, args.iters))
+            row("FI bwd fast B4 C3 1080p flow-grid %d" % grid, B * H * W, 180, timeit(bwd, args.iters))
+            del in1, flow, filt, gout
+            torch.cuda.empty_cache()
 
     if only is None or "fp" in only:
         B, H, W = 16, 1080, 1920
