@@ -46,6 +46,15 @@ BYTES_FWD = (2 * C + 2 + FS * FS) * 4          # 96 B/px
 BYTES_BWD = (3 * C + 2 * (2 + FS * FS)) * 4    # 180 B/px
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) per launch of the two kernels from the committed ncu --set full
+    capture of this same command (profiles/traffic.json, written by tools/ncu_traffic.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
 def peak_hbm():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -67,7 +76,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -213,12 +222,13 @@ def run_ours(args, rank, world, local_rank):
         if events is not None:
             events[3].record()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()      # nvidia-smi needs ~0.2 s to start: sample across warm-up + timed + e2e
+    t_wall0 = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    if sampler:
-        sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = lib.launch_count()
@@ -230,7 +240,6 @@ def run_ours(args, rank, world, local_rank):
     launches = lib.launch_count() - n0 + args.steps          # + the gi1 memset per step
     t_dev = e0.elapsed_time(e1) * 1e-3
     barrier()
-    clocks = sampler.stop() if sampler else None
     t_fwd = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
     t_bwd = statistics.mean(e[2].elapsed_time(e[3]) for e in ev) * 1e-3
 
@@ -262,6 +271,17 @@ def run_ours(args, rank, world, local_rank):
     t_e2e = x0.elapsed_time(x1) * 1e-3 / n_e2e
     barrier()
 
+    # ---- clocks: sampled since before warm-up; if the whole run was shorter than a few sampling
+    # periods keep running the SAME step (untimed) until there are samples under load
+    clocks = None
+    if sampler:
+        while time.perf_counter() - t_wall0 < 1.5:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["window"] = "warm-up + timed steps + e2e steps (+ identical untimed steps up to 1.5 s)"
+
     # ---- max over ranks
     if distributed:
         tt = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd], device=dev, dtype=torch.float64)
@@ -272,6 +292,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * px_step * args.steps / t_dev / 1e6
     e2e_val = world * px_step / t_e2e / 1e6
     peak, peak_kind = peak_hbm()
+    traffic = ncu_traffic()
     ach_b = px_step * BYTES_BWD / t_bwd / 1e9
     ach_f = px_step * BYTES_FWD / t_fwd / 1e9
 
@@ -287,10 +308,10 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": t_e2e * 1e3, "api": "my_package.modules.FilterInterpolationModule + autograd"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "FilterInterpolation backward", "bound": "hbm", "achieved": ach_b, "peak": peak,
-                     "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_b / peak, "traffic": None,
+                     "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic.get("fi_bwd_bytes_per_launch"),
                      "bytes_per_launch": px_step * BYTES_BWD, "ms_per_launch": t_bwd * 1e3},
         "roofline_fwd": {"kernel": "FilterInterpolation forward", "bound": "hbm", "achieved": ach_f, "peak": peak,
-                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_f / peak, "traffic": None,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_f / peak, "traffic": traffic.get("fi_fwd_bytes_per_launch"),
                          "bytes_per_launch": px_step * BYTES_FWD, "ms_per_launch": t_fwd * 1e3,
                          "mpx_s_per_gpu": px_step / t_fwd / 1e6},
     }
@@ -311,8 +332,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

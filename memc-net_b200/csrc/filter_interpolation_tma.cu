@@ -125,6 +125,37 @@ __device__ __forceinline__ void prof_mark(const FiArgs& p, int tile_i, int k) {
         p.prof[((long long)blockIdx.x * 8 + tile_i) * 6 + k] = clock64();
 }
 
+// Same bounding box computed by ONE warp (each lane walks TW*TH/32 pixels): no block barrier and
+// no shared atomics between the flow tile landing and the image TMA being issued.
+template <class K>
+__device__ __forceinline__ void tile_box_warp(const float* s_flow, int x0, int y0, int W, int H, int lane, int& bx,
+                                              int& by) {
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < K::TW * K::TH / 32; ++k) {
+        const int idx = k * 32 + lane;
+        const int yl = idx / K::TW, xl = idx % K::TW;
+        const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * K::TW + xl], s_flow[(K::TH + yl) * K::TW + xl]);
+        if (g.valid && x0 + xl < W && y0 + yl < H) {
+            mnx = min(mnx, g.ix); mxx = max(mxx, g.ix);
+            mny = min(mny, g.iy); mxy = max(mxy, g.iy);
+        }
+    }
+    mnx = warp_min(mnx); mxx = warp_max(mxx); mny = warp_min(mny); mxy = warp_max(mxy);
+    if (mnx > mxx) {  // nothing valid: any legal origin
+        bx = 0;
+        by = 0;
+        return;
+    }
+    bx = mnx - 1;
+    by = mny - 1;
+    const int need_w = mxx - mnx + 4 + 3, need_h = mxy - mny + 4;
+    if (need_w > K::SW) bx += (need_w - K::SW) / 2;
+    if (need_h > K::SH) by += (need_h - K::SH) / 2;
+    bx = max(0, min(bx, W - K::SW)) & ~3;
+    by = max(0, min(by, H - K::SH));
+}
+
 // ====================================================================================
 // forward
 // ====================================================================================
@@ -254,6 +285,94 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
 }
 
 bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m);  // m[5]
+
+// ------------------------------------------------------------------------------------
+// forward, second generation of the one-tile-per-CTA kernel: shorter dependent chain.
+//   * the image neighbourhood of the tile (a generous PW x PH box around the tile) is
+//     PREFETCHED INTO L2 at CTA start, before the flow is known, so that the data-dependent
+//     image TMA issued later mostly hits L2;
+//   * the bounding box is computed by warp 0 alone right after the flow tile lands (no block
+//     barrier, no shared atomics); the other warps go straight to the waits.
+// ------------------------------------------------------------------------------------
+constexpr int PREF_W = 96, PREF_H = 48;  // L2 prefetch box
+
+template <int C, class K, bool PFL2>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_fwd_tma2_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                   const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_pref,
+                   const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    constexpr Layout lay = make_layout<K>(C, 16, false);
+    const float* s_filt = reinterpret_cast<const float*>(sm + lay.off_a);
+    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);  // 0 flow, 1 filter, 2 image
+    volatile int* s_box = reinterpret_cast<volatile int*>(bars + 3);  // bx, by (written by lane 0 of warp 0)
+    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H;
+
+    prof_mark(p, 0, 0);
+    if (tid == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::mbar_init(&bars[2], 1);
+        tma::fence_barrier_init();
+        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
+        tma::load_4d(sm + lay.off_a, &m_filt, x0, y0, 0, b, &bars[1]);
+        if (PFL2) tma::prefetch_l2_4d(&m_pref, (x0 + TW / 2 - PREF_W / 2) & ~3, y0 + TH / 2 - PREF_H / 2, 0, b);
+    }
+    __syncthreads();  // barriers initialised before anybody waits on them
+
+    tma::mbar_wait(&bars[0], 0, 1);
+    prof_mark(p, 0, 1);
+    if (warp == 0) {
+        int bx, by;
+        tile_box_warp<K>(s_flow, x0, y0, W, H, lane, bx, by);
+        if (lane == 0) {
+            s_box[0] = bx;
+            s_box[1] = by;
+            tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);  // release: publishes s_box to the waiters
+            tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
+        }
+    }
+    prof_mark(p, 0, 2);
+    tma::mbar_wait(&bars[1], 0, 2);
+    tma::mbar_wait(&bars[2], 0, 3);
+    prof_mark(p, 0, 3);
+    const int bx = s_box[0], by = s_box[1];
+    fwd_compute_tile<C, K>(p, s_filt, s_flow, s_img, x0, y0, b, bx, by, lane, warp);
+    prof_mark(p, 0, 4);
+}
+
+template <int C, class K, bool PFL2>
+int launch_fwd2(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH || a.W < PREF_W || a.H < PREF_H) return 0;
+    CUtensorMap m[5], mpref;
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    if (!tma::make_map_nchw(&mpref, a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, PREF_W, PREF_H, a.C,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return 0;
+    static bool configured = false;
+    constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_fwd_tma2_kernel<C, K, PFL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        configured = true;
+    }
+    dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
+    fi_fwd_tma2_kernel<C, K, PFL2><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], mpref, a);
+    count_launch();
+    return check_launch("FilterInterpolation forward (TMA v2)") == 0 ? 1 : -1;
+}
 
 // ------------------------------------------------------------------------------------
 // persistent forward: each CTA walks tiles blockIdx.x, blockIdx.x + grid, ... (raster order,
@@ -941,6 +1060,11 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 9: r = launch_fwd_persist<3, FwdP4>(stream, a); break;
             case 10: r = launch_fwd<3, FwdF>(stream, a); break;
             case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
+            case 20: r = launch_fwd2<3, FwdE, false>(stream, a); break;
+            case 21: r = launch_fwd2<3, FwdE, true>(stream, a); break;
+            case 22: r = launch_fwd2<3, FwdC, true>(stream, a); break;
+            case 23: r = launch_fwd2<3, FwdF, true>(stream, a); break;
+            case 24: r = launch_fwd2<3, FwdB, true>(stream, a); break;
             case 13: r = launch_fwd_pl<3, FwdL2, true>(stream, a); break;
             case 14: r = launch_fwd_pl<3, FwdL3, false>(stream, a); break;
             case 15: r = launch_fwd_pl<3, FwdL4, false>(stream, a); break;

@@ -83,6 +83,13 @@ __device__ __forceinline__ void store_4d(const CUtensorMap* map, int c0, int c1,
         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
         : "memory");
 }
+// 4-D tile prefetch global -> L2 only (no shared memory, no completion tracking)
+__device__ __forceinline__ void prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk groups have finished READING shared memory (safe to reuse / exit)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
