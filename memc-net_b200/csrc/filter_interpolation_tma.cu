@@ -375,6 +375,172 @@ int launch_fwd2(cudaStream_t stream, const FiArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------
+// forward for C > 4 (e.g. the 64-channel context features MEMC_Net_star warps with the same
+// flow / filter, networks/MEMC_Net_star.py:280-285): flow tile, filter tile and bounding box are
+// set up ONCE per tile, then the image is streamed through a two-buffer ring of CBK-channel
+// boxes while the 16 filter taps and the geometry of each pixel stay in registers
+// (the legacy kernel re-reads the 16 filter planes for every one of the 64 channels).
+// ------------------------------------------------------------------------------------
+constexpr int CBK = 4;  // channels per streamed box
+
+template <class K>
+__host__ __device__ constexpr int chunked_smem() {
+    return 16 * K::TH * K::TW * 4 + 2 * K::TH * K::TW * 4 + 2 * (CBK * K::SH * K::SW * 4) + 256;
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::NT, K::MINB)
+fi_fwd_tma_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                          const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, PPT = K::PPT;
+    constexpr int FILT_B = 16 * TH * TW * 4, FLOW_B = 2 * TH * TW * 4, IMG_B = CBK * SH * SW * 4;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    const float* s_filt = reinterpret_cast<const float*>(sm);
+    const float* s_flow = reinterpret_cast<const float*>(sm + FILT_B);
+    unsigned char* const sm_img0 = sm + FILT_B + FLOW_B;                        // 2 buffers, IMG_B apart
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_img0 + 2 * IMG_B);          // 0 flow, 1 filter, 2/3 image
+    int* s_bb = reinterpret_cast<int*>(bars + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H, C = p.C;
+    const int nchunk = (C + CBK - 1) / CBK;
+
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) tma::mbar_init(&bars[k], 1);
+        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(&bars[0], FLOW_B);
+        tma::load_4d(sm + FILT_B, &m_flow, x0, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], FILT_B);
+        tma::load_4d(sm, &m_filt, x0, y0, 0, b, &bars[1]);
+    }
+    tma::mbar_wait(&bars[0], 0, 51);
+    int bx, by;
+    tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
+    if (tid == 0) {
+        for (int ch = 0; ch < 2 && ch < nchunk; ++ch) {
+            tma::mbar_expect_tx(&bars[2 + ch], IMG_B);
+            tma::load_4d(sm_img0 + ch * IMG_B, &m_img, bx, by, ch * CBK, b, &bars[2 + ch]);
+        }
+    }
+    tma::mbar_wait(&bars[1], 0, 52);
+
+    // ---- per-pixel state kept in registers across the channel chunks
+    float wg[PPT][16], wq[PPT][4];
+    int off[PPT];      // >= 0: tap (0,0) offset inside the box (fast path); -1: slow path; -2: invalid; -3: outside
+    int Lx[PPT], Ty[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        int xl, yl;
+        tile_pixel<K>(k, lane, warp, xl, yl);
+        const int x = x0 + xl, y = y0 + yl;
+        off[k] = -3;
+        Lx[k] = Ty[k] = 0;
+        if (x >= W || y >= H) continue;
+        const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+        if (!g.valid) { off[k] = -2; continue; }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) wg[k][t] = s_filt[(t * TH + yl) * TW + xl];
+        const float a = g.alpha, bt = g.beta;
+        wq[k][0] = (1.0f - a) * (1.0f - bt); wq[k][1] = a * (1.0f - bt);
+        wq[k][2] = (1.0f - a) * bt;          wq[k][3] = a * bt;
+        Lx[k] = g.ix - 1;
+        Ty[k] = g.iy - 1;
+        const int lx = Lx[k] - bx, ly = Ty[k] - by;
+        const bool fast = (Lx[k] >= 0) && (Lx[k] + 3 <= W - 1) && (Ty[k] >= 0) && (Ty[k] + 3 <= H - 1) &&
+                          (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
+        off[k] = fast ? ly * SW + lx : -1;
+    }
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const float* s_img = reinterpret_cast<const float*>(sm_img0 + (ch & 1) * IMG_B);
+        tma::mbar_wait(&bars[2 + (ch & 1)], (ch >> 1) & 1, 53);
+        const int c0 = ch * CBK;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            if (off[k] == -3) continue;
+            int xl, yl;
+            tile_pixel<K>(k, lane, warp, xl, yl);
+            const int x = x0 + xl, y = y0 + yl;
+            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+#pragma unroll
+            for (int cc = 0; cc < CBK; ++cc) {
+                const int c = c0 + cc;
+                if (c >= C) break;
+                float v;
+                if (off[k] == -2) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
+                    v = __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x);
+                } else if (off[k] >= 0) {
+                    const float* base = s_img + cc * SH * SW + off[k];
+                    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            q[(j >> 1) * 2 + (i >> 1)] = fmaf(base[j * SW + i], wg[k][j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+                    v = wq[k][0] * q[0] + wq[k][1] * q[1] + wq[k][2] * q[2] + wq[k][3] * q[3];
+                } else {
+                    const float* img = in1b + c * p.in1.c;
+                    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int cx = clampi(Lx[k] + i, 0, W - 1), cy = clampi(Ty[k] + j, 0, H - 1);
+                            const int ux = cx - bx, uy = cy - by;
+                            const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+                            const float t = in_box ? s_img[cc * SH * SW + uy * SW + ux] : __ldg(img + (int64_t)cy * p.in1.h + cx);
+                            q[(j >> 1) * 2 + (i >> 1)] = fmaf(t, wg[k][j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+                        }
+                    v = wq[k][0] * q[0] + wq[k][1] * q[1] + wq[k][2] * q[2] + wq[k][3] * q[3];
+                }
+                stg_stream(outp + c * p.out.c, v);
+            }
+        }
+        __syncthreads();  // everybody is done with buffer ch&1
+        if (tid == 0 && ch + 2 < nchunk) {
+            tma::fence_proxy_async();
+            tma::mbar_expect_tx(&bars[2 + (ch & 1)], IMG_B);
+            tma::load_4d(sm_img0 + (ch & 1) * IMG_B, &m_img, bx, by, (ch + 2) * CBK, b, &bars[2 + (ch & 1)]);
+        }
+    }
+}
+
+template <class K>
+int launch_fwd_chunked(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[5];
+    FiArgs a4 = a;
+    if (!tma::make_map_nchw(&m[0], a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, K::TW, K::TH, 2,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B) ||
+        !tma::make_map_nchw(&m[1], a.filtp, a.B, 16, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, K::TW, K::TH, 16,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
+        !tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, K::SW, K::SH, CBK,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return 0;
+    static bool configured = false;
+    constexpr size_t smem = (size_t)chunked_smem<K>() + 128;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fi_fwd_tma_chunked_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        configured = true;
+    }
+    dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
+    fi_fwd_tma_chunked_kernel<K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a4);
+    count_launch();
+    return check_launch("FilterInterpolation forward (TMA, channel-chunked)") == 0 ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------
 // persistent forward: each CTA walks tiles blockIdx.x, blockIdx.x + grid, ... (raster order,
 // so concurrently running CTAs work on neighbouring tiles and share image rows in L2) with a
 // two-stage ring for (filter tile, image box) and a three-slot ring for the flow tile.  The
@@ -999,6 +1165,8 @@ using FwdP1 = Cfg<32, 16, 64, 40, 256, 1>;  // persistent, 137 KB: 1 CTA / SM
 using FwdP2 = Cfg<32, 8, 64, 22, 128, 3>;   // persistent,  73 KB: 3 CTAs / SM
 using FwdP3 = Cfg<64, 16, 96, 28, 512, 1>;  // persistent, 215 KB: 1 CTA / SM
 using FwdP4 = Cfg<32, 16, 64, 32, 256, 1>;  // persistent, 125 KB: 1 CTA / SM
+using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
+using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
 using FWD_DEFAULT = FwdE;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
 using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
@@ -1039,6 +1207,16 @@ static void prof_report(cudaStream_t stream, long long* dev) {
 int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
     FiArgs a = a_in;
     a.dbg = env_int("MEMC_TMA_DBG");
+    if (a.fs == 4 && a.C > CB && a.W % 4 == 0 && a.B <= 65535) {
+        // C > 4 (64-channel context warps): channel-chunked TMA variant.  Measured EQUAL to the generic
+        // kernel (1.15 vs 1.12 ms per 1080p frame at C=64: both are bound by the 16*C shared/L1
+        // gather wavefronts, not by HBM), so production keeps the generic kernel; selectable for work
+        // on it with MEMC_FI_FWD_CFG=30/31.
+        const int cfg = env_int("MEMC_FI_FWD_CFG");
+        if (cfg == 30) return launch_fwd_chunked<FwdK1>(stream, a);
+        if (cfg == 31) return launch_fwd_chunked<FwdK2>(stream, a);
+        return 0;
+    }
     if (a.dbg & 64) {
         static long long* dev = nullptr;
         if (!dev) cudaMalloc(reinterpret_cast<void**>(&dev), 256 * 8 * 6 * sizeof(long long));

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(BX* BY) fp_fillhole_kernel(const FpArgs p) {
 
 // ----------------------------------------------------------------------------- backward
 template <bool OVERWRITE>
-__global__ void __launch_bounds__(BX* BY) fp_bwd_kernel(const FpArgs p) {
+__global__ void __launch_bounds__(BX* BY, 6) fp_bwd_kernel(const FpArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;

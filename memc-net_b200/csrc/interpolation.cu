@@ -24,7 +24,10 @@ struct IpArgs {
 
 constexpr int BX = 32, BY = 8;
 
-__global__ void __launch_bounds__(BX* BY) ip_fwd_kernel(const IpArgs p) {
+// 1 pixel / thread and a dependent chain (flow -> 4*C gathers -> store): latency bound, so the
+// register cap buys occupancy (5 CTAs of 256 threads per SM) rather than unrolling depth.
+template <int CT>  // CT = 3: RGB specialisation (fully unrolled); CT = 0: any channel count
+__global__ void __launch_bounds__(BX* BY, 5) ip_fwd_kernel(const IpArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;
@@ -33,8 +36,9 @@ __global__ void __launch_bounds__(BX* BY) ip_fwd_kernel(const IpArgs p) {
     const float fx = ldg_stream(fl), fy = ldg_stream(fl + p.flow.c);
     const float x2 = (float)w + fx, y2 = (float)h + fy;
     float* ob = p.outp + b * p.out.b + h * p.out.h + w;
+    const int C = CT ? CT : p.C;
     if (!(x2 >= 0.0f && y2 >= 0.0f && x2 < (float)p.W && y2 < (float)p.H)) {
-        for (int c = 0; c < p.C; ++c) stg_stream(ob + c * p.out.c, 0.0f);
+        for (int c = 0; c < C; ++c) stg_stream(ob + c * p.out.c, 0.0f);
         return;
     }
     const int L = (int)x2, T = (int)y2;
@@ -44,15 +48,26 @@ __global__ void __launch_bounds__(BX* BY) ip_fwd_kernel(const IpArgs p) {
     const float wBL = (1.0f - a) * bt, wBR = a * bt;
     const float* img = p.in1p + b * p.in1.b;
     const int64_t oT = (int64_t)T * p.in1.h, oB = (int64_t)Bm * p.in1.h;
-    for (int c = 0; c < p.C; ++c, img += p.in1.c) {
-        const float v = wTL * __ldg(img + oT + L) + wTR * __ldg(img + oT + R) +
-                        wBL * __ldg(img + oB + L) + wBR * __ldg(img + oB + R);
-        stg_stream(ob + c * p.out.c, v);
+    if (CT) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float* im = img + c * p.in1.c;
+            const float v = wTL * __ldg(im + oT + L) + wTR * __ldg(im + oT + R) + wBL * __ldg(im + oB + L) +
+                            wBR * __ldg(im + oB + R);
+            stg_stream(ob + c * p.out.c, v);
+        }
+    } else {
+#pragma unroll 2
+        for (int c = 0; c < C; ++c, img += p.in1.c) {
+            const float v = wTL * __ldg(img + oT + L) + wTR * __ldg(img + oT + R) + wBL * __ldg(img + oB + L) +
+                            wBR * __ldg(img + oB + R);
+            stg_stream(ob + c * p.out.c, v);
+        }
     }
 }
 
 template <bool OVERWRITE>
-__global__ void __launch_bounds__(BX* BY) ip_bwd_kernel(const IpArgs p) {
+__global__ void __launch_bounds__(BX* BY, 4) ip_bwd_kernel(const IpArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;
@@ -94,7 +109,8 @@ static int ip_forward(cudaStream_t stream, const IpArgs& a, int flags) {
     (void)flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
-    ip_fwd_kernel<<<grid, block, 0, stream>>>(a);
+    if (a.C == 3) ip_fwd_kernel<3><<<grid, block, 0, stream>>>(a);
+    else ip_fwd_kernel<0><<<grid, block, 0, stream>>>(a);
     count_launch();
     return check_launch("Interpolation forward");
 }

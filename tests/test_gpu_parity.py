@@ -146,12 +146,15 @@ def test_filter_interpolation_vs_reference_cuda_kernels(L, shape):
     close(g3, host(r3), what="gi3 vs reference CUDA")
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0)])
-def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
+@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0),
+                                   (1, 64, 96, 160, 4.0), (2, 7, 64, 128, 2.0), (1, 5, 40, 100, 12.0)])
+def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape, monkeypatch):
     """The TMA path stages data differently but performs the SAME fp32 operations in the same
     order as the generic kernel, so the two must agree bit for bit (forward)."""
     from memc_b200 import synth
     B, C, H, W, sigma = shape
+    if C > 4:  # the channel-chunked variant is opt-in
+        monkeypatch.setenv("MEMC_FI_FWD_CFG", "30")
     t1, t2, t3, _ = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=9, device="cuda")
     outs = []
     for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
