@@ -1,0 +1,55 @@
+"""Host-resident batches through the adaptive-warp op: frame-pipelined H2D -> fwd (-> bwd) -> D2H.
+
+Frames are independent units of the path, so a batch that lives in pinned
+HOST memory is streamed through the GPU one frame at a time on a small ring of CUDA streams:
+while frame i computes, frame i+1 uploads and frame i-1 downloads (both PCIe directions and the
+SMs busy at once).  This is the public API bench.py's `e2e` number goes through.
+
+    pipe = FilterInterpolationHostPipeline(device, streams=3)
+    out, (gi1, gi2, gi3) = pipe.forward_backward(h_in1, h_flow, h_filt, h_gout, outputs=...)
+"""
+import torch
+
+from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+
+
+class FilterInterpolationHostPipeline(object):
+    def __init__(self, device, streams=3):
+        self.device = torch.device(device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(streams)))]
+        self.module = FilterInterpolationModule()
+
+    @staticmethod
+    def alloc_outputs(h_in1, h_flow, h_filt):
+        """Pinned host buffers for (output, gradinput1, gradinput2, gradinput3)."""
+        return tuple(torch.empty_like(t, device="cpu").pin_memory() for t in (h_in1, h_in1, h_flow, h_filt))
+
+    def forward_backward(self, h_in1, h_flow, h_filt, h_gout, outputs=None):
+        """All arguments are pinned CPU tensors [B, ...]; returns pinned CPU results.  Every frame's
+        inputs cross H2D and every frame's output + three gradients cross D2H on every call."""
+        for t in (h_in1, h_flow, h_filt, h_gout):
+            if t.is_cuda or not t.is_pinned():
+                raise ValueError("host pipeline expects pinned CPU tensors")
+        if outputs is None:
+            outputs = self.alloc_outputs(h_in1, h_flow, h_filt)
+        h_out, h_g1, h_g2, h_g3 = outputs
+        B = h_in1.size(0)
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for b in range(B):
+            s = self.streams[b % len(self.streams)]
+            with torch.cuda.stream(s):
+                a = h_in1[b:b + 1].to(self.device, non_blocking=True).requires_grad_()
+                f = h_flow[b:b + 1].to(self.device, non_blocking=True).requires_grad_()
+                k = h_filt[b:b + 1].to(self.device, non_blocking=True).requires_grad_()
+                g = h_gout[b:b + 1].to(self.device, non_blocking=True)
+                o = self.module(a, f, k)
+                g1, g2, g3 = torch.autograd.grad(o, (a, f, k), g)
+                h_out[b:b + 1].copy_(o.detach(), non_blocking=True)
+                h_g1[b:b + 1].copy_(g1, non_blocking=True)
+                h_g2[b:b + 1].copy_(g2, non_blocking=True)
+                h_g3[b:b + 1].copy_(g3, non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return h_out, (h_g1, h_g2, h_g3)

@@ -191,6 +191,27 @@ def test_filter_interpolation_backward_propagates_nonfinite_gradients(L):
     assert bool(torch.isnan(res[0][0]).any()) and bool(torch.isinf(res[0][0]).any())
 
 
+def test_host_pipeline_matches_direct_call(L):
+    """memc_b200.host_pipeline (pinned host batch, frame-pipelined over streams) == direct Module call."""
+    from memc_b200 import synth
+    from memc_b200.host_pipeline import FilterInterpolationHostPipeline
+    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+    B, C, H, W = 5, 3, 96, 160
+    t = synth.filter_interpolation_case(B, C, H, W, seed=21, device="cuda")
+    hs = [x.cpu().pin_memory() for x in t]
+    pipe = FilterInterpolationHostPipeline("cuda:0", streams=3)
+    h_out, (h1, h2, h3) = pipe.forward_backward(*hs)
+    torch.cuda.synchronize()
+    a, f, k = (x.clone().requires_grad_() for x in t[:3])
+    o = FilterInterpolationModule()(a, f, k)
+    g1, g2, g3 = torch.autograd.grad(o, (a, f, k), t[3])
+    torch.cuda.synchronize()
+    assert torch.equal(h_out, o.detach().cpu())
+    assert float((h1 - g1.cpu()).abs().max()) <= 1e-5 and torch.equal(h2, g2.cpu()) and torch.equal(h3, g3.cpu())
+    with pytest.raises(ValueError):
+        pipe.forward_backward(t[0], hs[1], hs[2], hs[3])   # device tensor where a pinned host tensor is expected
+
+
 def test_filter_interpolation_720p_vs_oracle(L):
     """One full 1280x720 frame (BASELINE.json configs[1] geometry) against the f64 oracle."""
     from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
