@@ -134,8 +134,9 @@ def cpu_reference_step(frames, threads):
 
 def cpu_threads():
     """The reference C code is single-threaded; frames are independent, so the CPU arm runs one
-    frame per host thread (capped at 128 to bound memory: ~0.2 GB of result buffers per frame in flight)."""
-    return max(1, min(os.cpu_count() or 1, 128))
+    frame per host thread (capped at 32: measured on the B200 host, 32 threads give 38.9 Mpx/s and 128 threads 24.2 Mpx/s --
+    the loops are memory-bound and oversubscribe the host's memory system beyond that)."""
+    return max(1, min(os.cpu_count() or 1, 32))
 
 
 def host_frames(n):
