@@ -1155,6 +1155,8 @@ using FwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  61 KB: 3 CTAs / SM
 using FwdC = Cfg<32, 16, 64, 40, 256, 3>;  //  67 KB: 3 CTAs / SM
 using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
 using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
+using FwdE2 = Cfg<32, 8, 64, 32, 128, 5>;  //  43 KB: 5 CTAs / SM, taller box (fewer fallback taps)
+using FwdE3 = Cfg<32, 8, 64, 28, 128, 5>;  //  40 KB
 using FwdF = Cfg<32, 8, 64, 24, 256, 5>;   //  37 KB: 5 CTAs / SM, 1 px / thread (<= 51 registers)
 using FwdG = Cfg<32, 16, 64, 32, 512, 3>;  //  61 KB: 3 CTAs / SM, 1 px / thread (<= 42 registers)
 using FwdL1 = Cfg<32, 8, 64, 24, 128, 5>;   // persistent-lite,  39 KB: 5 CTAs / SM
@@ -1172,7 +1174,9 @@ using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
 using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
 using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
 using BwdD = Cfg<32, 16, 64, 32, 512, 2>;  //  91 KB: 2 CTAs / SM, 1 px / thread
-using BWD_DEFAULT = BwdA;
+using BwdE = Cfg<32, 8, 64, 32, 256, 3>;   //  70 KB: 3 CTAs / SM, taller box
+using BwdF = Cfg<32, 8, 64, 28, 256, 3>;   //  64 KB
+using BWD_DEFAULT = BwdF;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 
 int env_int(const char* name) {
     const char* e = getenv(name);
@@ -1238,6 +1242,8 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 9: r = launch_fwd_persist<3, FwdP4>(stream, a); break;
             case 10: r = launch_fwd<3, FwdF>(stream, a); break;
             case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
+            case 17: r = launch_fwd<3, FwdE2>(stream, a); break;
+            case 18: r = launch_fwd<3, FwdE3>(stream, a); break;
             case 20: r = launch_fwd2<3, FwdE, false>(stream, a); break;
             case 21: r = launch_fwd2<3, FwdE, true>(stream, a); break;
             case 22: r = launch_fwd2<3, FwdC, true>(stream, a); break;
@@ -1272,6 +1278,8 @@ int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {
             case 2: return launch_bwd<3, true, BwdB>(stream, a);
             case 3: return launch_bwd<3, true, BwdC>(stream, a);
             case 4: return launch_bwd<3, true, BwdD>(stream, a);
+            case 5: return launch_bwd<3, true, BwdE>(stream, a);
+            case 6: return launch_bwd<3, true, BwdF>(stream, a);
             default: return launch_bwd<3, true, BWD_DEFAULT>(stream, a);
         }
     }

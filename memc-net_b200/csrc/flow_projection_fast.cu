@@ -26,13 +26,13 @@ namespace memc {
 
 namespace {
 
-constexpr int TW = 64, TH = 8, NT = 256, PPT = TW * TH / NT;  // source tile, 2 pixels / thread
-constexpr int SW = 96, SH = 24;                               // target box (pitch 96 = 3*32 words)
+constexpr int TW = 64, TH = 16, NT = 256, PPT = TW * TH / NT;  // source tile, 4 pixels / thread
+constexpr int SW = 96, SH = 32;                                // target box (pitch 96 = 3*32 words)
 constexpr int BOX = SW * SH;
 
 struct __align__(128) Smem {
-    float flow[2][TH][TW];  // 4 KB
-    int box[3][SH][SW];     // x, y (fixed point) and count: 27 KB; converted to fp32 in place
+    float flow[2][TH][TW];  // 8 KB
+    int box[3][SH][SW];     // x, y (fixed point) and count: 36 KB
     uint64_t bar;
     int bb[4];
     unsigned maxbits;
@@ -185,7 +185,7 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
 }
 
 // ------------------------------------------------------------------------------------
-// average + occupancy bit masks.  One CTA = one 32 x 32 pixel block, warp r = row r:
+// average + occupancy bit masks.  One CTA = one 128 x 32 pixel block:
 //   out /= count where count > 0 (my_lib_kernel.cu:1730-1736), and
 //   rowmask[b][y][x/32]  bit (x%32) = count[b][y][x] > 0      (32 pixels of a row per word)
 //   colmask[b][y/32][x]  bit (y%32) = count[b][y][x] > 0      (32 pixels of a column per word)
@@ -196,33 +196,49 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
 __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict__ out, const float* __restrict__ count,
                                                               unsigned* __restrict__ rowmask, unsigned* __restrict__ colmask,
                                                               int W, int H, int Wt, int Ht, int64_t out_c) {
-    __shared__ unsigned rw[32];
+    // CTA = 128 x 32 pixels: warp w handles rows w, w+8, w+16, w+24; a lane owns 4 consecutive
+    // pixels (128-bit accesses; W % 4 == 0 is a precondition of the fast path)
+    __shared__ unsigned rw[32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + lane;
+    const int x = blockIdx.x * 128 + lane * 4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // 8 warps x 4 rows = the block's 32 rows
+    for (int k = 0; k < 4; ++k) {
         const int r = warp + 8 * k, y = blockIdx.y * 32 + r;
-        float c = 0.f;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (x < W && y < H) {
             const int64_t o = (int64_t)y * W + x;
-            c = count[o];
-            if (c > 0.f) {
-                out[o] = out[o] / c;
-                out[out_c + o] = out[out_c + o] / c;
+            c = *reinterpret_cast<const float4*>(count + o);
+            if (c.x > 0.f || c.y > 0.f || c.z > 0.f || c.w > 0.f) {
+                float4 vx = *reinterpret_cast<float4*>(out + o), vy = *reinterpret_cast<float4*>(out + out_c + o);
+                if (c.x > 0.f) { vx.x /= c.x; vy.x /= c.x; }
+                if (c.y > 0.f) { vx.y /= c.y; vy.y /= c.y; }
+                if (c.z > 0.f) { vx.z /= c.z; vy.z /= c.z; }
+                if (c.w > 0.f) { vx.w /= c.w; vy.w /= c.w; }
+                *reinterpret_cast<float4*>(out + o) = vx;
+                *reinterpret_cast<float4*>(out + out_c + o) = vy;
             }
         }
-        const unsigned word = __ballot_sync(0xffffffffu, c > 0.f);
-        if (lane == 0) {
-            rw[r] = word;
-            if (y < H) rowmask[(int64_t)y * Wt + blockIdx.x] = word;
+        // nibble of this lane -> the 32-pixel word of its 8-lane group (bit = pixel x % 32)
+        unsigned nib = (c.x > 0.f ? 1u : 0u) | (c.y > 0.f ? 2u : 0u) | (c.z > 0.f ? 4u : 0u) | (c.w > 0.f ? 8u : 0u);
+        unsigned word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((lane & 7) == 0) {
+            const int wi = blockIdx.x * 4 + (lane >> 3);
+            rw[r][lane >> 3] = word;
+            if (y < H && wi < Wt) rowmask[(int64_t)y * Wt + wi] = word;
         }
     }
     __syncthreads();
-    if (warp == 0 && x < W) {  // column words, stored [y/32][x] so that a warp's loads coalesce
-        unsigned col = 0;
+    if (threadIdx.x < 128) {  // column words, stored [y/32][x] so that a warp's loads coalesce
+        const int cx = blockIdx.x * 128 + threadIdx.x;
+        if (cx < W) {
+            unsigned col = 0;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) col |= ((rw[k] >> lane) & 1u) << k;
-        colmask[(int64_t)blockIdx.y * W + x] = col;
+            for (int k = 0; k < 32; ++k) col |= ((rw[k][threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u) << k;
+            colmask[(int64_t)blockIdx.y * W + cx] = col;
+        }
     }
 }
 
@@ -354,7 +370,7 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     }
     unsigned* rowmask = masks;
     unsigned* colmask = masks + n_row;
-    const dim3 mgrid(Wt, Ht, 1);
+    const dim3 mgrid((a.W + 127) / 128, Ht, 1);
     int rc = 1;
     for (int b = 0; b < a.B && rc == 1; ++b) {
         float* outb = a.outp + (int64_t)b * a.out.b;

@@ -12,8 +12,8 @@ from tools.kbench import timeit, fi_calls, _peak
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--out", default="gpurun_out/sweep_fi.json")
-ap.add_argument("--fwd", default="5,20,21,22,23,24")
-ap.add_argument("--bwd", default="0")
+ap.add_argument("--fwd", default="5,17,18")
+ap.add_argument("--bwd", default="0,5,6")
 ap.add_argument("--bwd-int", action="store_true")
 args = ap.parse_args()
 lib.load()
