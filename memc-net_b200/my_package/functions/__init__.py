@@ -1,0 +1,1 @@
+"""Re-authored (static) autograd Functions behind the reference class names."""

@@ -1,0 +1,1 @@
+"""nn.Module wrappers of the motion-compensation ops (names fixed by the reference networks)."""
