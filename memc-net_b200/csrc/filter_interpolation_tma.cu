@@ -358,16 +358,8 @@ int launch_fwd2(cudaStream_t stream, const FiArgs& a) {
     if (!tma::make_map_nchw(&mpref, a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, PREF_W, PREF_H, a.C,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return 0;
-    static bool configured = false;
     constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_fwd_tma2_kernel<C, K, PFL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(fi_fwd_tma2_kernel<C, K, PFL2>, smem)) return 0;
     dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
     fi_fwd_tma2_kernel<C, K, PFL2><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], mpref, a);
     count_launch();
@@ -524,16 +516,8 @@ int launch_fwd_chunked(cudaStream_t stream, const FiArgs& a) {
         !tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, K::SW, K::SH, CBK,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return 0;
-    static bool configured = false;
     constexpr size_t smem = (size_t)chunked_smem<K>() + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_fwd_tma_chunked_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(fi_fwd_tma_chunked_kernel<K>, smem)) return 0;
     dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
     fi_fwd_tma_chunked_kernel<K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a4);
     count_launch();
@@ -662,19 +646,12 @@ int launch_fwd_persist(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
     CUtensorMap m[5];
     if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    static int configured = 0, n_sm = 0;
     constexpr size_t smem = (size_t)persist_smem<K>(C) + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_fwd_persist_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        configured = 1;
-    }
+    if (!ensure_dynamic_smem(fi_fwd_persist_kernel<C, K>, smem)) return 0;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) return 0;
     const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
     const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
     if (n_tiles > 0x7fffffffLL) return 0;
@@ -793,19 +770,12 @@ int launch_fwd_pl(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
     CUtensorMap m[5];
     if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    static int configured = 0, n_sm = 0;
     constexpr size_t smem = (size_t)pl_smem<K>(C, PF) + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_fwd_pl_kernel<C, K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        configured = 1;
-    }
+    if (!ensure_dynamic_smem(fi_fwd_pl_kernel<C, K, PF>, smem)) return 0;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) return 0;
     const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
     const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
     if (n_tiles > 0x7fffffffLL) return 0;
@@ -1110,16 +1080,8 @@ int launch_fwd(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
     CUtensorMap m[5];
     if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    static bool configured = false;  // per template instance
     constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_fwd_tma_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(fi_fwd_tma_kernel<C, K>, smem)) return 0;
     dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
     fi_fwd_tma_kernel<C, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a);
     count_launch();
@@ -1131,16 +1093,8 @@ int launch_bwd(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
     CUtensorMap m[5];
     if (!make_maps(a, true, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    static bool configured = false;
     constexpr size_t smem = (size_t)make_bwd_layout<K>(C).total + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fi_bwd_tma_kernel<C, OW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(fi_bwd_tma_kernel<C, OW, K>, smem)) return 0;
     dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
     fi_bwd_tma_kernel<C, OW, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[4], m[2], m[3], a);
     count_launch();

@@ -89,40 +89,54 @@ __global__ void __launch_bounds__(BX* BY) fp_fillhole_kernel(const FpArgs p) {
 }
 
 // ----------------------------------------------------------------------------- backward
+// Two pixels per thread (rows h and h + BY of a 32 x 16 block): the op is a dependent chain
+// flow -> 12 gathers -> store, so the second pixel's loads double the bytes in flight per thread.
 template <bool OVERWRITE>
 __global__ void __launch_bounds__(BX* BY, 6) fp_bwd_kernel(const FpArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
-    const int h = blockIdx.y * BY + threadIdx.y;
+    const int h0 = blockIdx.y * (2 * BY) + threadIdx.y;
     const int b = blockIdx.z;
-    if (w >= p.W || h >= p.H) return;
-    const float* fl = p.flowp + b * p.flow.b + h * p.flow.h + w;
-    const float fx = ldg_stream(fl);
-    const float fy = ldg_stream(fl + p.flow.c);
-    const float x2 = (float)w + fx, y2 = (float)h + fy;
-    float* gx = p.gip + b * p.gi.b + h * p.gi.h + w;
-    float* gy = gx + p.gi.c;
-    if (!fp_valid(x2, y2, p.W, p.H)) {
-        if (OVERWRITE) { stg_stream(gx, 0.f); stg_stream(gy, 0.f); }
-        return;
+    if (w >= p.W) return;
+    float fx[2], fy[2];
+    bool in[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int h = h0 + k * BY;
+        in[k] = h < p.H;
+        const float* fl = p.flowp + b * p.flow.b + (int64_t)min(h, p.H - 1) * p.flow.h + w;
+        fx[k] = ldg_stream(fl);
+        fy[k] = ldg_stream(fl + p.flow.c);
     }
-    const int L = (int)x2, T = (int)y2;
-    const int R = min(L + 1, p.W - 1), Bm = min(T + 1, p.H - 1);
     const float* cn = p.countp + b * p.count.b;
     const float* gox = p.goutp + b * p.out.b;
     const float* goy = gox + p.out.c;
-    const int64_t oT = (int64_t)T * p.out.h, oB = (int64_t)Bm * p.out.h;
-    const int64_t cT = (int64_t)T * p.count.h, cB = (int64_t)Bm * p.count.h;
-    const float c0 = __ldg(cn + cT + L), c1 = __ldg(cn + cT + R);
-    const float c2 = __ldg(cn + cB + L), c3 = __ldg(cn + cB + R);
-    // same order as my_lib_kernel.cu:1879-1896: ((( -a0/c0 ) - a1/c1) - a2/c2) - a3/c3
-    float sx = OVERWRITE ? 0.f : *gx;
-    float sy = OVERWRITE ? 0.f : *gy;
-    sx += -__ldg(gox + oT + L) / c0; sx += -__ldg(gox + oT + R) / c1;
-    sx += -__ldg(gox + oB + L) / c2; sx += -__ldg(gox + oB + R) / c3;
-    sy += -__ldg(goy + oT + L) / c0; sy += -__ldg(goy + oT + R) / c1;
-    sy += -__ldg(goy + oB + L) / c2; sy += -__ldg(goy + oB + R) / c3;
-    *gx = sx;
-    *gy = sy;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (!in[k]) continue;
+        const int h = h0 + k * BY;
+        const float x2 = (float)w + fx[k], y2 = (float)h + fy[k];
+        float* gx = p.gip + b * p.gi.b + (int64_t)h * p.gi.h + w;
+        float* gy = gx + p.gi.c;
+        if (!fp_valid(x2, y2, p.W, p.H)) {
+            if (OVERWRITE) { stg_stream(gx, 0.f); stg_stream(gy, 0.f); }
+            continue;
+        }
+        const int L = (int)x2, T = (int)y2;
+        const int R = min(L + 1, p.W - 1), Bm = min(T + 1, p.H - 1);
+        const int64_t oT = (int64_t)T * p.out.h, oB = (int64_t)Bm * p.out.h;
+        const int64_t cT = (int64_t)T * p.count.h, cB = (int64_t)Bm * p.count.h;
+        const float c0 = __ldg(cn + cT + L), c1 = __ldg(cn + cT + R);
+        const float c2 = __ldg(cn + cB + L), c3 = __ldg(cn + cB + R);
+        const float ax0 = __ldg(gox + oT + L), ax1 = __ldg(gox + oT + R), ax2 = __ldg(gox + oB + L), ax3 = __ldg(gox + oB + R);
+        const float ay0 = __ldg(goy + oT + L), ay1 = __ldg(goy + oT + R), ay2 = __ldg(goy + oB + L), ay3 = __ldg(goy + oB + R);
+        // same order as my_lib_kernel.cu:1879-1896: ((( -a0/c0 ) - a1/c1) - a2/c2) - a3/c3
+        float sx = OVERWRITE ? 0.f : *gx;
+        float sy = OVERWRITE ? 0.f : *gy;
+        sx += -ax0 / c0; sx += -ax1 / c1; sx += -ax2 / c2; sx += -ax3 / c3;
+        sy += -ay0 / c0; sy += -ay1 / c1; sy += -ay2 / c2; sy += -ay3 / c3;
+        *gx = sx;
+        *gy = sy;
+    }
 }
 
 // average (+ fill-hole) over frames [b0, b0 + nb) of `a` -- also used by the fast path
@@ -173,7 +187,7 @@ static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
 
 static int fp_backward(cudaStream_t stream, const FpArgs& a, int flags) {
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return 0;
-    dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
+    dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + 2 * BY - 1) / (2 * BY), a.B);
     if (flags & MEMC_B200_OVERWRITE) fp_bwd_kernel<true><<<grid, block, 0, stream>>>(a);
     else fp_bwd_kernel<false><<<grid, block, 0, stream>>>(a);
     count_launch();

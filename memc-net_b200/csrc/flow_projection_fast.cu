@@ -348,15 +348,8 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     if (!tma::make_map_nchw(&m_flow, a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, TH, 2,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return 0;
-    static bool configured = false;
     const size_t smem = sizeof(Smem) + 128;
-    if (!configured) {
-        if (cudaFuncSetAttribute(fp_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(fp_splat_kernel, smem)) return 0;
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
     // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
     const int Wt = (a.W + 31) / 32, Ht = (a.H + 31) / 32;

@@ -44,6 +44,14 @@ static inline int check_launch(const char* what) {
     return 0;
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory once per device (function attributes are
+// per device; one process may drive several).  Returns false if the device refuses.
+bool ensure_dynamic_smem_impl(const void* kernel, size_t bytes);  // runtime.cu: table keyed by (kernel, device)
+template <class KernelT>
+inline bool ensure_dynamic_smem(KernelT* kernel, size_t bytes) {
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // zero-fill a [B,C,H,W] strided tensor on `stream` (memset when dense, kernel otherwise)
 int zero_fill(cudaStream_t stream, float* p, View v, int B, int C, int H, int W);
 

@@ -15,6 +15,22 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* p, View v, int C,
     p[b * v.b + c * v.c + (int64_t)blockIdx.y * v.h + w] = 0.0f;
 }
 
+bool ensure_dynamic_smem_impl(const void* kernel, size_t bytes) {
+    struct Entry { const void* fn; int dev; };
+    static Entry done[512];
+    static int n_done = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    for (int i = 0; i < n_done; ++i)
+        if (done[i].fn == kernel && done[i].dev == dev) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (n_done < 512) done[n_done++] = Entry{kernel, dev};
+    return true;
+}
+
 int zero_fill(cudaStream_t stream, float* p, View v, int B, int C, int H, int W) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
     const bool dense = v.h == W && (C == 1 || v.c == (int64_t)H * W) && (B == 1 || v.b == (int64_t)C * H * W);

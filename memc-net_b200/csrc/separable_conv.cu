@@ -30,25 +30,36 @@ struct ScArgs {
 
 constexpr int BX = 32, BY = 8;
 
+// Two output pixels per thread (rows h and h + BY): twice the independent loads in flight.
 __global__ void __launch_bounds__(BX* BY) sc_fwd_kernel(const ScArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
-    const int h = blockIdx.y * BY + threadIdx.y;
+    const int h0 = blockIdx.y * (2 * BY) + threadIdx.y;
     const int b = blockIdx.z;
     const int fs = p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
-    if (w >= Wo || h >= Ho) return;
-    const float* vp = p.vertp + b * p.vert.b + h * p.vert.h + w;
-    const float* hp = p.horizp + b * p.horiz.b + h * p.horiz.h + w;
-    const float* img = p.in1p + b * p.in1.b + h * p.in1.h + w;
-    float* ob = p.outp + b * p.out.b + h * p.out.h + w;
-    for (int c = 0; c < p.C; ++c, img += p.in1.c) {
-        float acc = 0.f;
+    if (w >= Wo || h0 >= Ho) return;
+    const int h1 = min(h0 + BY, Ho - 1);          // second row (clamped: recomputed, not stored, if out of range)
+    const bool two = h0 + BY < Ho;
+    const float* vp0 = p.vertp + b * p.vert.b + h0 * p.vert.h + w;
+    const float* hp0 = p.horizp + b * p.horiz.b + h0 * p.horiz.h + w;
+    const float* vp1 = p.vertp + b * p.vert.b + h1 * p.vert.h + w;
+    const float* hp1 = p.horizp + b * p.horiz.b + h1 * p.horiz.h + w;
+    const float* img0 = p.in1p + b * p.in1.b + h0 * p.in1.h + w;
+    const float* img1 = p.in1p + b * p.in1.b + h1 * p.in1.h + w;
+    float* ob0 = p.outp + b * p.out.b + h0 * p.out.h + w;
+    float* ob1 = p.outp + b * p.out.b + h1 * p.out.h + w;
+    for (int c = 0; c < p.C; ++c, img0 += p.in1.c, img1 += p.in1.c) {
+        float acc0 = 0.f, acc1 = 0.f;
         for (int y = 0; y < fs; ++y) {
-            const float vy = __ldg(vp + y * p.vert.c);
-            const float* row = img + y * p.in1.h;
-            for (int x = 0; x < fs; ++x)
-                acc += __ldg(row + x) * vy * __ldg(hp + x * p.horiz.c);  // (t1*t2)*t3 as the reference
+            const float vy0 = __ldg(vp0 + y * p.vert.c), vy1 = __ldg(vp1 + y * p.vert.c);
+            const float* row0 = img0 + y * p.in1.h;
+            const float* row1 = img1 + y * p.in1.h;
+            for (int x = 0; x < fs; ++x) {  // (t1*t2)*t3 as the reference
+                acc0 += __ldg(row0 + x) * vy0 * __ldg(hp0 + x * p.horiz.c);
+                acc1 += __ldg(row1 + x) * vy1 * __ldg(hp1 + x * p.horiz.c);
+            }
         }
-        stg_stream(ob + c * p.out.c, acc);
+        stg_stream(ob0 + c * p.out.c, acc0);
+        if (two) stg_stream(ob1 + c * p.out.c, acc1);
     }
 }
 
@@ -120,7 +131,7 @@ static int sc_forward(cudaStream_t stream, const ScArgs& a, int flags) {
     if (a.fs <= 0) return -1;
     const int Ho = a.H - a.fs + 1, Wo = a.W - a.fs + 1;
     if (a.B <= 0 || a.C <= 0 || Ho <= 0 || Wo <= 0) return 0;
-    dim3 block(BX, BY, 1), grid((Wo + BX - 1) / BX, (Ho + BY - 1) / BY, a.B);
+    dim3 block(BX, BY, 1), grid((Wo + BX - 1) / BX, (Ho + 2 * BY - 1) / (2 * BY), a.B);
     sc_fwd_kernel<<<grid, block, 0, stream>>>(a);
     count_launch();
     return check_launch("SeparableConv forward");
