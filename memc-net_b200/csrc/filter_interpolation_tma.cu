@@ -525,144 +525,9 @@ int launch_fwd_chunked(cudaStream_t stream, const FiArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------
-// persistent forward: each CTA walks tiles blockIdx.x, blockIdx.x + grid, ... (raster order,
-// so concurrently running CTAs work on neighbouring tiles and share image rows in L2) with a
-// two-stage ring for (filter tile, image box) and a three-slot ring for the flow tile.  The
-// flow of tile i+2 and the filter/image of tile i+1 are in flight while tile i is computed:
-// the dependent chain flow -> bounding box -> image box is off the critical path.
-// ------------------------------------------------------------------------------------
-template <class K>
-__host__ __device__ constexpr int persist_smem(int C) {
-    return 2 * (16 * K::TH * K::TW * 4 + C * K::SH * K::SW * 4) + 3 * (2 * K::TH * K::TW * 4) + 256;
-}
-
-template <int C, class K>
-__global__ void __launch_bounds__(K::NT, K::MINB)
-fi_fwd_persist_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                      const __grid_constant__ CUtensorMap m_img, const FiArgs p, const int tiles_x,
-                      const int tiles_y, const int n_tiles) {
-    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
-    constexpr int FILT_B = 16 * TH * TW * 4, IMG_B = C * SH * SW * 4, FLOW_B = 2 * TH * TW * 4;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    unsigned char* const sm_filt0 = sm;                      // 2 stages, FILT_B apart
-    unsigned char* const sm_img0 = sm + 2 * FILT_B;          // 2 stages, IMG_B apart
-    unsigned char* const sm_flow = sm + 2 * FILT_B + 2 * IMG_B;  // 3 slots
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_flow + 3 * FLOW_B);  // [0,1] filter, [2,3] image, [4,5,6] flow
-    int* s_bb = reinterpret_cast<int*>(bars + 8);                        // 2 x 4 (double buffered)
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-    if (n == 0) return;
-    const int W = p.W, H = p.H;
-    const int per_frame = tiles_x * tiles_y;
-
-    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
-        const int t = (int)blockIdx.x + i * G;
-        b = t / per_frame;
-        const int r = t - b * per_frame;
-        const int ty = r / tiles_x;
-        x0 = (r - ty * tiles_x) * TW;
-        y0 = ty * TH;
-    };
-    auto issue_flow = [&](int i) {  // thread 0 only
-        int x0, y0, b;
-        tile_origin(i, x0, y0, b);
-        uint64_t* bar = &bars[4 + i % 3];
-        tma::mbar_expect_tx(bar, FLOW_B);
-        tma::load_4d(sm_flow + (i % 3) * FLOW_B, &m_flow, x0, y0, 0, b, bar);
-    };
-    auto issue_stage = [&](int i, int bx, int by) {  // thread 0 only: filter tile + image box of tile i
-        int x0, y0, b;
-        tile_origin(i, x0, y0, b);
-        const int st = i & 1;
-        tma::mbar_expect_tx(&bars[st], FILT_B);
-        tma::load_4d(sm_filt0 + st * FILT_B, &m_filt, x0, y0, 0, b, &bars[st]);
-        tma::mbar_expect_tx(&bars[2 + st], IMG_B);
-        tma::load_4d(sm_img0 + st * IMG_B, &m_img, bx, by, 0, b, &bars[2 + st]);
-    };
-
-    if (tid == 0) {
-        for (int k = 0; k < 7; ++k) tma::mbar_init(&bars[k], 1);
-        for (int k = 0; k < 8; ++k) s_bb[k] = (k & 1) ? INT_MIN : INT_MAX;  // {min,max,min,max} x 2
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        issue_flow(0);
-        if (n > 1) issue_flow(1);
-    }
-    // box of tile 0
-    int bx_cur, by_cur;
-    {
-        int x0, y0, b;
-        tile_origin(0, x0, y0, b);
-        tma::mbar_wait(&bars[4], 0, 21);
-        tile_box<K>(reinterpret_cast<const float*>(sm_flow), s_bb, x0, y0, W, H, lane, warp, bx_cur, by_cur);
-        if (tid == 0) issue_stage(0, bx_cur, by_cur);
-    }
-
-    for (int i = 0; i < n; ++i) {
-        int bx_next = 0, by_next = 0;
-        if (i + 1 < n) {  // (A) look ahead: box of tile i+1, launch its loads, and the flow of tile i+2
-            int x0, y0, b;
-            tile_origin(i + 1, x0, y0, b);
-            tma::mbar_wait(&bars[4 + (i + 1) % 3], ((i + 1) / 3) & 1, 22);
-            tile_box<K>(reinterpret_cast<const float*>(sm_flow + ((i + 1) % 3) * FLOW_B), s_bb + 4 * ((i + 1) & 1), x0,
-                        y0, W, H, lane, warp, bx_next, by_next);
-            if (tid == 0) {
-                tma::fence_proxy_async();  // stage (i+1)&1 / flow slot (i+2)%3 were last READ by generic loads
-                issue_stage(i + 1, bx_next, by_next);
-                if (i + 2 < n) issue_flow(i + 2);
-            }
-        }
-        // (B) compute tile i
-        {
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            const int st = i & 1;
-            tma::mbar_wait(&bars[st], (i >> 1) & 1, 23);
-            tma::mbar_wait(&bars[2 + st], (i >> 1) & 1, 24);
-            fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm_filt0 + st * FILT_B),
-                                   reinterpret_cast<const float*>(sm_flow + (i % 3) * FLOW_B),
-                                   reinterpret_cast<const float*>(sm_img0 + st * IMG_B), x0, y0, b, bx_cur, by_cur,
-                                   lane, warp);
-        }
-        // (R) recycle the bounding-box scratch of tile i (used again by tile i+2), then close the iteration:
-        // after this barrier nobody reads stage i&1 or flow slot i%3 any more.
-        if (tid == 0) {
-            int* bb = s_bb + 4 * (i & 1);
-            bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;
-        }
-        __syncthreads();
-        bx_cur = bx_next;
-        by_cur = by_next;
-    }
-}
-
-template <int C, class K>
-int launch_fwd_persist(cudaStream_t stream, const FiArgs& a) {
-    if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[5];
-    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    constexpr size_t smem = (size_t)persist_smem<K>(C) + 128;
-    if (!ensure_dynamic_smem(fi_fwd_persist_kernel<C, K>, smem)) return 0;
-    int dev = 0, n_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) return 0;
-    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
-    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
-    if (n_tiles > 0x7fffffffLL) return 0;
-    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
-    fi_fwd_persist_kernel<C, K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
-    count_launch();
-    return check_launch("FilterInterpolation forward (persistent TMA)") == 0 ? 1 : -1;
-}
-
-// ------------------------------------------------------------------------------------
-// persistent-lite forward: like the one-tile-per-CTA kernel (same smem budget, so the same
+// persistent-lite forward (experiment, selectable with MEMC_FI_FWD_CFG=12..16; a fully double-buffered
+// persistent ring was also built and measured slower still, see profiles/r01_fi_tile_sweep.md):
+// like the one-tile-per-CTA kernel (same smem budget, so the same
 // number of CTAs per SM), but every CTA walks tiles blockIdx.x, +grid, ... and PREFETCHES the
 // small flow tile (optionally also the filter tile) of its next tile while it computes the
 // current one.  The dependent chain per tile shrinks from
@@ -1117,10 +982,6 @@ using FwdL1 = Cfg<32, 8, 64, 24, 128, 5>;   // persistent-lite,  39 KB: 5 CTAs /
 using FwdL2 = Cfg<32, 8, 64, 24, 128, 4>;   // persistent-lite + filter prefetch, 55 KB: 4 CTAs / SM
 using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs / SM
 using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
-using FwdP1 = Cfg<32, 16, 64, 40, 256, 1>;  // persistent, 137 KB: 1 CTA / SM
-using FwdP2 = Cfg<32, 8, 64, 22, 128, 3>;   // persistent,  73 KB: 3 CTAs / SM
-using FwdP3 = Cfg<64, 16, 96, 28, 512, 1>;  // persistent, 215 KB: 1 CTA / SM
-using FwdP4 = Cfg<32, 16, 64, 32, 256, 1>;  // persistent, 125 KB: 1 CTA / SM
 using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
 using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
 using FWD_DEFAULT = FwdE;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
@@ -1190,10 +1051,6 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 3: r = launch_fwd<3, FwdC>(stream, a); break;
             case 4: r = launch_fwd<3, FwdD>(stream, a); break;
             case 5: r = launch_fwd<3, FwdE>(stream, a); break;
-            case 6: r = launch_fwd_persist<3, FwdP1>(stream, a); break;
-            case 7: r = launch_fwd_persist<3, FwdP2>(stream, a); break;
-            case 8: r = launch_fwd_persist<3, FwdP3>(stream, a); break;
-            case 9: r = launch_fwd_persist<3, FwdP4>(stream, a); break;
             case 10: r = launch_fwd<3, FwdF>(stream, a); break;
             case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
             case 17: r = launch_fwd<3, FwdE2>(stream, a); break;
