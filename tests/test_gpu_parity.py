@@ -212,6 +212,45 @@ def test_host_pipeline_matches_direct_call(L):
         pipe.forward_backward(t[0], hs[1], hs[2], hs[3])   # device tensor where a pinned host tensor is expected
 
 
+def test_ops_are_cuda_graph_capturable(L):
+    """The C ABI only enqueues work on the caller's stream (tensor maps travel as kernel
+    parameters, the FlowProjection scratch is stream-ordered), so whole steps can be captured
+    in a CUDA graph and replayed -- the launch-bound small-frame regime wants exactly that."""
+    from memc_b200 import synth
+    B, C, H, W = 2, 3, 96, 160
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, seed=31, device="cuda")
+    out, g1, g2, g3 = torch.empty_like(t1), torch.empty_like(t1), torch.empty_like(t2), torch.empty_like(t3)
+    count, proj = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(t2)
+    S, P = L.strides_of, L.ptr
+
+    def step():
+        st = L.stream_ptr(t1)
+        L.call("memc_b200_filter_interpolation_forward", st, B, C, H, W, 4, S(t1), S(t2), S(t3), S(out),
+               P(t1), P(t2), P(t3), P(out), L.OVERWRITE)
+        L.call("memc_b200_filter_interpolation_backward", st, B, C, H, W, 4, S(t1), S(t2), S(t3), S(tg),
+               S(g1), S(g2), S(g3), P(t1), P(t2), P(t3), P(tg), P(g1), P(g2), P(g3), L.OVERWRITE)
+        L.call("memc_b200_flow_projection_forward", st, B, H, W, 1, S(t2), S(count), S(proj),
+               P(t2), P(count), P(proj), L.OVERWRITE)
+
+    step()
+    torch.cuda.synchronize()
+    eager = [x.clone() for x in (out, g1, g2, g3, count, proj)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        step()                       # warm-up on the capture stream (function attributes, pool)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+    for x in (out, g1, g2, g3, count, proj):
+        x.fill_(float("nan"))
+    graph.replay()
+    torch.cuda.synchronize()
+    for got, exp, name in zip((out, g1, g2, g3, count, proj), eager, ("out", "gi1", "gi2", "gi3", "count", "proj")):
+        assert float((got - exp).abs().max()) <= 1e-5 * max(1.0, float(exp.abs().max())), name
+
+
 def test_filter_interpolation_720p_vs_oracle(L):
     """One full 1280x720 frame (BASELINE.json configs[1] geometry) against the f64 oracle."""
     from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
