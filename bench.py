@@ -280,6 +280,23 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop()
         clocks["window"] = "warm-up + timed steps + e2e steps (+ identical untimed steps up to 1.5 s)"
 
+    # ---- optional exchange: all-gather of the output batch over NCCL / NVLink, timed ALONE
+    # after the timed region -- the path itself has no data-path collective (frames are independent)
+    t_gather = None
+    if distributed:
+        bufs = [torch.empty_like(out) for _ in range(world)]
+        for _ in range(2):
+            dist.all_gather(bufs, out)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(5):
+            dist.all_gather(bufs, out)
+        q1.record()
+        torch.cuda.synchronize()
+        t_gather = q0.elapsed_time(q1) * 1e-3 / 5
+        del bufs
+
     # ---- max over ranks
     if distributed:
         tt = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd], device=dev, dtype=torch.float64)
@@ -316,6 +333,9 @@ def run_ours(args, rank, world, local_rank):
                          "mpx_s_per_gpu": px_step / t_fwd / 1e6},
     }
 
+    if t_gather is not None:
+        result["output_allgather"] = {"ms": t_gather * 1e3, "bytes_per_rank": out.numel() * 4,
+                                      "note": "NCCL all-gather of the output batch, timed alone; not part of value"}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = cpu_threads()

@@ -25,6 +25,11 @@
  *                             uninitialised buffers and skip its memsets;
  *        MEMC_B200_NO_FAST    force the generic (non-TMA) kernels (used by the tests to
  *                             cross-check the fast path);
+ *        MEMC_B200_FLOAT_ACCUM  FilterInterpolation backward: accumulate gradinput1 with fp32 shared
+ *                             atomics instead of the per-tile fixed point (slower; keeps fp32
+ *                             RELATIVE precision for gradients whose magnitude varies by many
+ *                             orders inside one 32x8 tile -- the fixed point guarantees an
+ *                             absolute error of ~2^-22 x the tile's largest contribution);
  *        MEMC_B200_NO_ZERO    with OVERWRITE: the caller has already zero-filled the
  *                             scatter targets (gradinput1 / count+output); lets bench.py
  *                             time the kernel apart from the memset.
@@ -55,6 +60,7 @@ typedef void *memc_stream_t; /* a cudaStream_t */
 #define MEMC_B200_OVERWRITE 1
 #define MEMC_B200_NO_FAST 2
 #define MEMC_B200_NO_ZERO 4
+#define MEMC_B200_FLOAT_ACCUM 8
 
 /* ---- library info ------------------------------------------------------------------ */
 MEMC_B200_API int memc_b200_abi_version(void);          /* bumped on any signature change            */

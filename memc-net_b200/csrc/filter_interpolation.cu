@@ -233,7 +233,9 @@ static int fi_forward(cudaStream_t stream, const FiArgs& a, int flags) {
     return check_launch("FilterInterpolation forward");
 }
 
-static int fi_backward(cudaStream_t stream, const FiArgs& a, int flags) {
+static int fi_backward(cudaStream_t stream, const FiArgs& a_in, int flags) {
+    FiArgs a = a_in;
+    a.flags = flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     if (a.fs <= 0) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;

@@ -885,7 +885,7 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     const float M = __uint_as_float(*s_maxbits);
     const bool finite = *s_maxbits < 0x7f800000u;
     float scale = 0.f, inv_scale = 0.f;
-    if (finite && M > 0.f) {
+    if (finite && M > 0.f && !(p.flags & MEMC_B200_FLOAT_ACCUM)) {
         int ex;
         frexpf(M, &ex);  // M < 2^ex
         constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;  // ceil(log2(TW*TH))

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmemc_b200.so")
 OVERWRITE = 1  # MEMC_B200_OVERWRITE
 NO_FAST = 2    # MEMC_B200_NO_FAST
 NO_ZERO = 4    # MEMC_B200_NO_ZERO
+FLOAT_ACCUM = 8  # MEMC_B200_FLOAT_ACCUM
 
 _lib = None
 

@@ -212,6 +212,31 @@ def test_host_pipeline_matches_direct_call(L):
         pipe.forward_backward(t[0], hs[1], hs[2], hs[3])   # device tensor where a pinned host tensor is expected
 
 
+def test_filter_interpolation_backward_float_accum_flag(L):
+    """MEMC_B200_FLOAT_ACCUM keeps fp32 relative precision when gradient magnitudes differ by
+    many orders inside a tile (the default fixed point only bounds the ABSOLUTE error by
+    ~2^-22 x the tile's largest contribution)."""
+    from memc_b200 import synth
+    B, C, H, W = 1, 3, 64, 96
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, sigma=1.0, seed=41, device="cuda")
+    tg.mul_(1e-4)
+    tg[0, :, 20, 30] = 1e4          # one huge gradient in a tile of tiny ones
+    res = {}
+    for name, flags in (("generic", L.OVERWRITE | L.NO_FAST), ("fixed", L.OVERWRITE), ("float", L.OVERWRITE | L.FLOAT_ACCUM)):
+        g1, g2, g3 = torch.empty_like(t1), torch.empty_like(t2), torch.empty_like(t3)
+        L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(tg), L.strides_of(g1), L.strides_of(g2),
+               L.strides_of(g3), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(tg), L.ptr(g1), L.ptr(g2), L.ptr(g3), flags)
+        res[name] = g1
+    torch.cuda.synchronize()
+    ref = res["generic"]
+    small = ref.abs() < 1e-3                      # cells that only received tiny contributions
+    rel = lambda a: float(((a - ref).abs() / ref.abs().clamp_min(1e-12))[small & (ref != 0)].max())
+    assert float((res["fixed"] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())   # absolute bound holds
+    assert rel(res["float"]) < 1e-3                                                     # relative precision kept
+    assert float((res["float"] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
 def test_ops_are_cuda_graph_capturable(L):
     """The C ABI only enqueues work on the caller's stream (tensor maps travel as kernel
     parameters, the FlowProjection scratch is stream-ordered), so whole steps can be captured
