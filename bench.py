@@ -179,7 +179,6 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from memc_b200 import lib, synth
-    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this package has no CPU path)")

@@ -14,7 +14,6 @@ Shape / stride checks restate my_lib_cuda.c (line refs per function).  The launc
 the reference-named extern "C" launchers of libmemc_b200.so.  CPU tensors are rejected
 loudly: this build has no CPU path (the reference's *_cpu_* symbols are not provided).
 """
-import ctypes
 import math
 
 from memc_b200 import lib as _lib

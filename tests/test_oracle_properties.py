@@ -1,7 +1,6 @@
 """Analytic known-answer / property tests of the oracle; they hold
 for the reference by construction of its algorithm and need no reference binary."""
 import numpy as np
-import pytest
 
 from oracle import cpu, pyloop
 

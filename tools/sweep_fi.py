@@ -6,7 +6,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "memc-net_b200")):
     sys.path.insert(0, p)
-from memc_b200 import lib, synth
+from memc_b200 import lib
 from tools.kbench import timeit, fi_calls, _peak
 
 ap = argparse.ArgumentParser()
