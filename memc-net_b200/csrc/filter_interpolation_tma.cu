@@ -45,16 +45,8 @@ struct Cfg {
     static_assert(TW % 32 == 0 && SW % 32 == 0 && (TW * TH) % NT == 0 && NT % 32 == 0, "bad tile config");
 };
 
-__device__ __forceinline__ int warp_min(int v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
+__device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }  // REDUX.MIN.S32
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
 struct Layout {
@@ -159,6 +151,57 @@ __device__ __forceinline__ void tile_box_warp(const float* s_flow, int x0, int y
 // ====================================================================================
 // forward
 // ====================================================================================
+// A pixel whose window touches the image border or leaves the staged box (a few lanes of ~5 % of
+// the warps on the benchmark field): per-tap clamping, box or global source per tap.  Run AFTER the
+// fast pixels of the thread (nothing of the fast path is live any more, so it does not add to the
+// register budget), one window row per iteration with the channel loop innermost: ~400 warp
+// instructions instead of ~2000 for a tap-by-tap loop per channel.
+template <int C, class K>
+__device__ __forceinline__ void fwd_slow_pixel(const FiArgs& p, const float* wcol, const int wstride, const float* s_img,
+                                               const float* in1b, int L, int T, int bx, int by, float a, float bt,
+                                               float (&res)[C]) {
+    constexpr int SW = K::SW, SH = K::SH;
+    const int W = p.W, H = p.H;
+    float q[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) q[c][0] = q[c][1] = q[c][2] = q[c][3] = 0.f;
+    // two window rows (8 taps x C loads, box or L2) are in flight at a time: two memory round trips
+    // per slow pixel; the quadrant of a tap is static
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+        float v[2][4][C], wt[2][4];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * jp + jj;
+            const int cy = clampi(T + j, 0, H - 1);
+            const int uy = cy - by;
+            const bool row_in = (unsigned)uy < (unsigned)SH;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cx = clampi(L + i, 0, W - 1);
+                const int ux = cx - bx;
+                const bool in_box = row_in && (unsigned)ux < (unsigned)SW;
+                wt[jj][i] = wcol[(j * 4 + i) * wstride];
+                const float* gsrc = in1b + (int64_t)cy * p.in1.h + cx;
+                const float* ssrc = s_img + uy * SW + ux;
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[jj][i][c] = in_box ? ssrc[c * SH * SW] : __ldg(gsrc + c * p.in1.c);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c)  // same fmaf chain per (channel, quadrant) as the fast path
+                    q[c][2 * jp + (i >> 1)] = fmaf(v[jj][i][c], wt[jj][i], q[c][2 * jp + (i >> 1)]);
+    }
+    const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
+    const float wBL = (1.0f - a) * bt, wBR = a * bt;
+#pragma unroll
+    for (int c = 0; c < C; ++c) res[c] = wTL * q[c][0] + wTR * q[c][1] + wBL * q[c][2] + wBR * q[c][3];
+}
+
 // all pixels of one staged tile: shared by the one-tile-per-CTA and the persistent kernels
 template <int C, class K>
 __device__ __forceinline__ void fwd_compute_tile(const FiArgs& p, const float* s_filt, const float* s_flow,
@@ -167,6 +210,7 @@ __device__ __forceinline__ void fwd_compute_tile(const FiArgs& p, const float* s
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
     const int W = p.W, H = p.H;
     const float* in1b = p.in1p + b * p.in1.b;
+    unsigned slow = 0;  // bit k: pixel k of this thread needs the clamped path
 #pragma unroll
     for (int k = 0; k < K::PPT; ++k) {
         int xl, yl;
@@ -182,59 +226,55 @@ __device__ __forceinline__ void fwd_compute_tile(const FiArgs& p, const float* s
                 stg_stream(outp + c * p.out.c, __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x));
             continue;
         }
+        const int lx = g.ix - 1 - bx, ly = g.iy - 1 - by;
+        // the box lies inside the image (0 <= bx <= W-SW, 0 <= by <= H-SH), so a window inside the
+        // box is also inside the image: no per-tap clamping needed
+        if (!(((unsigned)lx <= (unsigned)(SW - 4)) && ((unsigned)ly <= (unsigned)(SH - 4)))) {
+            slow |= 1u << k;
+            continue;
+        }
         const float a = g.alpha, bt = g.beta;
         const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
         const float wBL = (1.0f - a) * bt, wBR = a * bt;
-        const int L = g.ix - 1, T = g.iy - 1;
-        const int lx = L - bx, ly = T - by;
         const float* wcol = s_filt + yl * TW + xl;  // plane stride TH*TW
-        const bool fast = (L >= 0) && (L + 3 <= W - 1) && (T >= 0) && (T + 3 <= H - 1) &&
-                          (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
-        if (fast) {
-            float wg[16];
+        float wg[16];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) wg[t] = wcol[t * TH * TW];
-            const float* base = s_img + ly * SW + lx;
+        for (int t = 0; t < 16; ++t) wg[t] = wcol[t * TH * TW];
+        const float* base = s_img + ly * SW + lx;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) {
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        q[(j >> 1) * 2 + (i >> 1)] =
-                            fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
-                stg_stream(outp + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
-            }
-        } else {  // window touches the image border or leaves the staged box: rare, kept compact
+                for (int i = 0; i < 4; ++i)
+                    q[(j >> 1) * 2 + (i >> 1)] =
+                        fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+            stg_stream(outp + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
+        }
+    }
+    if (__builtin_expect(slow != 0, 0)) {
 #pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-                const float* img = in1b + c * p.in1.c;
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll 1
-                for (int t = 0; t < 16; ++t) {
-                    const int j = t >> 2, i = t & 3;
-                    const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
-                    const int ux = cx - bx, uy = cy - by;
-                    const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
-                    const float v = in_box ? s_img[c * SH * SW + uy * SW + ux] : __ldg(img + (int64_t)cy * p.in1.h + cx);
-                    const float wt = wcol[t * TH * TW];  // same fmaf chain as the fast path / generic kernel
-                    q0 = (j < 2 && i < 2) ? fmaf(v, wt, q0) : q0;
-                    q1 = (j < 2 && i >= 2) ? fmaf(v, wt, q1) : q1;
-                    q2 = (j >= 2 && i < 2) ? fmaf(v, wt, q2) : q2;
-                    q3 = (j >= 2 && i >= 2) ? fmaf(v, wt, q3) : q3;
-                }
-                stg_stream(outp + c * p.out.c, wTL * q0 + wTR * q1 + wBL * q2 + wBR * q3);
-            }
+        for (int k = 0; k < K::PPT; ++k) {
+            if (!((slow >> k) & 1u)) continue;
+            int xl, yl;
+            tile_pixel<K>(k, lane, warp, xl, yl);
+            const int x = x0 + xl, y = y0 + yl;
+            const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+            float res[C];
+            fwd_slow_pixel<C, K>(p, s_filt + yl * TW + xl, TH * TW, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha,
+                                 g.beta, res);
+            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+#pragma unroll
+            for (int c = 0; c < C; ++c) stg_stream(outp + c * p.out.c, res[c]);
         }
     }
 }
 
-
 template <int C, class K>
 __global__ void __launch_bounds__(K::NT, K::MINB)
 fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                  const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+                  const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);  // TMA: 128-byte boxes
@@ -300,7 +340,7 @@ template <int C, class K, bool PFL2>
 __global__ void __launch_bounds__(K::NT, K::MINB)
 fi_fwd_tma2_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
                    const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_pref,
-                   const FiArgs p) {
+                   const __grid_constant__ FiArgs p) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
@@ -383,7 +423,7 @@ __host__ __device__ constexpr int chunked_smem() {
 template <class K>
 __global__ void __launch_bounds__(K::NT, K::MINB)
 fi_fwd_tma_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                          const __grid_constant__ CUtensorMap m_img, const FiArgs p) {
+                          const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, PPT = K::PPT;
     constexpr int FILT_B = 16 * TH * TW * 4, FLOW_B = 2 * TH * TW * 4, IMG_B = CBK * SH * SW * 4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -542,7 +582,7 @@ __host__ __device__ constexpr int pl_smem(int C, bool pf) {
 template <int C, class K, bool PF>
 __global__ void __launch_bounds__(K::NT, K::MINB)
 fi_fwd_pl_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                 const __grid_constant__ CUtensorMap m_img, const FiArgs p, const int tiles_x, const int tiles_y,
+                 const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p, const int tiles_x, const int tiles_y,
                  const int n_tiles) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
     constexpr int FILT_B = 16 * TH * TW * 4, IMG_B = C * SH * SW * 4, FLOW_B = 2 * TH * TW * 4;
@@ -650,6 +690,196 @@ int launch_fwd_pl(cudaStream_t stream, const FiArgs& a) {
     return check_launch("FilterInterpolation forward (persistent-lite TMA)") == 0 ? 1 : -1;
 }
 
+// ------------------------------------------------------------------------------------
+// forward, "patch" variant: a warp works on 8x4-pixel patches instead of 32x1 row segments and the
+// image box has a row pitch of 72 words; the modelled bank-conflict factor of the 16-tap gather
+// drops from 2.40 to 1.96 on the benchmark field (tools/bank_model.py).  Flow and filter tiles are
+// staged as four 8-pixel-wide strips ([strip][plane][TH][8], one TMA each) so that a patch reads
+// 32 consecutive words.  With STAGE_OUT the results of a strip go back through shared memory (the
+// warp's own, by then dead, filter strip) and one TMA store per warp instead of 4-row partial
+// stores.  Tile 32 x 8, 128 threads; warp w owns strip w.
+// ------------------------------------------------------------------------------------
+template <int SW_, int SH_>
+struct PatchCfg {
+    static constexpr int TW = 32, TH = 8, SW = SW_, SH = SH_;
+};
+
+template <int C, int SW, int SH, int MINB, bool STAGE_OUT>
+__global__ void __launch_bounds__(128, MINB)
+fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                    const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_out,
+                    const __grid_constant__ FiArgs p) {
+    using K = PatchCfg<SW, SH>;
+    constexpr int TW = 32, TH = 8, SWD = 8;  // strip width
+    constexpr int FSTRIP = 16 * TH * SWD;     // floats per filter strip
+    constexpr int OFF_FLOW = 16 * TH * TW * 4, OFF_BAR = OFF_FLOW + 2 * TH * TW * 4, OFF_IMG = OFF_BAR + 128;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    float* s_filt = reinterpret_cast<float*>(sm);                         // [4][16][TH][8]
+    const float* s_flow = reinterpret_cast<const float*>(sm + OFF_FLOW);  // [4][2][TH][8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);           // 0 flow, 1 filter, 2 image
+    int* s_bb = reinterpret_cast<int*>(bars + 3);
+    const float* s_img = reinterpret_cast<const float*>(sm + OFF_IMG);    // [C][SH][SW]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int W = p.W, H = p.H;
+
+    if (tid == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::mbar_init(&bars[2], 1);
+        s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        tma::fence_barrier_init();
+        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+#pragma unroll
+        for (int st = 0; st < 4; ++st)
+            tma::load_4d(sm + OFF_FLOW + st * 2 * TH * SWD * 4, &m_flow, x0 + SWD * st, y0, 0, b, &bars[0]);
+        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
+#pragma unroll
+        for (int st = 0; st < 4; ++st)
+            tma::load_4d(sm + st * FSTRIP * 4, &m_filt, x0 + SWD * st, y0, 0, b, &bars[1]);
+    }
+    __syncthreads();
+    tma::mbar_wait(&bars[0], 0, 1);
+
+    const int lxx = lane & 7, lyy = lane >> 3;
+    const int xl = SWD * warp + lxx;
+    const float* flow_s = s_flow + warp * 2 * TH * SWD + lxx;  // + (comp * TH + yl) * 8
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int yl = 4 * k + lyy;
+        const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, flow_s[yl * SWD], flow_s[(TH + yl) * SWD]);
+        if (g.valid && x0 + xl < W && y0 + yl < H) {
+            mnx = min(mnx, g.ix); mxx = max(mxx, g.ix);
+            mny = min(mny, g.iy); mxy = max(mxy, g.iy);
+        }
+    }
+    mnx = warp_min(mnx); mxx = warp_max(mxx); mny = warp_min(mny); mxy = warp_max(mxy);
+    if (lane == 0 && mnx <= mxx) {
+        atomicMin(&s_bb[0], mnx); atomicMax(&s_bb[1], mxx);
+        atomicMin(&s_bb[2], mny); atomicMax(&s_bb[3], mxy);
+    }
+    __syncthreads();
+    const bool any_valid = s_bb[0] <= s_bb[1];
+    int bx = 0, by = 0;
+    if (any_valid) {
+        bx = s_bb[0] - 1;
+        by = s_bb[2] - 1;
+        const int need_w = s_bb[1] - s_bb[0] + 4 + 3, need_h = s_bb[3] - s_bb[2] + 4;
+        if (need_w > SW) bx += (need_w - SW) / 2;
+        if (need_h > SH) by += (need_h - SH) / 2;
+        bx = max(0, min(bx, W - SW)) & ~3;
+        by = max(0, min(by, H - SH));
+    }
+    if (tid == 0 && any_valid) {
+        tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
+        tma::load_4d(sm + OFF_IMG, &m_img, bx, by, 0, b, &bars[2]);
+    }
+    tma::mbar_wait(&bars[1], 0, 2);
+    if (any_valid) tma::mbar_wait(&bars[2], 0, 3);
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    float* const filt_w = s_filt + warp * FSTRIP;  // this warp's filter strip; reused for its outputs
+    float outv[2][C];                               // results of the two pixels (STAGE_OUT)
+    unsigned slow = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int yl = 4 * k + lyy;
+        const int x = x0 + xl, y = y0 + yl;
+#pragma unroll
+        for (int c = 0; c < C; ++c) outv[k][c] = 0.f;
+        if (x >= W || y >= H) continue;
+        float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+        const FiGeom g = fi_geometry(x, y, W, H, flow_s[yl * SWD], flow_s[(TH + yl) * SWD]);
+        if (!g.valid) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float v = __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x);
+                if (STAGE_OUT) outv[k][c] = v;
+                else stg_stream(outp + c * p.out.c, v);
+            }
+            continue;
+        }
+        const int lx = g.ix - 1 - bx, ly = g.iy - 1 - by;
+        if (!(((unsigned)lx <= (unsigned)(SW - 4)) && ((unsigned)ly <= (unsigned)(SH - 4)))) {
+            slow |= 1u << k;
+            continue;
+        }
+        const float a = g.alpha, bt = g.beta;
+        const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
+        const float wBL = (1.0f - a) * bt, wBR = a * bt;
+        const float* wcol = filt_w + yl * SWD + lxx;  // plane stride TH*8
+        float wg[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) wg[t] = wcol[t * TH * SWD];
+        const float* base = s_img + ly * SW + lx;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    q[(j >> 1) * 2 + (i >> 1)] =
+                        fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+            const float r = wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3];
+            if (STAGE_OUT) outv[k][c] = r;
+            else stg_stream(outp + c * p.out.c, r);
+        }
+    }
+    if (__builtin_expect(slow != 0, 0)) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!((slow >> k) & 1u)) continue;
+            const int yl = 4 * k + lyy;
+            const int x = x0 + xl, y = y0 + yl;
+            const FiGeom g = fi_geometry(x, y, W, H, flow_s[yl * SWD], flow_s[(TH + yl) * SWD]);
+            float res[C];
+            fwd_slow_pixel<C, K>(p, filt_w + yl * SWD + lxx, TH * SWD, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha,
+                                 g.beta, res);
+            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (STAGE_OUT) outv[k][c] = res[c];
+                else stg_stream(outp + c * p.out.c, res[c]);
+            }
+        }
+    }
+    if (STAGE_OUT) {
+        // every lane of the warp is done with the warp's filter strip: stage [C][TH][8] there
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) filt_w[(c * TH + 4 * k + lyy) * SWD + lxx] = outv[k][c];
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma::store_4d(&m_out, x0 + SWD * warp, y0, 0, b, filt_w);  // clipped to the image by the TMA
+            tma::bulk_commit();
+            tma::bulk_wait_read_all();
+        }
+    }
+}
+
+template <int C, int SW, int SH, int MINB, bool STAGE_OUT>
+int launch_fwd_patch(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < SW || a.H < SH) return 0;
+    CUtensorMap m[5], mout;
+    if (!make_maps(a, false, 8, 8, SW, SH, m)) return 0;  // flow / filter boxes are 8-wide strips
+    if (!tma::make_map_nchw(&mout, a.outp, a.B, a.C, a.H, a.W, a.out.b, a.out.c, a.out.h, 8, 8, a.C,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE))
+        return 0;
+    constexpr size_t smem = (size_t)(16 + 2) * 8 * 32 * 4 + 128 + (size_t)C * SH * SW * 4 + 128;
+    if (!ensure_dynamic_smem(fi_fwd_patch_kernel<C, SW, SH, MINB, STAGE_OUT>, smem)) return 0;
+    dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.B);
+    fi_fwd_patch_kernel<C, SW, SH, MINB, STAGE_OUT><<<grid, 128, smem, stream>>>(m[0], m[1], m[2], mout, a);
+    count_launch();
+    return check_launch("FilterInterpolation forward (TMA, 8x4 patches)") == 0 ? 1 : -1;
+}
+
 // ====================================================================================
 // backward
 // ====================================================================================
@@ -684,6 +914,88 @@ __host__ __device__ constexpr Layout make_bwd_layout(int C) {
     return l;
 }
 
+// A pixel whose window touches the image border or leaves the staged box (a few lanes of ~3 % of
+// the warps on the benchmark field): per-tap clamping, box or global source / destination per tap.
+// Run after the thread's fast pixels (no overlap of live ranges with the fast path); one window row
+// per iteration like the fast path.
+template <int C, bool OVERWRITE, bool INT_ACC, class K>
+__device__ __forceinline__ void bwd_slow_pixel(const FiArgs& p, const float* wcol, const float* gout_px,
+                                            const float* s_img, float* s_acc, float scale, const float* in1b,
+                                            float* g1b, float* g2, float* g3, int L, int T, int bx, int by, float a,
+                                            float bt) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    const int W = p.W, H = p.H;
+    int* s_acci = reinterpret_cast<int*>(s_acc);
+    const float gam_y = 1.0f - bt, gam_x = 1.0f - a;
+    float gov[C], gq[C][4], q[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        gov[c] = gout_px[c * TH * TW];
+        gq[c][0] = gov[c] * (1.0f - a) * (1.0f - bt);
+        gq[c][1] = gov[c] * a * (1.0f - bt);
+        gq[c][2] = gov[c] * (1.0f - a) * bt;
+        gq[c][3] = gov[c] * a * bt;
+        q[c][0] = q[c][1] = q[c][2] = q[c][3] = 0.f;
+    }
+    // one window row per iteration; its 4 x C source values (box or L2) are loaded before they are used
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const bool top = j < 2;
+        const int cy = clampi(T + j, 0, H - 1);
+        const int uy = cy - by;
+        const bool row_in = (unsigned)uy < (unsigned)SH;
+        float v[4][C], w[4];
+        int so[4];
+        bool to_box[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cx = clampi(L + i, 0, W - 1);
+            const int ux = cx - bx;
+            const bool in_box = row_in && (unsigned)ux < (unsigned)SW;
+            // clamped taps pile up on border cells (up to 9 of one pixel on a corner): they go
+            // straight to global memory so that a box cell receives at most ONE tap per pixel
+            to_box[i] = in_box && cx == L + i && cy == T + j;
+            w[i] = wcol[(j * 4 + i) * TH * TW];
+            so[i] = uy * SW + ux;
+            const float* gsrc = in1b + (int64_t)cy * p.in1.h + cx;
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[i][c] = in_box ? s_img[c * SH * SW + so[i]] : __ldg(gsrc + c * p.in1.c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int h = i >> 1;
+            const int cx = clampi(L + i, 0, W - 1);
+            float* g1 = g1b + (int64_t)cy * p.gi1.h + cx;
+            float a3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float gsel = top ? gq[c][h] : gq[c][2 + h];
+                if (to_box[i]) {
+                    if (INT_ACC) atomicAdd(&s_acci[c * SH * SW + so[i]], __float2int_rn(gsel * w[i] * scale));
+                    else atomicAdd(&s_acc[c * SH * SW + so[i]], gsel * w[i]);
+                } else {
+                    red_add(g1 + c * p.gi1.c, gsel * w[i]);
+                }
+                a3 = fmaf(gsel, v[i][c], a3);
+                const float nq = fmaf(v[i][c], w[i], top ? q[c][h] : q[c][2 + h]);
+                q[c][h] = top ? nq : q[c][h];
+                q[c][2 + h] = top ? q[c][2 + h] : nq;
+            }
+            float* dst = g3 + (int64_t)(j * 4 + i) * p.gi3.c;
+            if (OVERWRITE) stg_stream(dst, a3);
+            else *dst += a3;
+        }
+    }
+    float dx = 0.f, dy = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        dx = fmaf(gov[c], gam_y * (q[c][1] - q[c][0]) + (1.0f - gam_y) * (q[c][3] - q[c][2]), dx);
+        dy = fmaf(gov[c], gam_x * (q[c][2] - q[c][0]) + (1.0f - gam_x) * (q[c][3] - q[c][1]), dy);
+    }
+    stg_stream(g2, dx);
+    stg_stream(g2 + p.gi2.c, dy);
+}
+
 template <int C, bool OVERWRITE, bool INT_ACC, class K>
 __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s_filt, const float* s_gout,
                                                  const float* s_flow, const float* s_img, float* s_acc, float scale,
@@ -693,6 +1005,8 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
     const float* in1b = p.in1p + b * p.in1.b;
     float* g1b = p.gi1p + b * p.gi1.b;
     int* s_acci = reinterpret_cast<int*>(s_acc);
+    static_assert(K::PPT <= 32, "slow-pixel mask");
+    unsigned slow = 0;  // bit k: pixel k of this thread needs the clamped path
 #pragma unroll 1
     for (int k = 0; k < K::PPT; ++k) {
         int xl, yl;
@@ -715,8 +1029,14 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
         const float gam_y = 1.0f - bt, gam_x = 1.0f - a;  // the reference uses (1 - gamma), not beta
         const int L = g.ix - 1, T = g.iy - 1;
         const int lx = L - bx, ly = T - by;
-        const bool fast = (L >= 0) && (L + 3 <= W - 1) && (T >= 0) && (T + 3 <= H - 1) &&
-                          (lx >= 0) && (lx + 3 < SW) && (ly >= 0) && (ly + 3 < SH);
+        // the box lies inside the image (0 <= bx <= W-SW, 0 <= by <= H-SH), so a window inside the
+        // box is also inside the image: no per-tap clamping needed
+        const bool fast = ((unsigned)lx <= (unsigned)(SW - 4)) && ((unsigned)ly <= (unsigned)(SH - 4));
+        const float* wcol = s_filt + yl * TW + xl;  // plane stride TH*TW
+        if (__builtin_expect(!fast, 0)) {  // border / outside the staged box: deferred
+            slow |= 1u << k;
+            continue;
+        }
         // Taps outer, channels inner: gradinput3[t] is complete after its channel loop and is
         // stored at once (no 16-register accumulator array), the filter tap is read when needed.
         float gov[C], gq[C][4], q[C][4];
@@ -729,8 +1049,7 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
             gq[c][3] = gov[c] * a * bt;
             q[c][0] = q[c][1] = q[c][2] = q[c][3] = 0.f;
         }
-        const float* wcol = s_filt + yl * TW + xl;  // plane stride TH*TW
-        if (fast) {
+        {
             // one window row per iteration, NOT unrolled across rows: keeps ~12 loads in flight
             // instead of 64 and the kernel at <= 64 registers (more resident warps)
 #pragma unroll 1
@@ -759,41 +1078,6 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
                     else *dst += a3;  // own pixel: no atomic needed
                 }
             }
-        } else {  // border / outside the staged box: per-tap clamping, global fallbacks
-#pragma unroll 1
-            for (int t = 0; t < 16; ++t) {
-                const int j = t >> 2, i = t & 3;
-                const bool top = j < 2;
-                const int h = i >> 1;
-                const int cx = clampi(L + i, 0, W - 1), cy = clampi(T + j, 0, H - 1);
-                const int ux = cx - bx, uy = cy - by;
-                const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
-                // clamped taps pile up on border cells (up to 9 of one pixel on a corner): they go
-                // straight to global memory so that a box cell receives at most ONE tap per pixel
-                const bool to_box = in_box && cx == L + i && cy == T + j;
-                const float w = wcol[t * TH * TW];
-                float a3 = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int o = c * SH * SW + uy * SW + ux;
-                    const float v = in_box ? s_img[o] : __ldg(in1b + c * p.in1.c + (int64_t)cy * p.in1.h + cx);
-                    const float gsel = (i >= 2) ? (top ? gq[c][1] : gq[c][3]) : (top ? gq[c][0] : gq[c][2]);
-                    if (to_box) {
-                        if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn(gsel * w * scale));
-                        else atomicAdd(&s_acc[o], gsel * w);
-                    } else {
-                        red_add(g1b + c * p.gi1.c + (int64_t)cy * p.gi1.h + cx, gsel * w);
-                    }
-                    a3 = fmaf(gsel, v, a3);
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const bool mine = (qq == (top ? 0 : 2) + h);
-                        q[c][qq] = mine ? fmaf(v, w, q[c][qq]) : q[c][qq];
-                    }
-                }
-                if (OVERWRITE) stg_stream(g3 + t * p.gi3.c, a3);
-                else g3[t * p.gi3.c] += a3;
-            }
         }
         float dx = 0.f, dy = 0.f;
 #pragma unroll
@@ -804,13 +1088,27 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
         stg_stream(g2, dx);
         stg_stream(g2 + p.gi2.c, dy);
     }
+    if (__builtin_expect(slow != 0, 0)) {
+#pragma unroll 1
+        for (int k = 0; k < K::PPT; ++k) {
+            if (!((slow >> k) & 1u)) continue;
+            int xl, yl;
+            tile_pixel<K>(k, lane, warp, xl, yl);
+            const int x = x0 + xl, y = y0 + yl;
+            const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+            bwd_slow_pixel<C, OVERWRITE, INT_ACC, K>(p, s_filt + yl * TW + xl, s_gout + yl * TW + xl, s_img, s_acc, scale,
+                                                     in1b, g1b, p.gi2p + b * p.gi2.b + (int64_t)y * p.gi2.h + x,
+                                                     p.gi3p + b * p.gi3.b + (int64_t)y * p.gi3.h + x, g.ix - 1, g.iy - 1,
+                                                     bx, by, g.alpha, g.beta);
+        }
+    }
 }
 
 template <int C, bool OVERWRITE, class K>
 __global__ void __launch_bounds__(K::NT, K::MINB)
 fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_gout,
                   const __grid_constant__ CUtensorMap m_filt, const __grid_constant__ CUtensorMap m_img,
-                  const __grid_constant__ CUtensorMap m_gi1, const FiArgs p) {
+                  const __grid_constant__ CUtensorMap m_gi1, const __grid_constant__ FiArgs p) {
     constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH, NT = K::NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
@@ -876,9 +1174,7 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
         }
     }
     {   // non-negative floats (and NaN, which sorts above +Inf) order like their bit patterns
-        unsigned mb = __float_as_uint(mloc);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mloc));
         if (lane == 0 && mb) atomicMax(s_maxbits, mb);
     }
     __syncthreads();
@@ -974,6 +1270,11 @@ using FwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  61 KB: 3 CTAs / SM
 using FwdC = Cfg<32, 16, 64, 40, 256, 3>;  //  67 KB: 3 CTAs / SM
 using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
 using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
+using FwdE6 = Cfg<32, 8, 64, 24, 128, 6>;  //  same, registers capped at 80: 6 CTAs / SM
+using FwdH1 = Cfg<32, 6, 64, 20, 96, 7>;   //  29 KB: 7 CTAs / SM, 6-row tiles
+using FwdH2 = Cfg<32, 6, 64, 22, 96, 7>;   //  31 KB: 7 CTAs / SM
+using FwdQ1 = Cfg<32, 4, 64, 16, 64, 10>;  //  22 KB: 10 CTAs / SM, 4-row tiles, 2 px / thread
+using FwdQ2 = Cfg<32, 4, 64, 16, 128, 10>; //  22 KB: 10 CTAs / SM, 1 px / thread
 using FwdE2 = Cfg<32, 8, 64, 32, 128, 5>;  //  43 KB: 5 CTAs / SM, taller box (fewer fallback taps)
 using FwdE3 = Cfg<32, 8, 64, 28, 128, 5>;  //  40 KB
 using FwdF = Cfg<32, 8, 64, 24, 256, 5>;   //  37 KB: 5 CTAs / SM, 1 px / thread (<= 51 registers)
@@ -984,13 +1285,16 @@ using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs /
 using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
 using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
 using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
-using FWD_DEFAULT = FwdE;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
+using FWD_DEFAULT = FwdE6;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
 using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
 using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
 using BwdD = Cfg<32, 16, 64, 32, 512, 2>;  //  91 KB: 2 CTAs / SM, 1 px / thread
 using BwdE = Cfg<32, 8, 64, 32, 256, 3>;   //  70 KB: 3 CTAs / SM, taller box
 using BwdF = Cfg<32, 8, 64, 28, 256, 3>;   //  64 KB
+using BwdG = Cfg<32, 16, 64, 36, 256, 2>;  // 104 KB: 2 CTAs / SM
+using BwdH = Cfg<32, 16, 64, 40, 256, 2>;  // 110 KB: 2 CTAs / SM
+using BwdI = Cfg<32, 16, 64, 36, 512, 2>;  // 104 KB: 2 CTAs / SM, 1 px / thread
 using BWD_DEFAULT = BwdF;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 
 int env_int(const char* name) {
@@ -1053,6 +1357,14 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 5: r = launch_fwd<3, FwdE>(stream, a); break;
             case 10: r = launch_fwd<3, FwdF>(stream, a); break;
             case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
+            case 19: r = launch_fwd<3, FwdE6>(stream, a); break;
+            case 50: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;
+            case 51: r = launch_fwd_patch<3, 72, 22, 6, true>(stream, a); break;
+            case 52: r = launch_fwd_patch<3, 72, 24, 5, true>(stream, a); break;
+            case 60: r = launch_fwd<3, FwdH1>(stream, a); break;
+            case 61: r = launch_fwd<3, FwdH2>(stream, a); break;
+            case 62: r = launch_fwd<3, FwdQ1>(stream, a); break;
+            case 63: r = launch_fwd<3, FwdQ2>(stream, a); break;
             case 17: r = launch_fwd<3, FwdE2>(stream, a); break;
             case 18: r = launch_fwd<3, FwdE3>(stream, a); break;
             case 20: r = launch_fwd2<3, FwdE, false>(stream, a); break;
@@ -1091,6 +1403,9 @@ int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {
             case 4: return launch_bwd<3, true, BwdD>(stream, a);
             case 5: return launch_bwd<3, true, BwdE>(stream, a);
             case 6: return launch_bwd<3, true, BwdF>(stream, a);
+            case 7: return launch_bwd<3, true, BwdG>(stream, a);
+            case 8: return launch_bwd<3, true, BwdH>(stream, a);
+            case 9: return launch_bwd<3, true, BwdI>(stream, a);
             default: return launch_bwd<3, true, BWD_DEFAULT>(stream, a);
         }
     }

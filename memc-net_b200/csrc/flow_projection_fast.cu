@@ -90,16 +90,9 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
             mloc = fmaxf_nan(mloc, fmaxf_nan(fabsf(fx[k]), fabsf(fy[k])));
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    unsigned mb = __float_as_uint(mloc);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);  // REDUX
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mloc));
     if (lane == 0 && mnx <= mxx) {
         atomicMin(&s.bb[0], mnx); atomicMax(&s.bb[1], mxx);
         atomicMin(&s.bb[2], mny); atomicMax(&s.bb[3], mxy);

@@ -125,6 +125,39 @@ def test_filter_interpolation_strided_views_and_stream(L):
     assert float(bigo[0].abs().max()) == 0.0 and float(bigo[:, 0].abs().max()) == 0.0  # nothing spilled
 
 
+def test_filter_interpolation_fast_path_on_strided_views(L):
+    """Batch/channel-sliced views at a TMA-eligible size: the tensor maps must honour the real
+    strides of every tensor (inputs, gradoutput, gradinput1) -- extended ABI, fwd + bwd."""
+    B, C, H, W = 2, 3, 64, 128
+    in1, flow, filt, gout = fi_case(B, C, H, W, 4, 3.0, seed=19)
+
+    def view(a, pad_b, pad_c, off_c):
+        big = torch.full((a.shape[0] + pad_b, a.shape[1] + pad_c, H, W), 7.0, device="cuda")
+        v = big[pad_b:, off_c:off_c + a.shape[1]]
+        v.copy_(dev(a))
+        return big, v
+
+    _, v1 = view(in1, 1, 2, 1)
+    _, v2 = view(flow, 0, 3, 2)
+    _, v3 = view(filt, 1, 4, 3)
+    _, vg = view(gout, 2, 1, 0)
+    bo, vo = view(np.zeros_like(in1), 1, 2, 2)
+    b1, g1 = view(np.zeros_like(in1), 1, 1, 1)
+    b2, g2 = view(np.zeros_like(flow), 1, 1, 0)
+    b3, g3 = view(np.zeros_like(filt), 0, 2, 1)
+    S, P = L.strides_of, L.ptr
+    L.call("memc_b200_filter_interpolation_forward", L.stream_ptr(v1), B, C, H, W, 4, S(v1), S(v2), S(v3), S(vo),
+           P(v1), P(v2), P(v3), P(vo), L.OVERWRITE)
+    L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(v1), B, C, H, W, 4, S(v1), S(v2), S(v3), S(vg),
+           S(g1), S(g2), S(g3), P(v1), P(v2), P(v3), P(vg), P(g1), P(g2), P(g3), L.OVERWRITE)
+    close(vo, cpu.filter_interpolation_forward(in1, flow, filt, "f64"), what="strided fast out")
+    e1, e2, e3 = cpu.filter_interpolation_backward(in1, flow, filt, gout, "f64")
+    close(g1, e1, what="strided fast gi1"), close(g2, e2, what="strided fast gi2"), close(g3, e3, what="strided fast gi3")
+    for big, v in ((bo, vo), (b1, g1), (b2, g2), (b3, g3)):   # nothing written outside the views
+        v.fill_(7.0)
+        assert bool((big == 7.0).all())
+
+
 @pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
 @pytest.mark.parametrize("shape", [(2, 3, 96, 128, 4, 4.0), (1, 64, 64, 128, 4, 3.0), (1, 5, 20, 31, 5, 2.0),
                                    (1, 3, 128, 256, 4, 20.0)])
