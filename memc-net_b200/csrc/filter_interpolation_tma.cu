@@ -880,6 +880,323 @@ int launch_fwd_patch(cudaStream_t stream, const FiArgs& a) {
     return check_launch("FilterInterpolation forward (TMA, 8x4 patches)") == 0 ? 1 : -1;
 }
 
+// ------------------------------------------------------------------------------------
+// forward, WARP-SPECIALISED persistent ring.  The one-tile-per-CTA kernel spends 60 % of a CTA's
+// life waiting (flow TMA -> bounding box -> image TMA; profiles/r01_fi_fwd_phase_timeline.txt) and
+// its shared-memory data pipe idles a third of the time.  Here a CTA keeps walking tiles
+// blockIdx.x, +grid, ... and splits its warps by role:
+//
+//   producer warp   waits for a free ring slot, issues the filter-tile TMA, computes the tile's
+//                   bounding box from the (long since landed) flow tile with its 32 lanes, issues
+//                   the data-dependent image-box TMA, prefetches a later flow tile
+//   consumer warps  wait for "slot full", compute their pixels of the tile exactly like the
+//                   one-tile kernel (fwd_compute_tile), hand the slot back -- no block-wide barrier
+//
+// Slots: NS x (filter tile + image box), NFS x flow tile (small: prefetched further ahead).
+// The chain  release(i-NS) -> filter(i) + image(i) landed  has NS-1 tile-compute times of slack.
+// ------------------------------------------------------------------------------------
+template <class K, int C, int NS, int NFS>
+struct WsLayout {
+    static constexpr int FILT_B = 16 * K::TH * K::TW * 4, FLOW_B = 2 * K::TH * K::TW * 4, IMG_B = C * K::SH * K::SW * 4;
+    static constexpr int OFF_FILT = 0, OFF_IMG = NS * FILT_B, OFF_FLOW = OFF_IMG + NS * IMG_B;
+    static constexpr int OFF_BAR = OFF_FLOW + NFS * FLOW_B;  // full_flow[NFS], full_filt[NS], full_img[NS], empty[NS]
+    static constexpr int OFF_BOX = OFF_BAR + (NFS + 3 * NS) * 8;
+    static constexpr int TOTAL = OFF_BOX + NS * 8;
+    static_assert(FILT_B % 128 == 0 && FLOW_B % 128 == 0 && IMG_B % 128 == 0, "TMA destinations are 128-byte aligned");
+};
+
+template <int C, class K, int NS, int NFS>
+__global__ void __launch_bounds__(K::NT + 32, K::MINB)
+fi_fwd_ws_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                 const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p, const int tiles_x,
+                 const int tiles_y, const int n_tiles) {
+    using L = WsLayout<K, C, NS, NFS>;
+    constexpr int NCW = K::NT / 32;  // consumer warps; warp NCW is the producer
+    constexpr int LF = NFS - NS;     // flow look-ahead (tiles)
+    static_assert(LF >= 1, "flow ring must be deeper than the data ring");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full_flow = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
+    uint64_t* full_filt = full_flow + NFS;
+    uint64_t* full_img = full_filt + NS;
+    uint64_t* empty = full_img + NS;
+    volatile int* s_box = reinterpret_cast<volatile int*>(sm + L::OFF_BOX);  // [NS][2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+    const int W = p.W, H = p.H;
+    const int per_frame = tiles_x * tiles_y;
+    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
+        const int t = (int)blockIdx.x + i * G;
+        b = t / per_frame;
+        const int r = t - b * per_frame;
+        const int ty = r / tiles_x;
+        x0 = (r - ty * tiles_x) * K::TW;
+        y0 = ty * K::TH;
+    };
+
+    if (tid == 0) {
+        for (int k = 0; k < NFS; ++k) tma::mbar_init(&full_flow[k], 1);
+        for (int k = 0; k < NS; ++k) {
+            tma::mbar_init(&full_filt[k], 1);
+            tma::mbar_init(&full_img[k], 1);
+            tma::mbar_init(&empty[k], NCW);
+        }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (n == 0) return;
+
+    if (warp == NCW) {
+        // ================================ producer ================================
+        auto issue_flow = [&](int i) {  // lane 0
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            tma::mbar_expect_tx(&full_flow[i % NFS], L::FLOW_B);
+            tma::load_4d(sm + L::OFF_FLOW + (i % NFS) * L::FLOW_B, &m_flow, x0, y0, 0, b, &full_flow[i % NFS]);
+        };
+        if (lane == 0)
+            for (int i = 0; i < LF && i < n; ++i) issue_flow(i);
+        for (int i = 0; i < n; ++i) {
+            const int s = i % NS, fsl = i % NFS;
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            // bounding box first: it only needs the flow tile, not the slot
+            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 61);
+            int bx, by;
+            tile_box_warp<K>(reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B), x0, y0, W, H, lane, bx, by);
+            if (i >= NS) tma::mbar_wait(&empty[s], ((i / NS) - 1) & 1, 62);  // tile i-NS released the slot
+            if (lane == 0) {
+                tma::mbar_expect_tx(&full_filt[s], L::FILT_B);
+                tma::load_4d(sm + L::OFF_FILT + s * L::FILT_B, &m_filt, x0, y0, 0, b, &full_filt[s]);
+                s_box[2 * s] = bx;
+                s_box[2 * s + 1] = by;
+                tma::mbar_expect_tx(&full_img[s], L::IMG_B);  // release: publishes s_box to the waiters
+                tma::load_4d(sm + L::OFF_IMG + s * L::IMG_B, &m_img, bx, by, 0, b, &full_img[s]);
+                // flow slot (i+LF) % NFS was last read for tile i+LF-NFS = i-NS: released above
+                if (i + LF < n) issue_flow(i + LF);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ consumers ================================
+        for (int i = 0; i < n; ++i) {
+            const int s = i % NS, fsl = i % NFS;
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 63);
+            tma::mbar_wait(&full_filt[s], (i / NS) & 1, 64);
+            tma::mbar_wait(&full_img[s], (i / NS) & 1, 65);
+            const int bx = s_box[2 * s], by = s_box[2 * s + 1];
+            fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm + L::OFF_FILT + s * L::FILT_B),
+                                   reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B),
+                                   reinterpret_cast<const float*>(sm + L::OFF_IMG + s * L::IMG_B), x0, y0, b, bx, by, lane,
+                                   warp);
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[s]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Same ring, but the 16 filter planes never touch shared memory: every consumer thread (one pixel
+// per thread) loads the 16 taps of its pixel of the NEXT tile straight into registers
+// (coalesced 128-byte LDG.NC, no L1 allocation) before it computes the current tile.  Staging the
+// filter through shared memory costs the data pipe a TMA fill (64 B/px) plus an LDS pass
+// (16 wavefronts per 32 px); the direct load costs one pass.  Slots hold the image box only.
+// ------------------------------------------------------------------------------------
+template <class K, int C, int NS, int NFS>
+struct WrLayout {
+    static constexpr int FLOW_B = 2 * K::TH * K::TW * 4, IMG_B = C * K::SH * K::SW * 4;
+    static constexpr int OFF_IMG = 0, OFF_FLOW = NS * IMG_B;
+    static constexpr int OFF_BAR = OFF_FLOW + NFS * FLOW_B;  // full_flow[NFS], full_img[NS], empty[NS]
+    static constexpr int OFF_BOX = OFF_BAR + (NFS + 2 * NS) * 8;
+    static constexpr int TOTAL = OFF_BOX + NS * 8;
+    static_assert(FLOW_B % 128 == 0 && IMG_B % 128 == 0, "TMA destinations are 128-byte aligned");
+};
+
+// one pixel with its 16 filter taps in registers; arithmetic identical to fwd_compute_tile
+template <int C, class K>
+__device__ __forceinline__ void fwd_compute_pixel_rw(const FiArgs& p, const float (&wg)[16], const float* s_flow,
+                                                     const float* s_img, int x0, int y0, int b, int bx, int by, int xl,
+                                                     int yl) {
+    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
+    const int W = p.W, H = p.H;
+    const int x = x0 + xl, y = y0 + yl;
+    if (x >= W || y >= H) return;
+    const float* in1b = p.in1p + b * p.in1.b;
+    float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+    const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+    if (!g.valid) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            stg_stream(outp + c * p.out.c, __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x));
+        return;
+    }
+    const int lx = g.ix - 1 - bx, ly = g.iy - 1 - by;
+    if (__builtin_expect(!(((unsigned)lx <= (unsigned)(SW - 4)) && ((unsigned)ly <= (unsigned)(SH - 4))), 0)) {
+        float res[C];
+        fwd_slow_pixel<C, K>(p, wg, 1, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha, g.beta, res);
+#pragma unroll
+        for (int c = 0; c < C; ++c) stg_stream(outp + c * p.out.c, res[c]);
+        return;
+    }
+    const float a = g.alpha, bt = g.beta;
+    const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
+    const float wBL = (1.0f - a) * bt, wBR = a * bt;
+    const float* base = s_img + ly * SW + lx;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                q[(j >> 1) * 2 + (i >> 1)] = fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
+        stg_stream(outp + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
+    }
+}
+
+template <int C, class K, int NS, int NFS>
+__global__ void __launch_bounds__(K::NT + 32, K::MINB)
+fi_fwd_wr_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_img,
+                 const __grid_constant__ FiArgs p, const int tiles_x, const int tiles_y, const int n_tiles) {
+    using L = WrLayout<K, C, NS, NFS>;
+    constexpr int NCW = K::NT / 32;
+    constexpr int LF = NFS - NS;
+    static_assert(LF >= 1 && K::PPT == 1, "one pixel per consumer thread");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full_flow = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
+    uint64_t* full_img = full_flow + NFS;
+    uint64_t* empty = full_img + NS;
+    volatile int* s_box = reinterpret_cast<volatile int*>(sm + L::OFF_BOX);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+    const int W = p.W, H = p.H;
+    const int per_frame = tiles_x * tiles_y;
+    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
+        const int t = (int)blockIdx.x + i * G;
+        b = t / per_frame;
+        const int r = t - b * per_frame;
+        const int ty = r / tiles_x;
+        x0 = (r - ty * tiles_x) * K::TW;
+        y0 = ty * K::TH;
+    };
+
+    if (tid == 0) {
+        for (int k = 0; k < NFS; ++k) tma::mbar_init(&full_flow[k], 1);
+        for (int k = 0; k < NS; ++k) {
+            tma::mbar_init(&full_img[k], 1);
+            tma::mbar_init(&empty[k], NCW);
+        }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (n == 0) return;
+
+    if (warp == NCW) {
+        auto issue_flow = [&](int i) {  // lane 0
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            tma::mbar_expect_tx(&full_flow[i % NFS], L::FLOW_B);
+            tma::load_4d(sm + L::OFF_FLOW + (i % NFS) * L::FLOW_B, &m_flow, x0, y0, 0, b, &full_flow[i % NFS]);
+        };
+        if (lane == 0)
+            for (int i = 0; i < LF && i < n; ++i) issue_flow(i);
+        for (int i = 0; i < n; ++i) {
+            const int s = i % NS, fsl = i % NFS;
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 71);
+            int bx, by;
+            tile_box_warp<K>(reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B), x0, y0, W, H, lane, bx, by);
+            if (i >= NS) tma::mbar_wait(&empty[s], ((i / NS) - 1) & 1, 72);
+            if (lane == 0) {
+                s_box[2 * s] = bx;
+                s_box[2 * s + 1] = by;
+                tma::mbar_expect_tx(&full_img[s], L::IMG_B);
+                tma::load_4d(sm + L::OFF_IMG + s * L::IMG_B, &m_img, bx, by, 0, b, &full_img[s]);
+                if (i + LF < n) issue_flow(i + LF);
+            }
+            __syncwarp();
+        }
+    } else {
+        int xl, yl;
+        tile_pixel<K>(0, lane, warp, xl, yl);
+        auto load_w = [&](int i, float (&w)[16]) {
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            const int x = x0 + xl, y = y0 + yl;
+            const bool inb = x < W && y < H;
+            const float* fp = p.filtp + b * p.filt.b + (int64_t)(inb ? y : 0) * p.filt.h + (inb ? x : 0);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) w[t] = ldg_stream(fp + t * p.filt.c);
+        };
+        float wg[16], wn[16];
+        load_w(0, wg);
+        for (int i = 0; i < n; ++i) {
+            const int s = i % NS, fsl = i % NFS;
+            int x0, y0, b;
+            tile_origin(i, x0, y0, b);
+            if (i + 1 < n) load_w(i + 1, wn);
+            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 73);
+            tma::mbar_wait(&full_img[s], (i / NS) & 1, 75);
+            const int bx = s_box[2 * s], by = s_box[2 * s + 1];
+            fwd_compute_pixel_rw<C, K>(p, wg, reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B),
+                                       reinterpret_cast<const float*>(sm + L::OFF_IMG + s * L::IMG_B), x0, y0, b, bx, by, xl,
+                                       yl);
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[s]);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) wg[t] = wn[t];
+        }
+    }
+}
+
+template <int C, class K, int NS, int NFS>
+int launch_fwd_wr(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[5];
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    constexpr size_t smem = (size_t)WrLayout<K, C, NS, NFS>::TOTAL + 128;
+    if (!ensure_dynamic_smem(fi_fwd_wr_kernel<C, K, NS, NFS>, smem)) return 0;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) return 0;
+    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
+    if (n_tiles > 0x7fffffffLL) return 0;
+    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
+    fi_fwd_wr_kernel<C, K, NS, NFS><<<grid, K::NT + 32, smem, stream>>>(m[0], m[2], a, tiles_x, tiles_y, (int)n_tiles);
+    count_launch();
+    return check_launch("FilterInterpolation forward (warp-specialised ring, register filter)") == 0 ? 1 : -1;
+}
+
+template <int C, class K, int NS, int NFS>
+int launch_fwd_ws(cudaStream_t stream, const FiArgs& a) {
+    if (a.W < K::SW || a.H < K::SH) return 0;
+    CUtensorMap m[5];
+    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
+    constexpr size_t smem = (size_t)WsLayout<K, C, NS, NFS>::TOTAL + 128;
+    if (!ensure_dynamic_smem(fi_fwd_ws_kernel<C, K, NS, NFS>, smem)) return 0;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) return 0;
+    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
+    if (n_tiles > 0x7fffffffLL) return 0;
+    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
+    fi_fwd_ws_kernel<C, K, NS, NFS><<<grid, K::NT + 32, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
+    count_launch();
+    return check_launch("FilterInterpolation forward (warp-specialised TMA ring)") == 0 ? 1 : -1;
+}
+
 // ====================================================================================
 // backward
 // ====================================================================================
@@ -1285,6 +1602,12 @@ using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs /
 using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
 using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
 using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
+using FwdW1 = Cfg<32, 8, 64, 24, 256, 2>;   // warp-specialised ring: 8 consumer warps, 1 px / thread
+using FwdW2 = Cfg<32, 8, 64, 24, 128, 2>;   // 4 consumer warps, 2 px / thread
+using FwdW3 = Cfg<32, 8, 64, 24, 256, 3>;   // 2-slot ring, 3 CTAs / SM
+using FwdW4 = Cfg<32, 8, 64, 24, 128, 3>;
+using FwdW5 = Cfg<32, 16, 64, 32, 512, 1>;  // 16 consumer warps, one CTA / SM
+using FwdW6 = Cfg<32, 16, 64, 32, 256, 1>;
 using FWD_DEFAULT = FwdE6;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
 using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
@@ -1377,7 +1700,18 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 15: r = launch_fwd_pl<3, FwdL4, false>(stream, a); break;
             case 16: r = launch_fwd_pl<3, FwdL3, true>(stream, a); break;
             case 11: r = launch_fwd<3, FwdG>(stream, a); break;
-            default: r = launch_fwd<3, FWD_DEFAULT>(stream, a); break;
+            case 70: r = launch_fwd_ws<3, FwdW1, 3, 5>(stream, a); break;
+            case 80: r = launch_fwd_wr<3, FwdW1, 3, 5>(stream, a); break;
+            case 81: r = launch_fwd_wr<3, FwdW3, 3, 5>(stream, a); break;
+            case 82: r = launch_fwd_wr<3, FwdW3, 2, 3>(stream, a); break;
+            case 83: r = launch_fwd_wr<3, FwdW5, 3, 5>(stream, a); break;
+            case 71: r = launch_fwd_ws<3, FwdW2, 3, 5>(stream, a); break;
+            case 72: r = launch_fwd_ws<3, FwdW3, 2, 3>(stream, a); break;
+            case 73: r = launch_fwd_ws<3, FwdW4, 2, 3>(stream, a); break;
+            case 74: r = launch_fwd_ws<3, FwdW5, 3, 5>(stream, a); break;
+            case 75: r = launch_fwd_ws<3, FwdW6, 3, 5>(stream, a); break;
+            case 9: r = launch_fwd<3, FWD_DEFAULT>(stream, a); break;
+            default: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;  // best of the sweeps
         }
         if (a.prof && r == 1) prof_report(stream, a.prof);
         return r;

@@ -42,32 +42,36 @@ __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
     return x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1);
 }
 
-__global__ void __launch_bounds__(NT, 4)
-fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, const int b) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u));
+// One source tile.  The reference adds the SAME value (-fx, -fy, 1) to the four cells
+// (L..L+1) x (T..T+1) of every valid source pixel (my_lib_kernel.cu:1673-1689).  The sum over
+// sources is therefore a 2x2 box filter of the "corner histogram" A[T][L] += value: the tile
+// issues 3 shared atomics per source pixel (one cell) instead of 12, and the flush evaluates
+//     cell(x, y) = A[y][x] + A[y][x-1] + A[y-1][x] + A[y-1][x-1]
+// in exact integer arithmetic (every source is in exactly one A cell, so no partial sum can
+// exceed the tile total the fixed-point scale was sized for).  Taps whose cell is clamped at the
+// right / bottom image border (R == L or Bm == T) do not follow the box pattern: they go straight
+// to global memory, as do sources whose corner cell misses the staged box.
+//
+// Preconditions: a __syncthreads() separates this call from the CTA's previous use of `s`;
+// s.bar is an initialised mbarrier whose next phase parity is `phase`.
+__device__ __forceinline__ void splat_tile(Smem& s, const CUtensorMap* m_flow, int x0, int y0, int b, unsigned phase,
+                                           float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int W = p.W, H = p.H;
-
     if (tid == 0) {
-        tma::mbar_init(&s.bar, 1);
         s.bb[0] = INT_MAX; s.bb[1] = INT_MIN; s.bb[2] = INT_MAX; s.bb[3] = INT_MIN;
         s.maxbits = 0u;
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
+        tma::fence_proxy_async();  // the flow slot was last read with generic loads
         tma::mbar_expect_tx(&s.bar, sizeof(s.flow));
-        tma::load_4d(&s.flow[0][0][0], &m_flow, x0, y0, 0, b, &s.bar);
+        tma::load_4d(&s.flow[0][0][0], m_flow, x0, y0, 0, b, &s.bar);
     }
     {   // zero the box while the flow tile flies
         int4* z = reinterpret_cast<int4*>(&s.box[0][0][0]);
         for (int i = tid; i < 3 * BOX / 4; i += NT) z[i] = make_int4(0, 0, 0, 0);
     }
-    tma::mbar_wait(&s.bar, 0, 31);
+    __syncthreads();  // bounding-box cells initialised, box zeroed
+    tma::mbar_wait(&s.bar, phase, 31);
 
-    // ---- targets of my pixels, tile bounding box, tile max |flow|
+    // ---- targets of my pixels, tile bounding box of the corner cells, tile max |flow|
     float fx[PPT], fy[PPT];
     int L[PPT], T[PPT];
     bool ok[PPT];
@@ -98,20 +102,19 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
         atomicMin(&s.bb[2], mny); atomicMax(&s.bb[3], mxy);
         if (mb) atomicMax(&s.maxbits, mb);
     }
-    __syncthreads();  // also publishes the zeroed box
-    if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (nothing in flight)
+    __syncthreads();
+    if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (uniform; nothing in flight)
 
-    // target cells span [min L, max L + 1] x [min T, max T + 1]; box x origin multiple of 4 (TMA)
+    // corner cells span [min L, max L] x [min T, max T]; box x origin multiple of 4 (vector flush)
     int bx = s.bb[0], by = s.bb[2];
     {
-        const int need_w = s.bb[1] - s.bb[0] + 2 + 3, need_h = s.bb[3] - s.bb[2] + 2;
+        const int need_w = s.bb[1] - s.bb[0] + 1 + 3, need_h = s.bb[3] - s.bb[2] + 1;
         if (need_w > SW) bx += (need_w - SW) / 2;
         if (need_h > SH) by += (need_h - SH) / 2;
         bx = max(0, min(bx, W - SW)) & ~3;
         by = max(0, min(by, H - SH));
     }
-    // fixed-point scale (see header); a non-finite max (NaN flows are invalid, so only Inf-free
-    // finite values reach here) cannot occur: valid pixels have finite targets
+    // fixed-point scale (see header); valid pixels have finite flows, so M is finite
     const float M = __uint_as_float(s.maxbits);
     float scale = 1.0f, inv_scale = 1.0f;
     if (M > 0.f) {
@@ -123,58 +126,80 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
         inv_scale = ldexpf(1.0f, -e);
     }
 
-    float* ox = p.outp + (int64_t)b * p.out.b;
-    float* oy = ox + p.out.c;
-    float* cn = p.countp + (int64_t)b * p.count.b;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         if (!ok[k]) continue;
-        const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
-        const int qx = __float2int_rn(-fx[k] * scale), qy = __float2int_rn(-fy[k] * scale);
-        const int cxs[2] = {L[k], R}, cys[2] = {T[k], Bm};
+        const int ux = L[k] - bx, uy = T[k] - by;
+        const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+        if (in_box) {
+            atomicAdd(&s.box[0][uy][ux], __float2int_rn(-fx[k] * scale));
+            atomicAdd(&s.box[1][uy][ux], __float2int_rn(-fy[k] * scale));
+            atomicAdd(&s.box[2][uy][ux], 1);
+        }
+        const bool last_col = L[k] == W - 1, last_row = T[k] == H - 1;
+        if (__builtin_expect(!in_box || last_col || last_row, 0)) {
+            const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int cx = cxs[i], cy = cys[j];
-                const int ux = cx - bx, uy = cy - by;
-                // a clamped R / Bm repeats a cell (my_lib_kernel.cu:1673-1689): the repeat goes to
-                // global memory so that a box cell gets at most one hit per source pixel
-                const bool dup = (i == 1 && R == L[k]) || (j == 1 && Bm == T[k]);
-                if (!dup && (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH) {
-                    atomicAdd(&s.box[0][uy][ux], qx);
-                    atomicAdd(&s.box[1][uy][ux], qy);
-                    atomicAdd(&s.box[2][uy][ux], 1);
-                } else {
-                    red_add(ox + (int64_t)cy * p.out.h + cx, -fx[k]);
-                    red_add(oy + (int64_t)cy * p.out.h + cx, -fy[k]);
-                    red_add(cn + (int64_t)cy * p.count.h + cx, 1.0f);
+                for (int i = 0; i < 2; ++i) {
+                    // in the box: only the clamped repeats are missing from the 2x2 pattern
+                    if (in_box && !((i == 1 && last_col) || (j == 1 && last_row))) continue;
+                    const int cx = i ? R : L[k], cy = j ? Bm : T[k];
+                    red_add(ox + (int64_t)cy * out_h + cx, -fx[k]);
+                    red_add(oy + (int64_t)cy * out_h + cx, -fy[k]);
+                    red_add(cn + (int64_t)cy * cnt_h + cx, 1.0f);
                 }
-            }
+        }
     }
     __syncthreads();
-    // ---- flush: only the cells the tile actually hit (their bounding box, clipped to the staged
-    // box), four cells per 128-bit vector reduction (REDG.E.ADD.F32x4), all-zero vectors skipped.
-    // (A dense TMA reduce-add of the whole box is wasteful here: when flows converge, thousands of
-    // tiles would all add mostly-zero boxes onto the same few sectors.)
+    // ---- flush: 2x2 box filter over the touched corner cells, four output cells per 128-bit
+    // vector reduction (REDG.E.ADD.F32x4), all-zero vectors skipped.  Output cells beyond the image
+    // are dropped (their taps were sent directly above).
     {
-        const int cx0 = max(s.bb[0], bx) - bx, cx1 = min(s.bb[1] + 1, bx + SW - 1) - bx;
-        const int cy0 = max(s.bb[2], by) - by, cy1 = min(s.bb[3] + 1, by + SH - 1) - by;
-        if (cx0 <= cx1 && cy0 <= cy1) {
-            const int v0 = cx0 >> 2, nv = (cx1 >> 2) - v0 + 1, nr = cy1 - cy0 + 1;
+        const int ax0 = max(s.bb[0], bx) - bx, ax1 = min(s.bb[1], bx + SW - 1) - bx;
+        const int ay0 = max(s.bb[2], by) - by, ay1 = min(s.bb[3], by + SH - 1) - by;
+        if (ax0 <= ax1 && ay0 <= ay1) {
+            const int cx1 = min(ax1 + 1, W - 1 - bx), cy1 = min(ay1 + 1, H - 1 - by);
+            const int v0 = ax0 >> 2, nv = (cx1 >> 2) - v0 + 1, nr = cy1 - ay0 + 1;
             for (int i = tid; i < 3 * nr * nv; i += NT) {
                 const int pl = i / (nr * nv), r = i - pl * nr * nv;
-                const int uy = cy0 + r / nv, ux = (v0 + r % nv) << 2;
-                const int4 q = *reinterpret_cast<const int4*>(&s.box[pl][uy][ux]);
-                if ((q.x | q.y | q.z | q.w) == 0) continue;
+                const int uy = ay0 + r / nv, ux = (v0 + r % nv) << 2;  // ux <= SW (a multiple of 4)
+                int a[2][5];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int yy = uy - 1 + rr;
+                    const bool row_ok = (unsigned)yy < (unsigned)SH;
+                    a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
+                    int4 q = make_int4(0, 0, 0, 0);
+                    if (row_ok && ux < SW) q = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
+                    a[rr][1] = q.x; a[rr][2] = q.y; a[rr][3] = q.z; a[rr][4] = q.w;
+                }
+                int q[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
+                if ((q[0] | q[1] | q[2] | q[3]) == 0) continue;
                 const float sc = pl == 2 ? 1.0f : inv_scale;
-                const float4 v = make_float4((float)q.x * sc, (float)q.y * sc, (float)q.z * sc, (float)q.w * sc);
-                float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) +
-                             (int64_t)(by + uy) * (pl == 2 ? p.count.h : p.out.h) + bx + ux;
+                const float4 v = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
+                float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) + (int64_t)(by + uy) * (pl == 2 ? cnt_h : out_h) + bx + ux;
                 atomicAdd(reinterpret_cast<float4*>(dst), v);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(NT, 4)
+fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, const int b) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u));
+    if (threadIdx.x == 0) {
+        tma::mbar_init(&s.bar, 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    float* ox = p.outp + (int64_t)b * p.out.b;
+    splat_tile(s, &m_flow, blockIdx.x * TW, blockIdx.y * TH, b, 0u, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b,
+               p.out.h, p.count.h, p.W, p.H);
 }
 
 // ------------------------------------------------------------------------------------

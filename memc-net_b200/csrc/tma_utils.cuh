@@ -30,6 +30,10 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// plain arrival (release): a consumer warp hands a ring slot back to the producer
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // try_wait may suspend the thread in hardware for up to this many ns before reporting "not
 // yet": waiting warps then stop competing for issue slots with the warps that compute
 // (without the hint ~40 % of the executed instructions of the first version were wait spins).
