@@ -1,25 +1,26 @@
-// flow_projection_fast.cu -- FlowProjection forward for sm_100a: shared-memory privatised splat.
+// flow_projection_fast.cu -- FlowProjection forward for sm_100a: shared-memory privatised splat,
+// occupancy-mask hole filling, and (for MEMC_B200_OVERWRITE calls) the whole forward as one
+// persistent software-pipelined kernel.
 //
 // Same arithmetic as flow_projection.cu (reference my_lib_kernel.cu:1630-1836), different data
 // movement.  The legacy splat issues 12 global float atomics per source pixel (ncu: ~6.6 L2
 // reduction sectors per pixel, L2-atomic bound; 31 ms per 16 frames when flows converge).  Here a
 // CTA owns a TW x TH tile of SOURCE pixels:
 //
-//   TMA   flow tile (TW,TH,2) -> smem
-//   ...   targets p + flow, bounding box of the 2x2 target cells, M = max|flow| over the tile
+//   LDG   the flow of the tile's pixels, straight into registers (prefetched one tile ahead in
+//         the persistent kernel)
+//   ...   targets p + flow, bounding box of the target cells, M = max|flow| over the tile
 //   ...   the tile's contributions (-fx, -fy, +1) are accumulated in a SHARED-MEMORY box of
 //         3 planes (x, y, count) with native int32 shared atomics: count is an integer anyway,
 //         -fx / -fy are accumulated in fixed point with a per-tile power-of-two scale
-//         2^e, M * (TW*TH) * 2^e < 2^31 (a cell receives at most one unclamped hit per pixel;
-//         border-clamped duplicate hits bypass the box) -- order independent within the tile;
+//         2^e, M * (TW*TH) * 2^e < 2^31 -- order independent within the tile.
+//         The reference adds the SAME value to the four cells (L..L+1) x (T..T+1), so the box
+//         holds the "corner histogram" A[T][L] (3 shared atomics per source, not 12) and the
+//         flush applies the 2x2 box filter;
 //   ...   the touched part of the box is flushed with 128-bit vector reductions (4 cells each,
 //         all-zero vectors skipped).  Targets outside the box fall back to global atomics.
-//
-// The frames are processed ONE AT A TIME (memset -> splat -> average -> fill-hole per frame): a
-// frame's count+output planes (25 MB at 1080p) then stay L2-resident between the passes instead
-// of making three trips to HBM per pass over the whole batch.
 #include "flow_projection.cuh"
-#include "tma_utils.cuh"
+#include <limits.h>
 #include <stdlib.h>
 
 namespace memc {
@@ -31,15 +32,37 @@ constexpr int SW = 96, SH = 32;                                // target box (pi
 constexpr int BOX = SW * SH;
 
 struct __align__(128) Smem {
-    float flow[2][TH][TW];  // 8 KB
-    int box[3][SH][SW];     // x, y (fixed point) and count: 36 KB
-    uint64_t bar;
+    int box[3][SH][SW];  // x, y (fixed point) and count: 36 KB
     int bb[4];
     unsigned maxbits;
 };
 
 __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
     return x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1);
+}
+
+// pixel k of this thread inside a source tile: a warp owns 32-pixel row segments
+__device__ __forceinline__ void tile_pixel(int k, int& xl, int& yl) {
+    const int seg = (threadIdx.x >> 5) + k * (NT / 32);
+    yl = seg / (TW / 32);
+    xl = (threadIdx.x & 31) + 32 * (seg % (TW / 32));
+}
+
+// flow of this thread's pixels of tile (x0, y0) of frame b: coalesced read-only loads
+__device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View fv, int x0, int y0, int b, int W, int H,
+                                          float (&fx)[PPT], float (&fy)[PPT]) {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        int xl, yl;
+        tile_pixel(k, xl, yl);
+        const int x = x0 + xl, y = y0 + yl;
+        fx[k] = fy[k] = 0.f;
+        if (x < W && y < H) {
+            const float* f = flowp + (int64_t)b * fv.b + (int64_t)y * fv.h + x;
+            fx[k] = ldg_stream(f);
+            fy[k] = ldg_stream(f + fv.c);
+        }
+    }
 }
 
 // One source tile.  The reference adds the SAME value (-fx, -fy, 1) to the four cells
@@ -52,38 +75,33 @@ __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
 // right / bottom image border (R == L or Bm == T) do not follow the box pattern: they go straight
 // to global memory, as do sources whose corner cell misses the staged box.
 //
-// Preconditions: a __syncthreads() separates this call from the CTA's previous use of `s`;
-// s.bar is an initialised mbarrier whose next phase parity is `phase`.
-__device__ __forceinline__ void splat_tile(Smem& s, const CUtensorMap* m_flow, int x0, int y0, int b, unsigned phase,
+// CORNER = true (persistent pipeline): the destination planes hold the corner histogram itself;
+// the box is dumped as it is, out-of-box sources add their one corner cell, and the 2x2 filter
+// (with the border repeats) is applied by the averaging pass.
+//
+// Precondition: a __syncthreads() separates this call from the CTA's previous use of `s`.
+template <bool CORNER>
+__device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], const float (&fy)[PPT], int x0, int y0,
                                            float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
         s.bb[0] = INT_MAX; s.bb[1] = INT_MIN; s.bb[2] = INT_MAX; s.bb[3] = INT_MIN;
         s.maxbits = 0u;
-        tma::fence_proxy_async();  // the flow slot was last read with generic loads
-        tma::mbar_expect_tx(&s.bar, sizeof(s.flow));
-        tma::load_4d(&s.flow[0][0][0], m_flow, x0, y0, 0, b, &s.bar);
     }
-    {   // zero the box while the flow tile flies
+    {   // zero the box
         int4* z = reinterpret_cast<int4*>(&s.box[0][0][0]);
         for (int i = tid; i < 3 * BOX / 4; i += NT) z[i] = make_int4(0, 0, 0, 0);
     }
-    __syncthreads();  // bounding-box cells initialised, box zeroed
-    tma::mbar_wait(&s.bar, phase, 31);
-
     // ---- targets of my pixels, tile bounding box of the corner cells, tile max |flow|
-    float fx[PPT], fy[PPT];
     int L[PPT], T[PPT];
     bool ok[PPT];
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
     float mloc = 0.f;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-        const int seg = warp + k * (NT / 32);
-        const int yl = seg / (TW / 32), xl = lane + 32 * (seg % (TW / 32));
+        int xl, yl;
+        tile_pixel(k, xl, yl);
         const int x = x0 + xl, y = y0 + yl;
-        fx[k] = s.flow[0][yl][xl];
-        fy[k] = s.flow[1][yl][xl];
         const float x2 = (float)x + fx[k], y2 = (float)y + fy[k];
         ok[k] = x < W && y < H && fp_valid(x2, y2, W, H);
         L[k] = ok[k] ? (int)x2 : 0;
@@ -97,13 +115,14 @@ __device__ __forceinline__ void splat_tile(Smem& s, const CUtensorMap* m_flow, i
     mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);  // REDUX
     mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mloc));
+    __syncthreads();  // bounding-box cells initialised, box zeroed
     if (lane == 0 && mnx <= mxx) {
         atomicMin(&s.bb[0], mnx); atomicMax(&s.bb[1], mxx);
         atomicMin(&s.bb[2], mny); atomicMax(&s.bb[3], mxy);
         if (mb) atomicMax(&s.maxbits, mb);
     }
     __syncthreads();
-    if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (uniform; nothing in flight)
+    if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (uniform across the CTA)
 
     // corner cells span [min L, max L] x [min T, max T]; box x origin multiple of 4 (vector flush)
     int bx = s.bb[0], by = s.bb[2];
@@ -136,6 +155,14 @@ __device__ __forceinline__ void splat_tile(Smem& s, const CUtensorMap* m_flow, i
             atomicAdd(&s.box[1][uy][ux], __float2int_rn(-fy[k] * scale));
             atomicAdd(&s.box[2][uy][ux], 1);
         }
+        if (CORNER) {
+            if (__builtin_expect(!in_box, 0)) {
+                red_add(ox + (int64_t)T[k] * out_h + L[k], -fx[k]);
+                red_add(oy + (int64_t)T[k] * out_h + L[k], -fy[k]);
+                red_add(cn + (int64_t)T[k] * cnt_h + L[k], 1.0f);
+            }
+            continue;
+        }
         const bool last_col = L[k] == W - 1, last_row = T[k] == H - 1;
         if (__builtin_expect(!in_box || last_col || last_row, 0)) {
             const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
@@ -153,56 +180,65 @@ __device__ __forceinline__ void splat_tile(Smem& s, const CUtensorMap* m_flow, i
         }
     }
     __syncthreads();
-    // ---- flush: 2x2 box filter over the touched corner cells, four output cells per 128-bit
-    // vector reduction (REDG.E.ADD.F32x4), all-zero vectors skipped.  Output cells beyond the image
+    // ---- flush the touched corner cells: four cells per 128-bit vector reduction
+    // (REDG.E.ADD.F32x4), all-zero vectors skipped; a warp walks rows, its lanes the vectors of a
+    // row.  !CORNER: the 2x2 box filter is applied on the way out; output cells beyond the image
     // are dropped (their taps were sent directly above).
     {
         const int ax0 = max(s.bb[0], bx) - bx, ax1 = min(s.bb[1], bx + SW - 1) - bx;
         const int ay0 = max(s.bb[2], by) - by, ay1 = min(s.bb[3], by + SH - 1) - by;
         if (ax0 <= ax1 && ay0 <= ay1) {
-            const int cx1 = min(ax1 + 1, W - 1 - bx), cy1 = min(ay1 + 1, H - 1 - by);
-            const int v0 = ax0 >> 2, nv = (cx1 >> 2) - v0 + 1, nr = cy1 - ay0 + 1;
-            for (int i = tid; i < 3 * nr * nv; i += NT) {
-                const int pl = i / (nr * nv), r = i - pl * nr * nv;
-                const int uy = ay0 + r / nv, ux = (v0 + r % nv) << 2;  // ux <= SW (a multiple of 4)
-                int a[2][5];
+            const int cx1 = CORNER ? ax1 : min(ax1 + 1, W - 1 - bx), cy1 = CORNER ? ay1 : min(ay1 + 1, H - 1 - by);
+            const int v0 = ax0 >> 2, v1 = cx1 >> 2;  // vector columns (ux = 4 v <= SW)
+            for (int uy = ay0 + (tid >> 5); uy <= cy1; uy += NT / 32)
+                for (int v = v0 + lane; v <= v1; v += 32) {
+                    const int ux = v << 2;
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int yy = uy - 1 + rr;
-                    const bool row_ok = (unsigned)yy < (unsigned)SH;
-                    a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
-                    int4 q = make_int4(0, 0, 0, 0);
-                    if (row_ok && ux < SW) q = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
-                    a[rr][1] = q.x; a[rr][2] = q.y; a[rr][3] = q.z; a[rr][4] = q.w;
+                    for (int pl = 0; pl < 3; ++pl) {
+                        int q[4];
+                        if (CORNER) {
+                            const int4 t = *reinterpret_cast<const int4*>(&s.box[pl][uy][ux]);
+                            q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
+                        } else {
+                            int a[2][5];
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                const int yy = uy - 1 + rr;
+                                const bool row_ok = (unsigned)yy < (unsigned)SH;
+                                a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
+                                int4 t = make_int4(0, 0, 0, 0);
+                                if (row_ok && ux < SW) t = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
+                                a[rr][1] = t.x; a[rr][2] = t.y; a[rr][3] = t.z; a[rr][4] = t.w;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
+                        }
+                        if ((q[0] | q[1] | q[2] | q[3]) == 0) continue;
+                        const float sc = pl == 2 ? 1.0f : inv_scale;
+                        const float4 val = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
+                        float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) + (int64_t)(by + uy) * (pl == 2 ? cnt_h : out_h) + bx + ux;
+                        atomicAdd(reinterpret_cast<float4*>(dst), val);
+                    }
                 }
-                int q[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
-                if ((q[0] | q[1] | q[2] | q[3]) == 0) continue;
-                const float sc = pl == 2 ? 1.0f : inv_scale;
-                const float4 v = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
-                float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) + (int64_t)(by + uy) * (pl == 2 ? cnt_h : out_h) + bx + ux;
-                atomicAdd(reinterpret_cast<float4*>(dst), v);
-            }
         }
     }
 }
 
-__global__ void __launch_bounds__(NT, 4)
-fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, const int b) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u));
-    if (threadIdx.x == 0) {
-        tma::mbar_init(&s.bar, 1);
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
+// ------------------------------------------------------------------------------------
+// Reference-contract calls (the caller's pre-zeroed buffers are accumulated into): frame by frame
+// memset -> splat -> average + masks, then one fill-hole launch.  A frame's count+output planes
+// (25 MB at 1080p) stay L2-resident between the passes.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 4) fp_splat_kernel(const FpArgs p, const int b) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    float fx[PPT], fy[PPT];
+    load_flow(p.flowp, p.flow, x0, y0, b, p.W, p.H, fx, fy);
     float* ox = p.outp + (int64_t)b * p.out.b;
-    splat_tile(s, &m_flow, blockIdx.x * TW, blockIdx.y * TH, b, 0u, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b,
-               p.out.h, p.count.h, p.W, p.H);
+    splat_tile<false>(s, fx, fy, x0, y0, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b, p.out.h, p.count.h, p.W, p.H);
 }
 
-// ------------------------------------------------------------------------------------
 // average + occupancy bit masks.  One CTA = one 128 x 32 pixel block:
 //   out /= count where count > 0 (my_lib_kernel.cu:1730-1736), and
 //   rowmask[b][y][x/32]  bit (x%32) = count[b][y][x] > 0      (32 pixels of a row per word)
@@ -210,7 +246,6 @@ fp_splat_kernel(const __grid_constant__ CUtensorMap m_flow, const FpArgs p, cons
 // The masks turn fill-hole's per-pixel linear walks (O(W) loads when holes are large: the
 // legacy kernel needs 30 ms per 16 frames when the flow converges and most of the frame is a
 // hole) into a few word loads plus clz / ffs -- with exactly the same result.
-// ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict__ out, const float* __restrict__ count,
                                                               unsigned* __restrict__ rowmask, unsigned* __restrict__ colmask,
                                                               int W, int H, int Wt, int Ht, int64_t out_c) {
@@ -326,8 +361,329 @@ __global__ void __launch_bounds__(256) fp_fillhole_mask_kernel(float* __restrict
     oy[row + x] = sy / den;
 }
 
-// Library-owned stream-ordered memory pool for the occupancy masks (the only scratch memory the
-// library ever allocates).  A private pool with a high release threshold keeps the blocks
+// ------------------------------------------------------------------------------------
+// The whole forward as ONE persistent cooperative kernel (MEMC_B200_OVERWRITE calls).
+//
+// The per-frame sequence above needs 4-5 launches per frame, each far too short (10-30 us) to
+// fill the GPU between launch ramp and tail.  Here every CTA keeps pulling work items from ONE
+// ordered queue; the items of a "cycle" c are
+//
+//     average(frame c-2) tiles,  fill-hole(frame c-3) tiles,  splat(frame c) tiles
+//
+// and an item waits (per-frame completion counters, acquire loads -- no grid-wide barrier) for
+//     splat(f)     <- average(f-3) complete   (the accumulator slot f % 3 was handed back zeroed)
+//     average(f)   <- splat(f) complete
+//     fill-hole(f) <- average(f) complete      (needs the whole frame's occupancy masks)
+// Every dependency lies at least a full cycle back in the queue (or behind the cycle's average /
+// fill items), so the waits are already satisfied when an item is pulled; all CTAs are
+// co-resident (cooperative launch) and dependencies only point backwards in queue order, so the
+// oldest unfinished item can always run.
+//
+// The accumulators live in a three-frame scratch ring (75 MB at 1080p) that stays mostly
+// L2-resident: HBM sees the flow once (8 B/px) and the results once (12 B/px).  The flow of the
+// NEXT splat tile is prefetched into registers while the current item is processed.
+//
+// Fill-hole uses two mask levels: the 32-pixel words of the per-frame kernels plus one summary
+// bit per word (row: which words of the row are non-empty; column likewise), so a search is a
+// handful of loads however large the hole is.
+//
+// Coherence: everything other CTAs produced inside the launch is read with ld.global.cg (L2);
+// the masks (written once, never read before their frame's fill items, 128-byte padded per
+// frame) may go through L1.
+// ------------------------------------------------------------------------------------
+struct FpPipe {
+    int B, H, W, fillhole;
+    const float* flowp;
+    View flow;
+    float* outp;
+    float* countp;
+    int64_t out_b, out_c, cnt_b;
+    float* scratch;     // [3][3][H*W]: sum x, sum y, count of three frames in flight; zero on entry
+    unsigned* ctrl;     // [0] queue head, [1 + f] splat tiles of frame f done, [1 + B + f] average tiles done; zero on entry
+    unsigned* rowsum;   // [B][rs_stride]  (H x Wt32 words used)   zero on entry
+    unsigned* colsum;   // [B][cs_stride]  (Ht32 x W words used)   zero on entry
+    unsigned* rowmask;  // [B][rm_stride]  (H x Wt words used)
+    unsigned* colmask;  // [B][cm_stride]  (Ht x W words used)
+    int64_t rs_stride, cs_stride, rm_stride, cm_stride;  // per-frame strides, multiples of 32 words
+    int Wt, Ht, Wt32, Ht32, nS_x, nS_y, nA_x, nA_y;
+    int dbg;  // development (MEMC_FP_DBG): 1 skip splat, 2 skip average, 4 skip fill -- timing only
+};
+
+// thread 0: spin until *counter >= target (acquire); a lost producer becomes a launch error
+__device__ __forceinline__ void wait_count(const unsigned* counter, unsigned target) {
+    for (unsigned spins = 0;; ++spins) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) return;
+        __nanosleep(64);
+        if (spins > (1u << 24)) {  // ~1 s
+            printf("memc_b200: FlowProjection pipeline dependency timed out in block %d\n", blockIdx.x);
+            __trap();
+        }
+    }
+}
+
+// average + masks of one 128 x 32 block of frame f (layout of fp_average_mask_kernel); the
+// accumulator cells it consumed are handed back zeroed
+__device__ __forceinline__ void pipe_average_tile(const FpPipe& p, unsigned (*rw)[4], int idx, int f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bxx = idx % p.nA_x, byy = idx / p.nA_x;
+    const int W = p.W, H = p.H;
+    const int64_t plane = (int64_t)H * W;
+    float* acc = p.scratch + (int64_t)(f % 3) * 3 * plane;
+    float* ox = p.outp + (int64_t)f * p.out_b;
+    float* oy = ox + p.out_c;
+    float* cn = p.countp + (int64_t)f * p.cnt_b;
+    unsigned* rowmask = p.rowmask + (int64_t)f * p.rm_stride;
+    unsigned* colmask = p.colmask + (int64_t)f * p.cm_stride;
+    unsigned* rowsum = p.rowsum + (int64_t)f * p.rs_stride;
+    unsigned* colsum = p.colsum + (int64_t)f * p.cs_stride;
+    const int x = bxx * 128 + lane * 4;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        // two rows per round, all six 128-bit loads in flight together (the pass is latency bound)
+        float4 c[2], sx[2], sy[2];
+        bool in[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int y = byy * 32 + warp + 8 * (2 * kk + h);
+            in[h] = x < W && y < H;
+            c[h] = sx[h] = sy[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[h]) {
+                const int64_t o = (int64_t)y * W + x;
+                c[h] = __ldcg(reinterpret_cast<const float4*>(acc + 2 * plane + o));
+                sx[h] = __ldcg(reinterpret_cast<const float4*>(acc + o));
+                sy[h] = __ldcg(reinterpret_cast<const float4*>(acc + plane + o));
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = warp + 8 * (2 * kk + h), y = byy * 32 + r;
+            const float4 cc = c[h];
+            if (in[h]) {
+                const int64_t o = (int64_t)y * W + x;
+                float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
+                if (cc.x > 0.f || cc.y > 0.f || cc.z > 0.f || cc.w > 0.f) {
+                    // my_lib_kernel.cu:1730-1736: divide where count > 0 (nothing was added elsewhere)
+                    if (cc.x > 0.f) { vx.x = sx[h].x / cc.x; vy.x = sy[h].x / cc.x; }
+                    if (cc.y > 0.f) { vx.y = sx[h].y / cc.y; vy.y = sy[h].y / cc.y; }
+                    if (cc.z > 0.f) { vx.z = sx[h].z / cc.z; vy.z = sy[h].z / cc.z; }
+                    if (cc.w > 0.f) { vx.w = sx[h].w / cc.w; vy.w = sy[h].w / cc.w; }
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __stcg(reinterpret_cast<float4*>(acc + o), z);
+                    __stcg(reinterpret_cast<float4*>(acc + plane + o), z);
+                    __stcg(reinterpret_cast<float4*>(acc + 2 * plane + o), z);
+                }
+                __stcg(reinterpret_cast<float4*>(ox + o), vx);  // fill-hole reads neighbours back from L2
+                __stcg(reinterpret_cast<float4*>(oy + o), vy);
+                __stcs(reinterpret_cast<float4*>(cn + o), cc);
+            }
+            unsigned nib = (cc.x > 0.f ? 1u : 0u) | (cc.y > 0.f ? 2u : 0u) | (cc.z > 0.f ? 4u : 0u) | (cc.w > 0.f ? 8u : 0u);
+            unsigned word = nib << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            // summary bits of this row's four words (4 | 32: they share one summary word), on lane 0
+            const int wi = bxx * 4 + (lane >> 3);
+            unsigned sbit = (word != 0u && wi < p.Wt) ? 1u << (wi & 31) : 0u;
+            sbit |= __shfl_xor_sync(0xffffffffu, sbit, 8);
+            sbit |= __shfl_xor_sync(0xffffffffu, sbit, 16);
+            if ((lane & 7) == 0) {
+                rw[r][lane >> 3] = word;
+                if (y < H && wi < p.Wt) rowmask[(int64_t)y * p.Wt + wi] = word;
+            }
+            if (lane == 0 && y < H && sbit) atomicOr(&rowsum[(int64_t)y * p.Wt32 + ((bxx * 4) >> 5)], sbit);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cx = bxx * 128 + threadIdx.x;
+        if (cx < W) {
+            unsigned col = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) col |= ((rw[k][threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u) << k;
+            colmask[(int64_t)byy * W + cx] = col;
+            if (col) atomicOr(&colsum[(int64_t)(byy >> 5) * W + cx], 1u << (byy & 31));
+        }
+    }
+}
+
+// highest set bit strictly below position `pos` in a two-level bit set; -1 if none.
+// words[i * wstride] = level-1 word i, sums[j * sstride] = summary word j (bit = word non-empty)
+__device__ __forceinline__ int find_below(const unsigned* words, int64_t wstride, const unsigned* sums, int64_t sstride,
+                                          int pos, unsigned word0) {
+    const int wi0 = pos >> 5;
+    const unsigned m = word0 & ((1u << (pos & 31)) - 1u);
+    if (m) return wi0 * 32 + 31 - __clz(m);
+    for (int si = wi0 >> 5; si >= 0; --si) {
+        unsigned sm = sums[si * sstride];
+        if (si == (wi0 >> 5)) sm &= (1u << (wi0 & 31)) - 1u;  // words strictly below wi0
+        if (sm) {
+            const int wi = si * 32 + 31 - __clz(sm);
+            return wi * 32 + 31 - __clz(words[wi * wstride]);
+        }
+    }
+    return -1;
+}
+// lowest set bit strictly above `pos` (unit strides); n_sum = number of summary words
+__device__ __forceinline__ int find_above(const unsigned* words, const unsigned* sums, int n_sum, int pos, unsigned word0) {
+    const int wi0 = pos >> 5, bit = pos & 31;
+    const unsigned m = bit == 31 ? 0u : (word0 & ~((2u << bit) - 1u));
+    if (m) return wi0 * 32 + __ffs(m) - 1;
+    for (int si = wi0 >> 5; si < n_sum; ++si) {
+        unsigned sm = sums[si];
+        if (si == (wi0 >> 5)) sm = (wi0 & 31) == 31 ? 0u : (sm & ~((2u << (wi0 & 31)) - 1u));  // words strictly above wi0
+        if (sm) {
+            const int wi = si * 32 + __ffs(sm) - 1;
+            return wi * 32 + __ffs(words[wi]) - 1;
+        }
+    }
+    return -1;
+}
+
+// fill-hole of one 128 x 32 block of frame f
+__device__ __forceinline__ void pipe_fill_tile(const FpPipe& p, unsigned (*rw)[4], int idx, int f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bxx = idx % p.nA_x, byy = idx / p.nA_x;
+    const int W = p.W, H = p.H;
+    float* ox = p.outp + (int64_t)f * p.out_b;
+    float* oy = ox + p.out_c;
+    const unsigned* rowmask = p.rowmask + (int64_t)f * p.rm_stride;
+    const unsigned* colmask = p.colmask + (int64_t)f * p.cm_stride;
+    const unsigned* rowsum = p.rowsum + (int64_t)f * p.rs_stride;
+    const unsigned* colsum = p.colsum + (int64_t)f * p.cs_stride;
+    // the block's 32 x 4 row words, staged once; most blocks have no hole at all
+    int holes = 0;
+    if (threadIdx.x < 128) {
+        const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const int y = byy * 32 + r, wi = bxx * 4 + q;
+        unsigned word = 0xffffffffu;
+        if (y < H && wi < p.Wt) {
+            word = rowmask[(int64_t)y * p.Wt + wi];
+            const int valid = W - wi * 32;  // pixels of this word inside the image
+            if (valid < 32) word |= ~((1u << valid) - 1u);
+        }
+        rw[r][q] = word;
+        holes = word != 0xffffffffu;
+    }
+    if (!__syncthreads_or(holes)) return;
+#pragma unroll 2
+    for (int sub = 0; sub < 16; ++sub) {  // 16 sub-blocks of 32 x 8 (one row per warp)
+        const int q = sub & 3, r = (sub >> 2) * 8 + warp;
+        const int x = bxx * 128 + q * 32 + lane, y = byy * 32 + r;
+        const unsigned word = rw[r][q];
+        if ((word >> lane) & 1u) continue;  // counted pixel (or outside the image): not a hole
+        const unsigned* rm = rowmask + (int64_t)y * p.Wt;
+        const unsigned mword = rm[x >> 5];
+        const int lo = find_below(rm, 1, rowsum + (int64_t)y * p.Wt32, 1, x, mword);
+        const int ro = find_above(rm, rowsum + (int64_t)y * p.Wt32, p.Wt32, x, mword);
+        const unsigned* cm = colmask + x;  // [y/32][x]
+        const int uo = find_below(cm, W, colsum + x, W, y, cm[(int64_t)(y >> 5) * W]);
+        if (lo < 0 && ro < 0 && uo < 0) continue;  // nothing found: stays 0
+        float sx = 0.f, sy = 0.f, den = 0.f;
+        const int64_t row = (int64_t)y * W;
+        if (lo >= 0) { sx += __ldcg(ox + row + lo); sy += __ldcg(oy + row + lo); den += 1.f; }
+        if (ro >= 0) { sx += __ldcg(ox + row + ro); sy += __ldcg(oy + row + ro); den += 1.f; }
+        if (uo >= 0) { sx += __ldcg(ox + (int64_t)uo * W + x); sy += __ldcg(oy + (int64_t)uo * W + x); den += 1.f; }
+        ox[row + x] = sx / den;
+        oy[row + x] = sy / den;
+    }
+}
+
+// queue position -> work item.  type 0 splat, 1 average, 2 fill-hole, -1 nothing (frame out of
+// range), -2 end of queue.  Decoded by thread 0 only (runtime divisions) and published through smem.
+struct Item {
+    int type, frame, tile, tx;  // tx: splat tile column (tile = row), else unused
+};
+__device__ __forceinline__ Item decode_item(const FpPipe& p, int nS, int nA, int total, int q) {
+    Item it;
+    it.frame = it.tile = it.tx = 0;
+    if (q >= total) { it.type = -2; return it; }
+    const int per_cycle = 2 * nA + nS;
+    const int c = q / per_cycle, r = q - c * per_cycle;
+    if (r < nA) { it.type = 1; it.frame = c - 2; it.tile = r; }
+    else if (r < 2 * nA) { it.type = 2; it.frame = c - 3; it.tile = r - nA; }
+    else { it.type = 0; it.frame = c; it.tile = (r - 2 * nA) / p.nS_x; it.tx = (r - 2 * nA) - it.tile * p.nS_x; }
+    if (it.frame < 0 || it.frame >= p.B || (it.type == 2 && !p.fillhole)) it.type = -1;
+    return it;
+}
+
+// completion signal: the release orders the CTA's writes and reductions (observed by this thread
+// through the preceding bar.sync) before the counter update
+__device__ __forceinline__ void signal_done(unsigned* counter, unsigned n) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ Item s_q[3];  // items fetched ahead by thread 0
+    unsigned (*rw)[4] = reinterpret_cast<unsigned(*)[4]>(&s.box[0][0][0]);  // 32 x 4 words, aliases the box
+    const int tid = threadIdx.x;
+    const int nS = p.nS_x * p.nS_y, nA = p.nA_x * p.nA_y;
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int total = (p.B + 3) * (2 * nA + nS);
+    unsigned* done_S = p.ctrl + 1;
+    unsigned* done_A = p.ctrl + 1 + p.B;
+    int known_S = -1, known_A = -1;  // frames up to here are known complete (uniform across the CTA)
+    unsigned pending = 0;            // finished items of the current run not yet signalled
+    if (tid == 0) {
+        s_q[0] = decode_item(p, nS, nA, total, (int)atomicAdd(p.ctrl, 1u));
+        s_q[1] = decode_item(p, nS, nA, total, (int)atomicAdd(p.ctrl, 1u));
+    }
+    __syncthreads();
+    Item it = s_q[0], in = s_q[1];
+    int slot = 2;
+    float cfx[PPT], cfy[PPT], nfx[PPT], nfy[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) cfx[k] = cfy[k] = nfx[k] = nfy[k] = 0.f;
+    if (it.type == 0) load_flow(p.flowp, p.flow, it.tx * TW, it.tile * TH, it.frame, p.W, p.H, cfx, cfy);
+    while (it.type != -2) {
+        int fetched = 0;
+        if (tid == 0) fetched = (int)atomicAdd(p.ctrl, 1u);  // the position after next; consumed at the end of this item
+        if (in.type == 0) load_flow(p.flowp, p.flow, in.tx * TW, in.tile * TH, in.frame, p.W, p.H, nfx, nfy);
+        {   // dependency of this item: normally long satisfied and already known
+            const unsigned* dep = nullptr;
+            unsigned need = 0;
+            if (it.type == 0 && it.frame >= 3 && known_A < it.frame - 3) { dep = done_A + it.frame - 3; need = nA; known_A = it.frame - 3; }
+            if (it.type == 1 && known_S < it.frame) { dep = done_S + it.frame; need = nS; known_S = it.frame; }
+            if (it.type == 2 && known_A < it.frame) { dep = done_A + it.frame; need = nA; known_A = it.frame; }
+            if (dep) {
+                if (tid == 0) wait_count(dep, need);
+                __syncthreads();
+            }
+        }
+        if (it.type == 0) {
+            if (!(p.dbg & 1)) {
+                float* acc = p.scratch + (int64_t)(it.frame % 3) * 3 * plane;
+                splat_tile<false>(s, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W, p.H);
+            }
+        } else if (it.type == 1) {
+            if (!(p.dbg & 2)) pipe_average_tile(p, rw, it.tile, it.frame);
+        } else if (it.type == 2) {
+            if (!(p.dbg & 4)) pipe_fill_tile(p, rw, it.tile, it.frame);
+        }
+        if (tid == 0) s_q[slot] = decode_item(p, nS, nA, total, fetched);
+        __syncthreads();  // s_q[slot] published; this item is done with shared memory and with its global writes
+        // completion counters: one signal per run of same-kind items (a CTA's splat tiles of a frame
+        // come in a row); a run ends when the next item differs
+        if (it.type == 0 || it.type == 1) {
+            ++pending;
+            if (in.type != it.type || in.frame != it.frame) {
+                if (tid == 0) signal_done((it.type == 0 ? done_S : done_A) + it.frame, pending);
+                pending = 0;
+            }
+        }
+        it = in;
+        in = s_q[slot];
+        slot = slot == 2 ? 0 : slot + 1;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) { cfx[k] = nfx[k]; cfy[k] = nfy[k]; }
+    }
+}
+
+// Library-owned stream-ordered memory pool for scratch memory (occupancy masks, the pipeline's
+// accumulator ring).  A private pool with a high release threshold keeps the blocks
 // cached across calls; the device's default pool would hand them back to the OS at every
 // synchronisation (measured: 2 ms per call).  One pool per device, created on first use.
 cudaMemPool_t scratch_pool() {
@@ -352,21 +708,86 @@ cudaMemPool_t scratch_pool() {
     return pools[dev];
 }
 
+size_t pad32(size_t n) { return (n + 31) & ~(size_t)31; }
+
+// OVERWRITE calls: the persistent pipeline.  1 = handled, 0 = not applicable, -1 = error
+int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
+    const size_t smem = sizeof(Smem);
+    if (!ensure_dynamic_smem(fp_pipeline_kernel, smem)) return 0;
+    int dev = 0, n_sm = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || n_sm <= 0) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fp_pipeline_kernel, NT, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    per_sm = per_sm > 4 ? 4 : per_sm;
+    const int64_t plane = (int64_t)a.H * a.W;
+    FpPipe p;
+    p.B = a.B; p.H = a.H; p.W = a.W; p.fillhole = a.fillhole;
+    p.flowp = a.flowp; p.flow = a.flow;
+    p.outp = a.outp; p.countp = a.countp;
+    p.out_b = a.out.b; p.out_c = a.out.c; p.cnt_b = a.count.b;
+    p.Wt = (a.W + 31) / 32; p.Ht = (a.H + 31) / 32;
+    p.Wt32 = (p.Wt + 31) / 32; p.Ht32 = (p.Ht + 31) / 32;
+    p.nS_x = (a.W + TW - 1) / TW; p.nS_y = (a.H + TH - 1) / TH;
+    p.nA_x = (a.W + 127) / 128; p.nA_y = p.Ht;
+    p.dbg = 0;
+    if (const char* e = getenv("MEMC_FP_DBG")) p.dbg = atoi(e);
+    p.rs_stride = (int64_t)pad32((size_t)a.H * p.Wt32);
+    p.cs_stride = (int64_t)pad32((size_t)p.Ht32 * a.W);
+    p.rm_stride = (int64_t)pad32((size_t)a.H * p.Wt);
+    p.cm_stride = (int64_t)pad32((size_t)p.Ht * a.W);
+    const size_t n_acc = pad32((size_t)3 * 3 * plane), n_ctrl = pad32((size_t)2 * a.B + 1);
+    const size_t n_sum = (size_t)a.B * (p.rs_stride + p.cs_stride), n_mask = (size_t)a.B * (p.rm_stride + p.cm_stride);
+    // one stream-ordered block: [accumulators | ctrl | summaries || masks]; the first three start zeroed
+    float* blk = nullptr;
+    cudaMemPool_t pool = scratch_pool();
+    if (!pool ||
+        cudaMallocFromPoolAsync(reinterpret_cast<void**>(&blk), (n_acc + n_ctrl + n_sum + n_mask) * 4, pool, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    p.scratch = blk;
+    p.ctrl = reinterpret_cast<unsigned*>(blk + n_acc);
+    p.rowsum = p.ctrl + n_ctrl;
+    p.colsum = p.rowsum + (size_t)a.B * p.rs_stride;
+    p.rowmask = p.colsum + (size_t)a.B * p.cs_stride;
+    p.colmask = p.rowmask + (size_t)a.B * p.rm_stride;
+    int rc = 1;
+    if (cudaMemsetAsync(blk, 0, (n_acc + n_ctrl + n_sum) * 4, stream) != cudaSuccess) rc = -1;
+    count_launch();
+    if (rc == 1) {
+        void* args[] = {&p};
+        if (cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fp_pipeline_kernel), dim3(n_sm * per_sm), dim3(NT), args,
+                                        smem, stream) != cudaSuccess)
+            rc = -1;
+        count_launch();
+        if (check_launch("FlowProjection forward (persistent pipeline)")) rc = -1;
+    }
+    cudaFreeAsync(blk, stream);
+    return rc;
+}
+
 }  // namespace
 
 int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero) {
-    if (const char* e = getenv("MEMC_TMA_DBG")) if (atoi(e) & 32) return 0;  // development: generic path
+    int dbg = 0;
+    if (const char* e = getenv("MEMC_TMA_DBG")) dbg = atoi(e);
+    if (dbg & 32) return 0;  // development: generic path
     if (a.W < SW || a.H < SH || a.W % 4) return 0;
     // dense frames only: per-frame memset and the 128-bit averaging pass want contiguous planes
     const int64_t plane = (int64_t)a.H * a.W;
     if (a.out.h != a.W || a.out.c != plane || a.count.h != a.W) return 0;
     if ((reinterpret_cast<uintptr_t>(a.outp) & 15u) || (reinterpret_cast<uintptr_t>(a.countp) & 15u)) return 0;
     if (a.out.b % 4 || a.count.b % 4) return 0;
-    CUtensorMap m_flow;
-    if (!tma::make_map_nchw(&m_flow, a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, TH, 2,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
-        return 0;
-    const size_t smem = sizeof(Smem) + 128;
+    if (overwrite && !(dbg & 128)) {  // the library produces every element: persistent pipeline
+        const int r = fp_forward_pipeline(stream, a);
+        if (r != 0) return r;
+    }
+    const size_t smem = sizeof(Smem);
     if (!ensure_dynamic_smem(fp_splat_kernel, smem)) return 0;
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
     // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
@@ -391,7 +812,7 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
             if (cudaMemsetAsync(cntb, 0, sizeof(float) * plane, stream) != cudaSuccess) rc = -1;
             count_launch(2);
         }
-        fp_splat_kernel<<<grid, NT, smem, stream>>>(m_flow, a, b);
+        fp_splat_kernel<<<grid, NT, smem, stream>>>(a, b);
         fp_average_mask_kernel<<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
                                                            colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
         count_launch(2);

@@ -411,6 +411,43 @@ def test_flow_projection_vs_reference_cuda_kernels(L, fillhole):
         close(gi, host(ref.gpu_flow_projection_backward(t, r_count, gout)), what="FlowProjection bwd vs reference CUDA")
 
 
+@pytest.mark.parametrize("shape", [(7, 64, 96), (5, 70, 260), (3, 33, 3840), (1, 1100, 128), (4, 45, 2100)])
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_flow_projection_pipeline_many_frames(L, shape, fillhole):
+    """The persistent pipeline (OVERWRITE calls): more frames than accumulator slots, ragged
+    sizes, rows / columns longer than 32 mask words (two-level fill-hole search), vs the oracle."""
+    from memc_b200 import synth
+    S, P = L.strides_of, L.ptr
+    B, H, W = shape
+    for t in (synth.smooth_flow(B, H, W, 5.0, seed=11, device="cuda"), synth.tear_flow(B, H, W, 9.0, seed=5, device="cuda"),
+              synth.radial_flow(B, H, W, 0.9, device="cuda")):
+        count, out = torch.full((B, 1, H, W), 7.0, device="cuda"), torch.full_like(t, -3.0)  # garbage: OVERWRITE ignores it
+        st = L.stream_ptr(t)
+        assert L.call("memc_b200_flow_projection_forward", st, B, H, W, fillhole, S(t), S(count), S(out), P(t), P(count),
+                      P(out), L.OVERWRITE) == 0
+        eo, ec = cpu.flow_projection_forward(host(t), fillhole, "f64")
+        assert np.array_equal(host(count), ec), "count must be exact"
+        close(out, eo, tol=5e-5, what="pipeline %s fillhole=%d" % (shape, fillhole))
+
+
+def test_flow_projection_pipeline_equals_per_frame_path(L, monkeypatch):
+    """Same call through the persistent pipeline and through the per-frame launches
+    (MEMC_TMA_DBG=128): count bit-equal, output equal up to the fp32 summation order."""
+    from memc_b200 import synth
+    S, P = L.strides_of, L.ptr
+    B, H, W = 6, 270, 480
+    t = synth.smooth_flow(B, H, W, 6.0, seed=3, device="cuda")
+    res = []
+    for dbg in ("0", "128"):
+        monkeypatch.setenv("MEMC_TMA_DBG", dbg)
+        count, out = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(t)
+        assert L.call("memc_b200_flow_projection_forward", L.stream_ptr(t), B, H, W, 1, S(t), S(count), S(out), P(t),
+                      P(count), P(out), L.OVERWRITE) == 0
+        res.append((count, out))
+    assert torch.equal(res[0][0], res[1][0])
+    assert float((res[0][1] - res[1][1]).abs().max()) <= TOL
+
+
 def test_flow_projection_fillhole_follows_requires_grad(L):
     """FlowProjectionModule(input.requires_grad): holes are filled only when no grad is
     required (reference FlowProjectionLayer.py:15) -- callers use torch.no_grad()."""
