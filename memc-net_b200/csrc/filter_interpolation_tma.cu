@@ -37,12 +37,16 @@ namespace {
 constexpr int CB = 4;  // max channels staged per box
 
 // TW x TH output tile, SW x SH image box, NT threads, MINB resident CTAs per SM (launch bound)
-template <int TW_, int TH_, int SW_, int SH_, int NT_, int MINB_>
+// PATCH: a warp instruction covers an 8 x 4 pixel patch instead of a 32-pixel row segment (fewer
+// bank conflicts in the tap gather when SW % 32 == 8, profiles/r01_bank_conflict_model.md)
+template <int TW_, int TH_, int SW_, int SH_, int NT_, int MINB_, bool PATCH_ = false>
 struct Cfg {
     static constexpr int TW = TW_, TH = TH_, SW = SW_, SH = SH_, NT = NT_, MINB = MINB_;
+    static constexpr bool PATCH = PATCH_;
     static constexpr int SEGS = TW / 32;      // 32-pixel row segments per tile row
     static constexpr int PPT = TW * TH / NT;  // pixels per thread
-    static_assert(TW % 32 == 0 && SW % 32 == 0 && (TW * TH) % NT == 0 && NT % 32 == 0, "bad tile config");
+    static_assert(TW % 32 == 0 && (PATCH_ ? SW % 4 == 0 && TH % 4 == 0 : SW % 32 == 0) && (TW * TH) % NT == 0 && NT % 32 == 0,
+                  "bad tile config");
 };
 
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }  // REDUX.MIN.S32
@@ -68,8 +72,13 @@ __host__ __device__ constexpr Layout make_layout(int C, int planes_a, bool with_
 template <class K>
 __device__ __forceinline__ void tile_pixel(int k, int lane, int warp, int& xl, int& yl) {
     const int seg = warp + k * (K::NT / 32);
-    yl = seg / K::SEGS;
-    xl = lane + 32 * (seg % K::SEGS);
+    if (K::PATCH) {  // patch `seg` of the tile: TW/8 patches per patch row
+        yl = 4 * (seg / (K::TW / 8)) + (lane >> 3);
+        xl = 8 * (seg % (K::TW / 8)) + (lane & 7);
+    } else {
+        yl = seg / K::SEGS;
+        xl = lane + 32 * (seg % K::SEGS);
+    }
 }
 
 // bounding box of the source windows over the tile's valid pixels -> box origin (bx, by)
@@ -1602,6 +1611,9 @@ using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs /
 using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
 using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
 using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
+using FwdK3 = Cfg<32, 16, 72, 32, 256, 2, true>;  // channel-chunked, 8x4 patches, box pitch 72: 110 KB
+using FwdK4 = Cfg<32, 16, 72, 28, 256, 2, true>;  // 101 KB
+using FwdK5 = Cfg<32, 8, 72, 24, 128, 4, true>;   // 8-row tiles:  73 KB -> 3 CTAs / SM
 using FwdW1 = Cfg<32, 8, 64, 24, 256, 2>;   // warp-specialised ring: 8 consumer warps, 1 px / thread
 using FwdW2 = Cfg<32, 8, 64, 24, 128, 2>;   // 4 consumer warps, 2 px / thread
 using FwdW3 = Cfg<32, 8, 64, 24, 256, 3>;   // 2-slot ring, 3 CTAs / SM
@@ -1654,14 +1666,17 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
     FiArgs a = a_in;
     a.dbg = env_int("MEMC_TMA_DBG");
     if (a.fs == 4 && a.C > CB && a.W % 4 == 0 && a.B <= 65535) {
-        // C > 4 (64-channel context warps): channel-chunked TMA variant.  Measured EQUAL to the generic
-        // kernel (1.15 vs 1.12 ms per 1080p frame at C=64: both are bound by the 16*C shared/L1
-        // gather wavefronts, not by HBM), so production keeps the generic kernel; selectable for work
-        // on it with MEMC_FI_FWD_CFG=30/31.
+        // C > 4 (64-channel context warps): channel-chunked TMA variant, 8x4 patches.  0.88 ms per
+        // 1080p frame at C = 64 vs 1.11 ms for the generic kernel: both are bound by the 16*C
+        // shared / L1 gather wavefronts per pixel, not by HBM (profiles/r01_kernel_table.md).
         const int cfg = env_int("MEMC_FI_FWD_CFG");
+        if (cfg == 32) return launch_fwd_chunked<FwdK3>(stream, a);
+        if (cfg == 33) return launch_fwd_chunked<FwdK4>(stream, a);
+        if (cfg == 34) return launch_fwd_chunked<FwdK5>(stream, a);
         if (cfg == 30) return launch_fwd_chunked<FwdK1>(stream, a);
         if (cfg == 31) return launch_fwd_chunked<FwdK2>(stream, a);
-        return 0;
+        if (cfg == 9) return 0;  // generic kernel
+        return launch_fwd_chunked<FwdK3>(stream, a);
     }
     if (a.dbg & 64) {
         static long long* dev = nullptr;
