@@ -3,8 +3,9 @@
     python tools/kbench.py [--out gpurun_out/kbench.json] [--iters 20] [--only fi,fp,...]
 
 Times every op through the C ABI with CUDA events (median of --iters after 3 warm-ups, inputs
-far larger than L2 or an L2 flush between iterations), ours vs the reference's legacy kernels
-recompiled for sm_100a (oracle/_ref/libmemc_ref_gpu.so) when present.
+far larger than L2 or an L2 flush between iterations).  The comparison with the reference's
+legacy kernels recompiled for sm_100a lives in tests/legacy_bench.py (only tests/ may touch
+oracle/).
 """
 import argparse
 import json
@@ -89,11 +90,7 @@ def main():
     only = set(args.only.split(",")) if args.only else None
     peak, peak_kind = _peak()
     lib.load()
-    try:
-        from oracle import ref
-        have_ref = ref.available_gpu()
-    except Exception:
-        have_ref = False
+    have_ref, ref = False, None  # legacy comparison: tests/legacy_bench.py
     res = {"peak_gbs": peak, "peak_kind": peak_kind, "gpu": torch.cuda.get_device_name(0), "rows": []}
 
     def row(name, px, bytes_per_px, t, t_ref=None, **kw):
