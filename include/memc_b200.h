@@ -187,6 +187,23 @@ MEMC_B200_API int memc_b200_filter_interpolation_backward(
     const float *input1, const float *flow, const float *filter, const float *gradoutput,
     float *gradinput1, float *gradinput2, float *gradinput3, int flags);
 
+/* Fused call site of the reference's networks (networks/MEMC_Net.py:258-264, MEMC_Net_star.py:272-278,
+ * `FilterInterpolate`):
+ *     output = occlusion_0 * FilterInterpolation(input1_0, flow_0, filter_0)
+ *            + occlusion_1 * FilterInterpolation(input1_1, flow_1, filter_1)
+ * occlusion_k is [B,1,H,W] (broadcast over the channels); every element of `output` is written
+ * (OVERWRITE semantics whatever `flags` says); bit-identical to the composition of
+ * memc_b200_filter_interpolation_forward and the fp32 blend.  fs == 4, C == 3 take one fused
+ * kernel; anything else is composed inside the library (two warps into stream-ordered scratch). */
+MEMC_B200_API int memc_b200_filter_interpolation_blend_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1_0, memc_strides s_flow_0, memc_strides s_filter_0,
+    memc_strides s_in1_1, memc_strides s_flow_1, memc_strides s_filter_1,
+    memc_strides s_occ_0, memc_strides s_occ_1, memc_strides s_out,
+    const float *input1_0, const float *flow_0, const float *filter_0,
+    const float *input1_1, const float *flow_1, const float *filter_1,
+    const float *occlusion_0, const float *occlusion_1, float *output, int flags);
+
 MEMC_B200_API int memc_b200_flow_projection_forward(
     memc_stream_t stream, int batch, int h, int w, int fillhole,
     memc_strides s_flow, memc_strides s_count, memc_strides s_out,

@@ -256,9 +256,74 @@ static int fi_backward(cudaStream_t stream, const FiArgs& a_in, int flags) {
     return check_launch("FilterInterpolation backward");
 }
 
+// blend of two warped frames with their occlusion maps, rounded like the PyTorch composition
+// occ0 * w0 + occ1 * w1 (two products, one sum; networks/MEMC_Net.py:262)
+__global__ void __launch_bounds__(256) fi_blend_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                       const float* __restrict__ occ0, View v0, const float* __restrict__ occ1,
+                                                       View v1, float* __restrict__ out, View vo, int C, int H, int W) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const float a0 = __ldg(occ0 + b * v0.b + (int64_t)y * v0.h + x), a1 = __ldg(occ1 + b * v1.b + (int64_t)y * v1.h + x);
+    const int64_t plane = (int64_t)H * W;
+    for (int c = 0; c < C; ++c) {
+        const int64_t i = ((int64_t)b * C + c) * plane + (int64_t)y * W + x;  // the warps are dense scratch tensors
+        out[b * vo.b + c * vo.c + (int64_t)y * vo.h + x] = __fadd_rn(__fmul_rn(a0, w0[i]), __fmul_rn(a1, w1[i]));
+    }
+}
+
+// out = occ0 * FI(src 0) + occ1 * FI(src 1); a0.outp / a0.out describe `out`
+static int fi_blend_forward(cudaStream_t stream, const FiArgs& a0, const FiArgs& a1, const float* occ0, View v0,
+                            const float* occ1, View v1, int flags) {
+    if (a0.B <= 0 || a0.C <= 0 || a0.H <= 0 || a0.W <= 0) return 0;
+    if (a0.fs <= 0) return -1;
+    if (!(flags & MEMC_B200_NO_FAST)) {
+        const int r = fi_blend_forward_fast(stream, a0, a1, occ0, v0, occ1, v1);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
+    // composition of the plain ops through two dense scratch frames
+    const size_t n = (size_t)a0.B * a0.C * a0.H * a0.W;
+    float* tmp = static_cast<float*>(scratch_alloc(stream, 2 * n * sizeof(float)));
+    if (!tmp) return -1;
+    const View dense = mk_view(memc_strides{(int64_t)a0.C * a0.H * a0.W, (int64_t)a0.H * a0.W, (int64_t)a0.W});
+    int rc = 0;
+    for (int k = 0; k < 2 && rc == 0; ++k) {
+        FiArgs a = k ? a1 : a0;
+        a.outp = tmp + k * n;
+        a.out = dense;
+        rc = fi_forward(stream, a, flags | MEMC_B200_OVERWRITE);
+    }
+    if (rc == 0) {
+        dim3 grid((a0.W + 255) / 256, a0.H, a0.B);
+        fi_blend_kernel<<<grid, 256, 0, stream>>>(tmp, tmp + n, occ0, v0, occ1, v1, a0.outp, a0.out, a0.C, a0.H, a0.W);
+        count_launch();
+        rc = check_launch("FilterInterpolation blend");
+    }
+    scratch_free(stream, tmp);
+    return rc;
+}
+
 }  // namespace memc
 
 using namespace memc;
+
+extern "C" int memc_b200_filter_interpolation_blend_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
+    memc_strides s_in1_0, memc_strides s_flow_0, memc_strides s_filter_0,
+    memc_strides s_in1_1, memc_strides s_flow_1, memc_strides s_filter_1,
+    memc_strides s_occ_0, memc_strides s_occ_1, memc_strides s_out,
+    const float* input1_0, const float* flow_0, const float* filter_0,
+    const float* input1_1, const float* flow_1, const float* filter_1,
+    const float* occlusion_0, const float* occlusion_1, float* output, int flags) {
+    FiArgs a0{}, a1{};
+    a0.B = a1.B = batch; a0.C = a1.C = channel; a0.H = a1.H = h; a0.W = a1.W = w; a0.fs = a1.fs = filter_size;
+    a0.in1 = mk_view(s_in1_0); a0.flow = mk_view(s_flow_0); a0.filt = mk_view(s_filter_0);
+    a1.in1 = mk_view(s_in1_1); a1.flow = mk_view(s_flow_1); a1.filt = mk_view(s_filter_1);
+    a0.out = a1.out = mk_view(s_out);
+    a0.in1p = input1_0; a0.flowp = flow_0; a0.filtp = filter_0;
+    a1.in1p = input1_1; a1.flowp = flow_1; a1.filtp = filter_1;
+    a0.outp = a1.outp = output;
+    return fi_blend_forward(stream, a0, a1, occlusion_0, mk_view(s_occ_0), occlusion_1, mk_view(s_occ_1), flags);
+}
 
 extern "C" int memc_b200_filter_interpolation_forward(
     memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,

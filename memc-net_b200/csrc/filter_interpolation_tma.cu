@@ -713,44 +713,52 @@ struct PatchCfg {
     static constexpr int TW = 32, TH = 8, SW = SW_, SH = SH_;
 };
 
-template <int C, int SW, int SH, int MINB, bool STAGE_OUT>
-__global__ void __launch_bounds__(128, MINB)
-fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                    const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_out,
-                    const __grid_constant__ FiArgs p) {
-    using K = PatchCfg<SW, SH>;
-    constexpr int TW = 32, TH = 8, SWD = 8;  // strip width
-    constexpr int FSTRIP = 16 * TH * SWD;     // floats per filter strip
-    constexpr int OFF_FLOW = 16 * TH * TW * 4, OFF_BAR = OFF_FLOW + 2 * TH * TW * 4, OFF_IMG = OFF_BAR + 128;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    float* s_filt = reinterpret_cast<float*>(sm);                         // [4][16][TH][8]
-    const float* s_flow = reinterpret_cast<const float*>(sm + OFF_FLOW);  // [4][2][TH][8]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);           // 0 flow, 1 filter, 2 image
-    int* s_bb = reinterpret_cast<int*>(bars + 3);
-    const float* s_img = reinterpret_cast<const float*>(sm + OFF_IMG);    // [C][SH][SW]
+// shared-memory carve-up of the patch kernels (byte offsets from the 128-byte aligned base)
+struct PatchSmem {
+    static constexpr int TW = 32, TH = 8, SWD = 8;   // tile, strip width
+    static constexpr int FSTRIP = 16 * TH * SWD;      // floats per filter strip
+    static constexpr int OFF_FLOW = 16 * TH * TW * 4, OFF_BAR = OFF_FLOW + 2 * TH * TW * 4, OFF_IMG = OFF_BAR + 128;
+};
 
+// One SOURCE of a patch tile: stage its flow / filter strips and its image box, compute this
+// thread's two pixels into res[k][c] (nothing is stored).  bars[0..2] are initialised mbarriers whose
+// next completion has parity `parity`; for a second source the caller passes parity ^ 1.
+// `first` = false: the shared memory still holds the previous source, so its readers are drained
+// (block barrier) before the TMA engine overwrites it.
+// STORE: results go straight to p.outp as they are produced (keeps them out of the register budget)
+// and res[][] is left untouched.
+template <int C, int SW, int SH, bool STORE, bool FIRST>
+__device__ __forceinline__ void patch_pass(unsigned char* sm, const CUtensorMap* m_flow, const CUtensorMap* m_filt,
+                                           const CUtensorMap* m_img, const FiArgs& p, float (&res)[2][C]) {
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, b = blockIdx.z;  // one tile per CTA
+    constexpr unsigned parity = FIRST ? 0u : 1u;
+    constexpr bool first = FIRST;
+    using K = PatchCfg<SW, SH>;
+    using S = PatchSmem;
+    constexpr int TW = S::TW, TH = S::TH, SWD = S::SWD, FSTRIP = S::FSTRIP;
+    float* s_filt = reinterpret_cast<float*>(sm);                            // [4][16][TH][8]
+    const float* s_flow = reinterpret_cast<const float*>(sm + S::OFF_FLOW);  // [4][2][TH][8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);           // 0 flow, 1 filter, 2 image
+    int* s_bb = reinterpret_cast<int*>(bars + 3);
+    const float* s_img = reinterpret_cast<const float*>(sm + S::OFF_IMG);    // [C][SH][SW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
     const int W = p.W, H = p.H;
 
+    if (!first) __syncthreads();  // every reader of the previous source's tiles is done
     if (tid == 0) {
-        tma::mbar_init(&bars[0], 1);
-        tma::mbar_init(&bars[1], 1);
-        tma::mbar_init(&bars[2], 1);
         s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
-        tma::fence_barrier_init();
+        if (!first) tma::fence_proxy_async();
         tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
 #pragma unroll
         for (int st = 0; st < 4; ++st)
-            tma::load_4d(sm + OFF_FLOW + st * 2 * TH * SWD * 4, &m_flow, x0 + SWD * st, y0, 0, b, &bars[0]);
+            tma::load_4d(sm + S::OFF_FLOW + st * 2 * TH * SWD * 4, m_flow, x0 + SWD * st, y0, 0, b, &bars[0]);
         tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
 #pragma unroll
         for (int st = 0; st < 4; ++st)
-            tma::load_4d(sm + st * FSTRIP * 4, &m_filt, x0 + SWD * st, y0, 0, b, &bars[1]);
+            tma::load_4d(sm + st * FSTRIP * 4, m_filt, x0 + SWD * st, y0, 0, b, &bars[1]);
     }
     __syncthreads();
-    tma::mbar_wait(&bars[0], 0, 1);
+    tma::mbar_wait(&bars[0], parity, 1);
 
     const int lxx = lane & 7, lyy = lane >> 3;
     const int xl = SWD * warp + lxx;
@@ -782,32 +790,34 @@ fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_con
         bx = max(0, min(bx, W - SW)) & ~3;
         by = max(0, min(by, H - SH));
     }
-    if (tid == 0 && any_valid) {
+    // (the image barrier completes once per pass even when nothing is valid: parities stay in step)
+    if (tid == 0) {
         tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
-        tma::load_4d(sm + OFF_IMG, &m_img, bx, by, 0, b, &bars[2]);
+        tma::load_4d(sm + S::OFF_IMG, m_img, bx, by, 0, b, &bars[2]);
     }
-    tma::mbar_wait(&bars[1], 0, 2);
-    if (any_valid) tma::mbar_wait(&bars[2], 0, 3);
+    tma::mbar_wait(&bars[1], parity, 2);
+    tma::mbar_wait(&bars[2], parity, 3);
 
     const float* in1b = p.in1p + b * p.in1.b;
-    float* const filt_w = s_filt + warp * FSTRIP;  // this warp's filter strip; reused for its outputs
-    float outv[2][C];                               // results of the two pixels (STAGE_OUT)
+    const float* filt_w = s_filt + warp * FSTRIP;  // this warp's filter strip
     unsigned slow = 0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int yl = 4 * k + lyy;
         const int x = x0 + xl, y = y0 + yl;
+        if (!STORE) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) outv[k][c] = 0.f;
+            for (int c = 0; c < C; ++c) res[k][c] = 0.f;
+        }
         if (x >= W || y >= H) continue;
         float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
         const FiGeom g = fi_geometry(x, y, W, H, flow_s[yl * SWD], flow_s[(TH + yl) * SWD]);
-        if (!g.valid) {
+        if (!g.valid) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float v = __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x);
-                if (STAGE_OUT) outv[k][c] = v;
-                else stg_stream(outp + c * p.out.c, v);
+                if (STORE) stg_stream(outp + c * p.out.c, v);
+                else res[k][c] = v;
             }
             continue;
         }
@@ -833,9 +843,9 @@ fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_con
                 for (int i = 0; i < 4; ++i)
                     q[(j >> 1) * 2 + (i >> 1)] =
                         fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
-            const float r = wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3];
-            if (STAGE_OUT) outv[k][c] = r;
-            else stg_stream(outp + c * p.out.c, r);
+            const float v = wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3];
+            if (STORE) stg_stream(outp + c * p.out.c, v);
+            else res[k][c] = v;
         }
     }
     if (__builtin_expect(slow != 0, 0)) {
@@ -845,32 +855,128 @@ fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_con
             const int yl = 4 * k + lyy;
             const int x = x0 + xl, y = y0 + yl;
             const FiGeom g = fi_geometry(x, y, W, H, flow_s[yl * SWD], flow_s[(TH + yl) * SWD]);
-            float res[C];
-            fwd_slow_pixel<C, K>(p, filt_w + yl * SWD + lxx, TH * SWD, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha,
-                                 g.beta, res);
-            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+            if (STORE) {
+                float r[C];
+                fwd_slow_pixel<C, K>(p, filt_w + yl * SWD + lxx, TH * SWD, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha,
+                                     g.beta, r);
+                float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (STAGE_OUT) outv[k][c] = res[c];
-                else stg_stream(outp + c * p.out.c, res[c]);
+                for (int c = 0; c < C; ++c) stg_stream(outp + c * p.out.c, r[c]);
+            } else {
+                fwd_slow_pixel<C, K>(p, filt_w + yl * SWD + lxx, TH * SWD, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha,
+                                     g.beta, res[k]);
             }
         }
     }
+}
+
+__device__ __forceinline__ unsigned char* patch_smem_init() {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PatchSmem::OFF_BAR);
+    if (threadIdx.x == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::mbar_init(&bars[2], 1);
+        tma::fence_barrier_init();
+    }
+    return sm;  // the first patch_pass's block barrier publishes the barriers
+}
+
+template <int C, int SW, int SH, int MINB, bool STAGE_OUT>
+__global__ void __launch_bounds__(128, MINB)
+fi_fwd_patch_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                    const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_out,
+                    const __grid_constant__ FiArgs p) {
+    constexpr int TW = 32, TH = 8, SWD = 8;
+    unsigned char* sm = patch_smem_init();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    float res[2][C];
+    patch_pass<C, SW, SH, !STAGE_OUT, true>(sm, &m_flow, &m_filt, &m_img, p, res);
+    const int lxx = lane & 7, lyy = lane >> 3;
     if (STAGE_OUT) {
-        // every lane of the warp is done with the warp's filter strip: stage [C][TH][8] there
+        // every lane of the warp is done with the warp's filter strip: stage [C][TH][8] there, one
+        // TMA store per warp (clipped to the image by the TMA) instead of 4-row partial stores
+        float* filt_w = reinterpret_cast<float*>(sm) + warp * PatchSmem::FSTRIP;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c) filt_w[(c * TH + 4 * k + lyy) * SWD + lxx] = outv[k][c];
+            for (int c = 0; c < C; ++c) filt_w[(c * TH + 4 * k + lyy) * SWD + lxx] = res[k][c];
         tma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            tma::store_4d(&m_out, x0 + SWD * warp, y0, 0, b, filt_w);  // clipped to the image by the TMA
+            tma::store_4d(&m_out, x0 + SWD * warp, y0, 0, b, filt_w);
             tma::bulk_commit();
             tma::bulk_wait_read_all();
         }
     }
+}
+
+// ------------------------------------------------------------------------------------
+// Fused call site (networks/MEMC_Net.py:258-264, MEMC_Net_star.py:272-278):
+//     out = occlusion0 * FilterInterpolation(ref0, flow0, filter0)
+//         + occlusion1 * FilterInterpolation(ref1, flow1, filter1)
+// Two patch passes over the same tile, blended in registers: the two warped frames never go to
+// HBM (the composition writes them, reads them back twice and runs three elementwise kernels).
+// The blend is rounded exactly like the composition (two products, one sum -- no FMA), so the
+// result is bit-identical to it.
+// ------------------------------------------------------------------------------------
+struct BlendArgs {
+    const float* occ0p;
+    const float* occ1p;
+    View occ0, occ1;  // [B,1,H,W]
+};
+
+template <int C, int SW, int SH, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+fi_blend_patch_kernel(const __grid_constant__ CUtensorMap m_flow0, const __grid_constant__ CUtensorMap m_filt0,
+                      const __grid_constant__ CUtensorMap m_img0, const __grid_constant__ CUtensorMap m_flow1,
+                      const __grid_constant__ CUtensorMap m_filt1, const __grid_constant__ CUtensorMap m_img1,
+                      const __grid_constant__ FiArgs p0, const __grid_constant__ FiArgs p1,
+                      const __grid_constant__ BlendArgs bl) {
+    constexpr int TW = 32, TH = 8, SWD = 8;
+    unsigned char* sm = patch_smem_init();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int lxx = lane & 7, lyy = lane >> 3;
+    // the occlusion maps of this thread's pixels: in flight during both passes
+    float o0[2], o1[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int x = x0 + SWD * warp + lxx, y = y0 + 4 * k + lyy;
+        o0[k] = o1[k] = 0.f;
+        if (x < p0.W && y < p0.H) {
+            o0[k] = ldg_stream(bl.occ0p + b * bl.occ0.b + (int64_t)y * bl.occ0.h + x);
+            o1[k] = ldg_stream(bl.occ1p + b * bl.occ1.b + (int64_t)y * bl.occ1.h + x);
+        }
+    }
+    float r0[2][C], r1[2][C];
+    patch_pass<C, SW, SH, false, true>(sm, &m_flow0, &m_filt0, &m_img0, p0, r0);
+    patch_pass<C, SW, SH, false, false>(sm, &m_flow1, &m_filt1, &m_img1, p1, r1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int x = x0 + SWD * warp + lxx, y = y0 + 4 * k + lyy;
+        if (x >= p0.W || y >= p0.H) continue;
+        float* outp = p0.outp + b * p0.out.b + (int64_t)y * p0.out.h + x;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            stg_stream(outp + c * p0.out.c, __fadd_rn(__fmul_rn(o0[k], r0[k][c]), __fmul_rn(o1[k], r1[k][c])));
+    }
+}
+
+template <int C, int SW, int SH, int MINB>
+int launch_blend_patch(cudaStream_t stream, const FiArgs& a0, const FiArgs& a1, const BlendArgs& bl) {
+    if (a0.W < SW || a0.H < SH) return 0;
+    CUtensorMap m0[5], m1[5];
+    if (!make_maps(a0, false, 8, 8, SW, SH, m0) || !make_maps(a1, false, 8, 8, SW, SH, m1)) return 0;
+    constexpr size_t smem = (size_t)(16 + 2) * 8 * 32 * 4 + 128 + (size_t)C * SH * SW * 4 + 128;
+    if (!ensure_dynamic_smem(fi_blend_patch_kernel<C, SW, SH, MINB>, smem)) return 0;
+    dim3 grid((a0.W + 31) / 32, (a0.H + 7) / 8, a0.B);
+    fi_blend_patch_kernel<C, SW, SH, MINB><<<grid, 128, smem, stream>>>(m0[0], m0[1], m0[2], m1[0], m1[1], m1[2], a0, a1, bl);
+    count_launch();
+    return check_launch("FilterInterpolation pair + occlusion blend (fused)") == 0 ? 1 : -1;
 }
 
 template <int C, int SW, int SH, int MINB, bool STAGE_OUT>
@@ -1699,6 +1805,7 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
             case 50: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;
             case 51: r = launch_fwd_patch<3, 72, 22, 6, true>(stream, a); break;
             case 52: r = launch_fwd_patch<3, 72, 24, 5, true>(stream, a); break;
+            case 53: r = launch_fwd_patch<3, 72, 22, 5, false>(stream, a); break;
             case 60: r = launch_fwd<3, FwdH1>(stream, a); break;
             case 61: r = launch_fwd<3, FwdH2>(stream, a); break;
             case 62: r = launch_fwd<3, FwdQ1>(stream, a); break;
@@ -1737,6 +1844,14 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
         case 4: return launch_fwd<4, FWD_DEFAULT>(stream, a);
     }
     return 0;
+}
+
+// fused pair + blend: 1 = handled, 0 = preconditions not met (caller composes the plain ops), -1 = error
+int fi_blend_forward_fast(cudaStream_t stream, const FiArgs& a0, const FiArgs& a1, const float* occ0, View v_occ0,
+                          const float* occ1, View v_occ1) {
+    if (a0.fs != 4 || a0.C != 3 || a0.W % 4 || a0.B > 65535) return 0;
+    BlendArgs bl{occ0, occ1, v_occ0, v_occ1};
+    return launch_blend_patch<3, 72, 22, 5>(stream, a0, a1, bl);
 }
 
 int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {

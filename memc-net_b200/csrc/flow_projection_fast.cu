@@ -682,32 +682,6 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
     }
 }
 
-// Library-owned stream-ordered memory pool for scratch memory (occupancy masks, the pipeline's
-// accumulator ring).  A private pool with a high release threshold keeps the blocks
-// cached across calls; the device's default pool would hand them back to the OS at every
-// synchronisation (measured: 2 ms per call).  One pool per device, created on first use.
-cudaMemPool_t scratch_pool() {
-    static cudaMemPool_t pools[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!pools[dev]) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        cudaMemPool_t pool = nullptr;
-        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        pools[dev] = pool;
-    }
-    return pools[dev];
-}
-
 size_t pad32(size_t n) { return (n + 31) & ~(size_t)31; }
 
 // OVERWRITE calls: the persistent pipeline.  1 = handled, 0 = not applicable, -1 = error
@@ -740,16 +714,11 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
     p.cs_stride = (int64_t)pad32((size_t)p.Ht32 * a.W);
     p.rm_stride = (int64_t)pad32((size_t)a.H * p.Wt);
     p.cm_stride = (int64_t)pad32((size_t)p.Ht * a.W);
-    const size_t n_acc = pad32((size_t)3 * 3 * plane), n_ctrl = pad32((size_t)2 * a.B + 1);
+    const size_t n_acc = pad32((size_t)(a.B < 3 ? a.B : 3) * 3 * plane), n_ctrl = pad32((size_t)2 * a.B + 1);  // slots f % 3
     const size_t n_sum = (size_t)a.B * (p.rs_stride + p.cs_stride), n_mask = (size_t)a.B * (p.rm_stride + p.cm_stride);
     // one stream-ordered block: [accumulators | ctrl | summaries || masks]; the first three start zeroed
-    float* blk = nullptr;
-    cudaMemPool_t pool = scratch_pool();
-    if (!pool ||
-        cudaMallocFromPoolAsync(reinterpret_cast<void**>(&blk), (n_acc + n_ctrl + n_sum + n_mask) * 4, pool, stream) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+    float* blk = static_cast<float*>(scratch_alloc(stream, (n_acc + n_ctrl + n_sum + n_mask) * 4));
+    if (!blk) return 0;
     p.scratch = blk;
     p.ctrl = reinterpret_cast<unsigned*>(blk + n_acc);
     p.rowsum = p.ctrl + n_ctrl;
@@ -767,7 +736,7 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
         count_launch();
         if (check_launch("FlowProjection forward (persistent pipeline)")) rc = -1;
     }
-    cudaFreeAsync(blk, stream);
+    scratch_free(stream, blk);
     return rc;
 }
 
@@ -783,7 +752,9 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     if (a.out.h != a.W || a.out.c != plane || a.count.h != a.W) return 0;
     if ((reinterpret_cast<uintptr_t>(a.outp) & 15u) || (reinterpret_cast<uintptr_t>(a.countp) & 15u)) return 0;
     if (a.out.b % 4 || a.count.b % 4) return 0;
-    if (overwrite && !(dbg & 128)) {  // the library produces every element: persistent pipeline
+    // the library produces every element: persistent pipeline (from 3 frames on; below that its phases
+    // cannot overlap across frames and the per-frame launches are quicker: 43 vs 58 us at B = 1, 720p)
+    if (overwrite && a.B >= 3 && !(dbg & 128)) {
         const int r = fp_forward_pipeline(stream, a);
         if (r != 0) return r;
     }
@@ -793,13 +764,8 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
     const int Wt = (a.W + 31) / 32, Ht = (a.H + 31) / 32;
     const size_t n_row = (size_t)a.B * a.H * Wt, n_col = (size_t)a.B * a.W * Ht;
-    unsigned* masks = nullptr;
-    cudaMemPool_t pool = scratch_pool();
-    if (!pool || cudaMallocFromPoolAsync(reinterpret_cast<void**>(&masks), (n_row + n_col) * sizeof(unsigned), pool,
-                                         stream) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+    unsigned* masks = static_cast<unsigned*>(scratch_alloc(stream, (n_row + n_col) * sizeof(unsigned)));
+    if (!masks) return 0;
     unsigned* rowmask = masks;
     unsigned* colmask = masks + n_row;
     const dim3 mgrid((a.W + 127) / 128, Ht, 1);
@@ -825,7 +791,7 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
         count_launch();
         if (check_launch("FlowProjection fill-hole (masks)")) rc = -1;
     }
-    cudaFreeAsync(masks, stream);
+    scratch_free(stream, masks);
     return rc;
 }
 

@@ -52,6 +52,10 @@ inline bool ensure_dynamic_smem(KernelT* kernel, size_t bytes) {
     return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// stream-ordered scratch memory from the library's private pool (runtime.cu); nullptr on failure
+void* scratch_alloc(cudaStream_t stream, size_t bytes);
+void scratch_free(cudaStream_t stream, void* p);
+
 // zero-fill a [B,C,H,W] strided tensor on `stream` (memset when dense, kernel otherwise)
 int zero_fill(cudaStream_t stream, float* p, View v, int B, int C, int H, int W);
 

@@ -1,0 +1,86 @@
+"""Fused call sites of the reference's networks -- optional fast
+paths NEXT TO the unchanged `my_package` API.
+
+    FilterInterpolate(ref0, ref2, offset, filter, occlusion)
+        = occlusion[0] * FilterInterpolationModule()(ref0, offset[0], filter[0])
+        + occlusion[1] * FilterInterpolationModule()(ref2, offset[1], filter[1])
+
+is the static method of the same name in networks/MEMC_Net.py:258-264 and
+networks/MEMC_Net_star.py:272-278 (their sixth argument `filter_size2` is unused there and optional
+here), so a network can rebind it:  `MEMC_Net.FilterInterpolate = staticmethod(fused.FilterInterpolate)`.
+
+Forward: one kernel warps both references and blends them in registers
+(memc_b200_filter_interpolation_blend_forward), bit-identical to the composition.  Backward: composed
+from the plain ops (FilterInterpolation backward per reference; the two warps are recomputed for the
+occlusion gradients), so training code keeps working.  CUDA only: like every op of this package it
+raises on CPU tensors -- there is no fallback.
+"""
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import lib as _lib
+
+
+def _prep(t, name):
+    return _lib.check_tensor(t, name).contiguous()
+
+
+def _fi_forward(in1, flow, filt, fs):
+    B, C, H, W = in1.shape
+    out = torch.empty_like(in1)
+    _lib.call("memc_b200_filter_interpolation_forward", _lib.stream_ptr(in1), B, C, H, W, fs, _lib.strides_of(in1),
+              _lib.strides_of(flow), _lib.strides_of(filt), _lib.strides_of(out), _lib.ptr(in1), _lib.ptr(flow),
+              _lib.ptr(filt), _lib.ptr(out), _lib.OVERWRITE)
+    return out
+
+
+def _fi_backward(in1, flow, filt, gout, fs):
+    B, C, H, W = in1.shape
+    g1, g2, g3 = torch.empty_like(in1), torch.empty_like(flow), torch.empty_like(filt)
+    _lib.call("memc_b200_filter_interpolation_backward", _lib.stream_ptr(in1), B, C, H, W, fs, _lib.strides_of(in1),
+              _lib.strides_of(flow), _lib.strides_of(filt), _lib.strides_of(gout), _lib.strides_of(g1), _lib.strides_of(g2),
+              _lib.strides_of(g3), _lib.ptr(in1), _lib.ptr(flow), _lib.ptr(filt), _lib.ptr(gout), _lib.ptr(g1),
+              _lib.ptr(g2), _lib.ptr(g3), _lib.OVERWRITE)
+    return g1, g2, g3
+
+
+class _FilterInterpolateBlend(Function):
+    @staticmethod
+    def forward(ctx, ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1):
+        ts = [_prep(t, n) for t, n in zip((ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1),
+                                          ("ref0", "offset[0]", "filter[0]", "occlusion[0]", "ref2", "offset[1]",
+                                           "filter[1]", "occlusion[1]"))]
+        ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ts
+        B, C, H, W = ref0.shape
+        ok = (ref1.shape == ref0.shape and flow0.shape == (B, 2, H, W) == flow1.shape and filt0.shape == filt1.shape and
+              filt0.shape[0] == B and filt0.shape[2:] == (H, W) and occ0.shape == (B, 1, H, W) == occ1.shape)
+        if not ok:
+            raise _lib.MemcB200Error("FilterInterpolate: inconsistent shapes " + " ".join(str(tuple(t.shape)) for t in ts))
+        fs = int(math.sqrt(float(filt0.size(1))))  # my_lib_cuda.c:619-620
+        out = torch.empty_like(ref0)
+        S, P = _lib.strides_of, _lib.ptr
+        _lib.call("memc_b200_filter_interpolation_blend_forward", _lib.stream_ptr(ref0), B, C, H, W, fs,
+                  S(ref0), S(flow0), S(filt0), S(ref1), S(flow1), S(filt1), S(occ0), S(occ1), S(out),
+                  P(ref0), P(flow0), P(filt0), P(ref1), P(flow1), P(filt1), P(occ0), P(occ1), P(out), _lib.OVERWRITE)
+        ctx.save_for_backward(*ts)
+        ctx.fs = fs
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ctx.saved_tensors
+        gout = _prep(gout, "gradoutput")
+        grads = []
+        for ref, flow, filt, occ in ((ref0, flow0, filt0, occ0), (ref1, flow1, filt1, occ1)):
+            warp = _fi_forward(ref, flow, filt, ctx.fs)                      # recomputed, not stored
+            g_occ = (gout * warp).sum(dim=1, keepdim=True)                   # d(occ * warp) / d occ
+            g1, g2, g3 = _fi_backward(ref, flow, filt, (gout * occ).contiguous(), ctx.fs)
+            grads += [g1, g2, g3, g_occ]
+        return tuple(grads)
+
+
+def FilterInterpolate(ref0, ref2, offset, filter, occlusion, filter_size2=None):  # noqa: A002 (reference's names)
+    """Drop-in for the networks' static method (networks/MEMC_Net.py:258-264)."""
+    return _FilterInterpolateBlend.apply(ref0, offset[0], filter[0], occlusion[0], ref2, offset[1], filter[1], occlusion[1])

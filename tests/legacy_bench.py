@@ -42,6 +42,14 @@ def ours_fp(flow, count, out):
              P(count), P(out), lib.OVERWRITE)
 
 
+def ours_blend(refs, flows, filts, occs, out):
+    B, C, H, W = refs[0].shape
+    lib.call("memc_b200_filter_interpolation_blend_forward", lib.stream_ptr(out), B, C, H, W, 4,
+             S(refs[0]), S(flows[0]), S(filts[0]), S(refs[1]), S(flows[1]), S(filts[1]), S(occs[0]), S(occs[1]), S(out),
+             P(refs[0]), P(flows[0]), P(filts[0]), P(refs[1]), P(flows[1]), P(filts[1]), P(occs[0]), P(occs[1]), P(out),
+             lib.OVERWRITE)
+
+
 def net_case(B, H, W, star, iters):
     """One frame pair of MEMC_Net (star=False) / MEMC_Net_star (star=True) per batch item."""
     dev = "cuda"
@@ -64,6 +72,16 @@ def net_case(B, H, W, star, iters):
         for k in range(len(ctxs)):
             ours_fi(ctxs[k], proj[k], filts[k], cwarp[k])
         return out
+
+    blended = torch.empty_like(refs[0])
+
+    def ours_fused():  # memc_b200.fused.FilterInterpolate in place of the two warps + blend
+        for k in range(2):
+            ours_fp(flows[k], cnt[k], proj[k])
+        ours_blend(refs, proj, filts, occs, blended)
+        for k in range(len(ctxs)):
+            ours_fi(ctxs[k], proj[k], filts[k], cwarp[k])
+        return blended
 
     def legacy():
         for k in range(2):
@@ -99,8 +117,10 @@ def net_case(B, H, W, star, iters):
         err = max(err, float((a - b).abs().max()))
     del a, b
     t_o, t_l = timeit(ours, iters), timeit(legacy, max(3, iters // 2))
+    t_f = timeit(ours_fused, iters)
     return {"name": "%s op sequence, B=%d x %dx%d" % ("MEMC_Net_star" if star else "MEMC_Net", B, W, H),
-            "ours_ms": t_o * 1e3, "legacy_ms": t_l * 1e3, "speedup": t_l / t_o, "max_abs_projected_flow_vs_legacy": err_fp,
+            "ours_ms": t_o * 1e3, "ours_fused_blend_ms": t_f * 1e3, "legacy_ms": t_l * 1e3, "speedup": t_l / t_o,
+            "speedup_fused": t_l / t_f, "max_abs_projected_flow_vs_legacy": err_fp,
             "max_abs_warps_vs_legacy_same_flow": err,
             "frame_pairs_per_s": B / t_o}
 

@@ -324,6 +324,39 @@ def test_filter_interpolation_720p_vs_oracle(L):
     close(g1, e1, what="720p gi1"), close(g2, e2, what="720p gi2"), close(g3, e3, what="720p gi3")
 
 
+# ------------------------------------------------------ fused call site
+@pytest.mark.parametrize("shape", [(2, 3, 96, 160, 4, 4.0), (1, 3, 270, 480, 4, 6.0), (1, 3, 37, 53, 4, 8.0),
+                                   (1, 3, 70, 260, 4, 30.0), (1, 5, 20, 31, 5, 2.0), (1, 64, 64, 128, 4, 3.0)])
+def test_fused_filter_interpolate_equals_composition(L, shape):
+    """memc_b200.fused.FilterInterpolate (one kernel: two warps + occlusion blend) vs the reference's
+    composition of two FilterInterpolationModule calls and the fp32 blend (networks/MEMC_Net.py:258-264):
+    forward bit-identical; gradients of all eight inputs equal those of autograd through the composition."""
+    from memc_b200 import fused
+    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+    B, C, H, W, fs, sigma = shape
+    g = torch.Generator().manual_seed(7)
+    cases = [fi_case(B, C, H, W, fs, sigma, seed=70 + k) for k in range(2)]
+
+    def leaves():
+        refs = [dev(c[0]).requires_grad_() for c in cases]
+        offs = [dev(c[1]).requires_grad_() for c in cases]
+        filts = [dev(c[2]).requires_grad_() for c in cases]
+        occs = [(0.5 + 0.3 * torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(9 + k))).cuda().requires_grad_()
+                for k in range(2)]
+        return refs, offs, filts, occs
+
+    gout = torch.randn(B, C, H, W, generator=g).cuda()
+    r, o, f, oc = leaves()
+    fused_out = fused.FilterInterpolate(r[0], r[1], o, f, oc, fs * fs)
+    fused_grads = torch.autograd.grad(fused_out, r + o + f + oc, gout)
+    r2, o2, f2, oc2 = leaves()
+    comp = oc2[0] * FilterInterpolationModule()(r2[0], o2[0], f2[0]) + oc2[1] * FilterInterpolationModule()(r2[1], o2[1], f2[1])
+    comp_grads = torch.autograd.grad(comp, r2 + o2 + f2 + oc2, gout)
+    assert torch.equal(fused_out, comp), "fused forward must be bit-identical to the composition"
+    for a, b, name in zip(fused_grads, comp_grads, ["ref0", "ref2", "off0", "off1", "filt0", "filt1", "occ0", "occ1"]):
+        close(a, host(b), tol=2e-5, what="fused grad " + name)
+
+
 # ------------------------------------------------------------------------ FlowProjection
 FP_SHAPES = [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0), (2, 96, 160, 6.0), (1, 70, 260, 1.0)]
 
