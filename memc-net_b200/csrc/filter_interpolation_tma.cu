@@ -336,86 +336,6 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
 bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m);  // m[5]
 
 // ------------------------------------------------------------------------------------
-// forward, second generation of the one-tile-per-CTA kernel: shorter dependent chain.
-//   * the image neighbourhood of the tile (a generous PW x PH box around the tile) is
-//     PREFETCHED INTO L2 at CTA start, before the flow is known, so that the data-dependent
-//     image TMA issued later mostly hits L2;
-//   * the bounding box is computed by warp 0 alone right after the flow tile lands (no block
-//     barrier, no shared atomics); the other warps go straight to the waits.
-// ------------------------------------------------------------------------------------
-constexpr int PREF_W = 96, PREF_H = 48;  // L2 prefetch box
-
-template <int C, class K, bool PFL2>
-__global__ void __launch_bounds__(K::NT, K::MINB)
-fi_fwd_tma2_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                   const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_pref,
-                   const __grid_constant__ FiArgs p) {
-    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    constexpr Layout lay = make_layout<K>(C, 16, false);
-    const float* s_filt = reinterpret_cast<const float*>(sm + lay.off_a);
-    const float* s_flow = reinterpret_cast<const float*>(sm + lay.off_flow);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.off_bar);  // 0 flow, 1 filter, 2 image
-    volatile int* s_box = reinterpret_cast<volatile int*>(bars + 3);  // bx, by (written by lane 0 of warp 0)
-    const float* s_img = reinterpret_cast<const float*>(sm + lay.off_img);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-    const int W = p.W, H = p.H;
-
-    prof_mark(p, 0, 0);
-    if (tid == 0) {
-        tma::mbar_init(&bars[0], 1);
-        tma::mbar_init(&bars[1], 1);
-        tma::mbar_init(&bars[2], 1);
-        tma::fence_barrier_init();
-        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
-        tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
-        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
-        tma::load_4d(sm + lay.off_a, &m_filt, x0, y0, 0, b, &bars[1]);
-        if (PFL2) tma::prefetch_l2_4d(&m_pref, (x0 + TW / 2 - PREF_W / 2) & ~3, y0 + TH / 2 - PREF_H / 2, 0, b);
-    }
-    __syncthreads();  // barriers initialised before anybody waits on them
-
-    tma::mbar_wait(&bars[0], 0, 1);
-    prof_mark(p, 0, 1);
-    if (warp == 0) {
-        int bx, by;
-        tile_box_warp<K>(s_flow, x0, y0, W, H, lane, bx, by);
-        if (lane == 0) {
-            s_box[0] = bx;
-            s_box[1] = by;
-            tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);  // release: publishes s_box to the waiters
-            tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
-        }
-    }
-    prof_mark(p, 0, 2);
-    tma::mbar_wait(&bars[1], 0, 2);
-    tma::mbar_wait(&bars[2], 0, 3);
-    prof_mark(p, 0, 3);
-    const int bx = s_box[0], by = s_box[1];
-    fwd_compute_tile<C, K>(p, s_filt, s_flow, s_img, x0, y0, b, bx, by, lane, warp);
-    prof_mark(p, 0, 4);
-}
-
-template <int C, class K, bool PFL2>
-int launch_fwd2(cudaStream_t stream, const FiArgs& a) {
-    if (a.W < K::SW || a.H < K::SH || a.W < PREF_W || a.H < PREF_H) return 0;
-    CUtensorMap m[5], mpref;
-    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    if (!tma::make_map_nchw(&mpref, a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, PREF_W, PREF_H, a.C,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
-        return 0;
-    constexpr size_t smem = (size_t)make_layout<K>(C, 16, false).total + 128;
-    if (!ensure_dynamic_smem(fi_fwd_tma2_kernel<C, K, PFL2>, smem)) return 0;
-    dim3 grid((a.W + K::TW - 1) / K::TW, (a.H + K::TH - 1) / K::TH, a.B);
-    fi_fwd_tma2_kernel<C, K, PFL2><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], mpref, a);
-    count_launch();
-    return check_launch("FilterInterpolation forward (TMA v2)") == 0 ? 1 : -1;
-}
-
-// ------------------------------------------------------------------------------------
 // forward for C > 4 (e.g. the 64-channel context features MEMC_Net_star warps with the same
 // flow / filter, networks/MEMC_Net_star.py:280-285): flow tile, filter tile and bounding box are
 // set up ONCE per tile, then the image is streamed through a two-buffer ring of CBK-channel
@@ -571,132 +491,6 @@ int launch_fwd_chunked(cudaStream_t stream, const FiArgs& a) {
     fi_fwd_tma_chunked_kernel<K><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a4);
     count_launch();
     return check_launch("FilterInterpolation forward (TMA, channel-chunked)") == 0 ? 1 : -1;
-}
-
-// ------------------------------------------------------------------------------------
-// persistent-lite forward (experiment, selectable with MEMC_FI_FWD_CFG=12..16; a fully double-buffered
-// persistent ring was also built and measured slower still, see profiles/r01_fi_tile_sweep.md):
-// like the one-tile-per-CTA kernel (same smem budget, so the same
-// number of CTAs per SM), but every CTA walks tiles blockIdx.x, +grid, ... and PREFETCHES the
-// small flow tile (optionally also the filter tile) of its next tile while it computes the
-// current one.  The dependent chain per tile shrinks from
-//     launch -> flow (HBM latency) -> bounding box -> image box (L2/HBM latency) -> compute
-// to  bounding box -> image box -> compute.
-// ------------------------------------------------------------------------------------
-template <class K>
-__host__ __device__ constexpr int pl_smem(int C, bool pf) {
-    return (pf ? 2 : 1) * 16 * K::TH * K::TW * 4 + 2 * (2 * K::TH * K::TW * 4) + C * K::SH * K::SW * 4 + 256;
-}
-
-template <int C, class K, bool PF>
-__global__ void __launch_bounds__(K::NT, K::MINB)
-fi_fwd_pl_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                 const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p, const int tiles_x, const int tiles_y,
-                 const int n_tiles) {
-    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
-    constexpr int FILT_B = 16 * TH * TW * 4, IMG_B = C * SH * SW * 4, FLOW_B = 2 * TH * TW * 4;
-    constexpr int NF = PF ? 2 : 1;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    unsigned char* const sm_filt = sm;                               // NF slots
-    unsigned char* const sm_flow = sm + NF * FILT_B;                 // 2 slots
-    unsigned char* const sm_img = sm_flow + 2 * FLOW_B;              // 1 slot
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_img + IMG_B);    // [0,1] flow, [2,3] filter, [4] image
-    int* s_bb = reinterpret_cast<int*>(bars + 6);                    // 2 x 4
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-    if (n == 0) return;
-    const int W = p.W, H = p.H;
-    const int per_frame = tiles_x * tiles_y;
-    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
-        const int t = (int)blockIdx.x + i * G;
-        b = t / per_frame;
-        const int r = t - b * per_frame;
-        const int ty = r / tiles_x;
-        x0 = (r - ty * tiles_x) * TW;
-        y0 = ty * TH;
-    };
-    auto issue_flow = [&](int i) {  // thread 0
-        int x0, y0, b;
-        tile_origin(i, x0, y0, b);
-        tma::mbar_expect_tx(&bars[i & 1], FLOW_B);
-        tma::load_4d(sm_flow + (i & 1) * FLOW_B, &m_flow, x0, y0, 0, b, &bars[i & 1]);
-    };
-    auto issue_filt = [&](int i) {  // thread 0
-        int x0, y0, b;
-        tile_origin(i, x0, y0, b);
-        const int sl = PF ? (i & 1) : 0;
-        tma::mbar_expect_tx(&bars[2 + sl], FILT_B);
-        tma::load_4d(sm_filt + sl * FILT_B, &m_filt, x0, y0, 0, b, &bars[2 + sl]);
-    };
-
-    if (tid == 0) {
-        for (int k = 0; k < 5; ++k) tma::mbar_init(&bars[k], 1);
-        for (int k = 0; k < 8; ++k) s_bb[k] = (k & 1) ? INT_MIN : INT_MAX;
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        issue_flow(0);
-        if (PF) issue_filt(0);
-    }
-    for (int i = 0; i < n; ++i) {
-        int x0, y0, b;
-        tile_origin(i, x0, y0, b);
-        if (tid == 0) {
-            tma::fence_proxy_async();  // the slots refilled below were last read by generic loads
-            if (i + 1 < n) {
-                issue_flow(i + 1);
-                if (PF) issue_filt(i + 1);
-            }
-            if (!PF) issue_filt(i);
-        }
-        prof_mark(p, i, 0);
-        tma::mbar_wait(&bars[i & 1], (i >> 1) & 1, 41);
-        prof_mark(p, i, 1);
-        const float* s_flow = reinterpret_cast<const float*>(sm_flow + (i & 1) * FLOW_B);
-        int bx, by;
-        tile_box<K>(s_flow, s_bb + 4 * (i & 1), x0, y0, W, H, lane, warp, bx, by);
-        prof_mark(p, i, 2);
-        if (tid == 0) {
-            tma::mbar_expect_tx(&bars[4], IMG_B);
-            tma::load_4d(sm_img, &m_img, bx, by, 0, b, &bars[4]);
-        }
-        const int fsl = PF ? (i & 1) : 0;
-        tma::mbar_wait(&bars[2 + fsl], PF ? ((i >> 1) & 1) : (i & 1), 42);
-        tma::mbar_wait(&bars[4], i & 1, 43);
-        prof_mark(p, i, 3);
-        fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm_filt + fsl * FILT_B), s_flow,
-                               reinterpret_cast<const float*>(sm_img), x0, y0, b, bx, by, lane, warp);
-        prof_mark(p, i, 4);
-        if (tid == 0) {
-            int* bb = s_bb + 4 * (i & 1);
-            bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;
-        }
-        __syncthreads();
-    }
-}
-
-template <int C, class K, bool PF>
-int launch_fwd_pl(cudaStream_t stream, const FiArgs& a) {
-    if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[5];
-    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    constexpr size_t smem = (size_t)pl_smem<K>(C, PF) + 128;
-    if (!ensure_dynamic_smem(fi_fwd_pl_kernel<C, K, PF>, smem)) return 0;
-    int dev = 0, n_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) return 0;
-    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
-    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
-    if (n_tiles > 0x7fffffffLL) return 0;
-    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
-    fi_fwd_pl_kernel<C, K, PF><<<grid, K::NT, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
-    count_launch();
-    return check_launch("FilterInterpolation forward (persistent-lite TMA)") == 0 ? 1 : -1;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1114,184 +908,6 @@ fi_fwd_ws_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_consta
     }
 }
 
-// ------------------------------------------------------------------------------------
-// Same ring, but the 16 filter planes never touch shared memory: every consumer thread (one pixel
-// per thread) loads the 16 taps of its pixel of the NEXT tile straight into registers
-// (coalesced 128-byte LDG.NC, no L1 allocation) before it computes the current tile.  Staging the
-// filter through shared memory costs the data pipe a TMA fill (64 B/px) plus an LDS pass
-// (16 wavefronts per 32 px); the direct load costs one pass.  Slots hold the image box only.
-// ------------------------------------------------------------------------------------
-template <class K, int C, int NS, int NFS>
-struct WrLayout {
-    static constexpr int FLOW_B = 2 * K::TH * K::TW * 4, IMG_B = C * K::SH * K::SW * 4;
-    static constexpr int OFF_IMG = 0, OFF_FLOW = NS * IMG_B;
-    static constexpr int OFF_BAR = OFF_FLOW + NFS * FLOW_B;  // full_flow[NFS], full_img[NS], empty[NS]
-    static constexpr int OFF_BOX = OFF_BAR + (NFS + 2 * NS) * 8;
-    static constexpr int TOTAL = OFF_BOX + NS * 8;
-    static_assert(FLOW_B % 128 == 0 && IMG_B % 128 == 0, "TMA destinations are 128-byte aligned");
-};
-
-// one pixel with its 16 filter taps in registers; arithmetic identical to fwd_compute_tile
-template <int C, class K>
-__device__ __forceinline__ void fwd_compute_pixel_rw(const FiArgs& p, const float (&wg)[16], const float* s_flow,
-                                                     const float* s_img, int x0, int y0, int b, int bx, int by, int xl,
-                                                     int yl) {
-    constexpr int TW = K::TW, TH = K::TH, SW = K::SW, SH = K::SH;
-    const int W = p.W, H = p.H;
-    const int x = x0 + xl, y = y0 + yl;
-    if (x >= W || y >= H) return;
-    const float* in1b = p.in1p + b * p.in1.b;
-    float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
-    const FiGeom g = fi_geometry(x, y, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
-    if (!g.valid) {  // my_lib_kernel.cu:1209-1213: copy the input pixel
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-            stg_stream(outp + c * p.out.c, __ldg(in1b + c * p.in1.c + (int64_t)y * p.in1.h + x));
-        return;
-    }
-    const int lx = g.ix - 1 - bx, ly = g.iy - 1 - by;
-    if (__builtin_expect(!(((unsigned)lx <= (unsigned)(SW - 4)) && ((unsigned)ly <= (unsigned)(SH - 4))), 0)) {
-        float res[C];
-        fwd_slow_pixel<C, K>(p, wg, 1, s_img, in1b, g.ix - 1, g.iy - 1, bx, by, g.alpha, g.beta, res);
-#pragma unroll
-        for (int c = 0; c < C; ++c) stg_stream(outp + c * p.out.c, res[c]);
-        return;
-    }
-    const float a = g.alpha, bt = g.beta;
-    const float wTL = (1.0f - a) * (1.0f - bt), wTR = a * (1.0f - bt);
-    const float wBL = (1.0f - a) * bt, wBR = a * bt;
-    const float* base = s_img + ly * SW + lx;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        float q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                q[(j >> 1) * 2 + (i >> 1)] = fmaf(base[c * SH * SW + j * SW + i], wg[j * 4 + i], q[(j >> 1) * 2 + (i >> 1)]);
-        stg_stream(outp + c * p.out.c, wTL * q[0] + wTR * q[1] + wBL * q[2] + wBR * q[3]);
-    }
-}
-
-template <int C, class K, int NS, int NFS>
-__global__ void __launch_bounds__(K::NT + 32, K::MINB)
-fi_fwd_wr_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_img,
-                 const __grid_constant__ FiArgs p, const int tiles_x, const int tiles_y, const int n_tiles) {
-    using L = WrLayout<K, C, NS, NFS>;
-    constexpr int NCW = K::NT / 32;
-    constexpr int LF = NFS - NS;
-    static_assert(LF >= 1 && K::PPT == 1, "one pixel per consumer thread");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    uint64_t* full_flow = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
-    uint64_t* full_img = full_flow + NFS;
-    uint64_t* empty = full_img + NS;
-    volatile int* s_box = reinterpret_cast<volatile int*>(sm + L::OFF_BOX);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-    const int W = p.W, H = p.H;
-    const int per_frame = tiles_x * tiles_y;
-    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
-        const int t = (int)blockIdx.x + i * G;
-        b = t / per_frame;
-        const int r = t - b * per_frame;
-        const int ty = r / tiles_x;
-        x0 = (r - ty * tiles_x) * K::TW;
-        y0 = ty * K::TH;
-    };
-
-    if (tid == 0) {
-        for (int k = 0; k < NFS; ++k) tma::mbar_init(&full_flow[k], 1);
-        for (int k = 0; k < NS; ++k) {
-            tma::mbar_init(&full_img[k], 1);
-            tma::mbar_init(&empty[k], NCW);
-        }
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (n == 0) return;
-
-    if (warp == NCW) {
-        auto issue_flow = [&](int i) {  // lane 0
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            tma::mbar_expect_tx(&full_flow[i % NFS], L::FLOW_B);
-            tma::load_4d(sm + L::OFF_FLOW + (i % NFS) * L::FLOW_B, &m_flow, x0, y0, 0, b, &full_flow[i % NFS]);
-        };
-        if (lane == 0)
-            for (int i = 0; i < LF && i < n; ++i) issue_flow(i);
-        for (int i = 0; i < n; ++i) {
-            const int s = i % NS, fsl = i % NFS;
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 71);
-            int bx, by;
-            tile_box_warp<K>(reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B), x0, y0, W, H, lane, bx, by);
-            if (i >= NS) tma::mbar_wait(&empty[s], ((i / NS) - 1) & 1, 72);
-            if (lane == 0) {
-                s_box[2 * s] = bx;
-                s_box[2 * s + 1] = by;
-                tma::mbar_expect_tx(&full_img[s], L::IMG_B);
-                tma::load_4d(sm + L::OFF_IMG + s * L::IMG_B, &m_img, bx, by, 0, b, &full_img[s]);
-                if (i + LF < n) issue_flow(i + LF);
-            }
-            __syncwarp();
-        }
-    } else {
-        int xl, yl;
-        tile_pixel<K>(0, lane, warp, xl, yl);
-        auto load_w = [&](int i, float (&w)[16]) {
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            const int x = x0 + xl, y = y0 + yl;
-            const bool inb = x < W && y < H;
-            const float* fp = p.filtp + b * p.filt.b + (int64_t)(inb ? y : 0) * p.filt.h + (inb ? x : 0);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) w[t] = ldg_stream(fp + t * p.filt.c);
-        };
-        float wg[16], wn[16];
-        load_w(0, wg);
-        for (int i = 0; i < n; ++i) {
-            const int s = i % NS, fsl = i % NFS;
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            if (i + 1 < n) load_w(i + 1, wn);
-            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 73);
-            tma::mbar_wait(&full_img[s], (i / NS) & 1, 75);
-            const int bx = s_box[2 * s], by = s_box[2 * s + 1];
-            fwd_compute_pixel_rw<C, K>(p, wg, reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B),
-                                       reinterpret_cast<const float*>(sm + L::OFF_IMG + s * L::IMG_B), x0, y0, b, bx, by, xl,
-                                       yl);
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(&empty[s]);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) wg[t] = wn[t];
-        }
-    }
-}
-
-template <int C, class K, int NS, int NFS>
-int launch_fwd_wr(cudaStream_t stream, const FiArgs& a) {
-    if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[5];
-    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    constexpr size_t smem = (size_t)WrLayout<K, C, NS, NFS>::TOTAL + 128;
-    if (!ensure_dynamic_smem(fi_fwd_wr_kernel<C, K, NS, NFS>, smem)) return 0;
-    int dev = 0, n_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) return 0;
-    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
-    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
-    if (n_tiles > 0x7fffffffLL) return 0;
-    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
-    fi_fwd_wr_kernel<C, K, NS, NFS><<<grid, K::NT + 32, smem, stream>>>(m[0], m[2], a, tiles_x, tiles_y, (int)n_tiles);
-    count_launch();
-    return check_launch("FilterInterpolation forward (warp-specialised ring, register filter)") == 0 ? 1 : -1;
-}
-
 template <int C, class K, int NS, int NFS>
 int launch_fwd_ws(cudaStream_t stream, const FiArgs& a) {
     if (a.W < K::SW || a.H < K::SH) return 0;
@@ -1697,45 +1313,16 @@ int launch_bwd(cudaStream_t stream, const FiArgs& a) {
 // tile configurations.  *_DEFAULT is what production uses; the others are selectable with
 // MEMC_FI_FWD_CFG / MEMC_FI_BWD_CFG (C == 3 only) for tools/kbench.py sweeps.
 //                  TW  TH  SW  SH   NT  MINB
-using FwdA = Cfg<64, 16, 96, 32, 512, 2>;  // 110 KB: 2 CTAs / SM
-using FwdB = Cfg<32, 16, 64, 32, 256, 3>;  //  61 KB: 3 CTAs / SM
-using FwdC = Cfg<32, 16, 64, 40, 256, 3>;  //  67 KB: 3 CTAs / SM
-using FwdD = Cfg<64, 8, 96, 24, 256, 3>;   //  64 KB: 3 CTAs / SM
 using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
 using FwdE6 = Cfg<32, 8, 64, 24, 128, 6>;  //  same, registers capped at 80: 6 CTAs / SM
-using FwdH1 = Cfg<32, 6, 64, 20, 96, 7>;   //  29 KB: 7 CTAs / SM, 6-row tiles
-using FwdH2 = Cfg<32, 6, 64, 22, 96, 7>;   //  31 KB: 7 CTAs / SM
-using FwdQ1 = Cfg<32, 4, 64, 16, 64, 10>;  //  22 KB: 10 CTAs / SM, 4-row tiles, 2 px / thread
-using FwdQ2 = Cfg<32, 4, 64, 16, 128, 10>; //  22 KB: 10 CTAs / SM, 1 px / thread
-using FwdE2 = Cfg<32, 8, 64, 32, 128, 5>;  //  43 KB: 5 CTAs / SM, taller box (fewer fallback taps)
-using FwdE3 = Cfg<32, 8, 64, 28, 128, 5>;  //  40 KB
-using FwdF = Cfg<32, 8, 64, 24, 256, 5>;   //  37 KB: 5 CTAs / SM, 1 px / thread (<= 51 registers)
-using FwdG = Cfg<32, 16, 64, 32, 512, 3>;  //  61 KB: 3 CTAs / SM, 1 px / thread (<= 42 registers)
-using FwdL1 = Cfg<32, 8, 64, 24, 128, 5>;   // persistent-lite,  39 KB: 5 CTAs / SM
-using FwdL2 = Cfg<32, 8, 64, 24, 128, 4>;   // persistent-lite + filter prefetch, 55 KB: 4 CTAs / SM
-using FwdL3 = Cfg<32, 16, 64, 40, 256, 3>;  // persistent-lite,  71 KB: 3 CTAs / SM
-using FwdL4 = Cfg<32, 8, 64, 24, 256, 5>;   // persistent-lite, 1 px / thread
-using FwdK1 = Cfg<64, 16, 96, 32, 512, 1>;  // channel-chunked (C > 4), 171 KB: 1 CTA / SM
 using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
 using FwdK3 = Cfg<32, 16, 72, 32, 256, 2, true>;  // channel-chunked, 8x4 patches, box pitch 72: 110 KB
-using FwdK4 = Cfg<32, 16, 72, 28, 256, 2, true>;  // 101 KB
-using FwdK5 = Cfg<32, 8, 72, 24, 128, 4, true>;   // 8-row tiles:  73 KB -> 3 CTAs / SM
 using FwdW1 = Cfg<32, 8, 64, 24, 256, 2>;   // warp-specialised ring: 8 consumer warps, 1 px / thread
-using FwdW2 = Cfg<32, 8, 64, 24, 128, 2>;   // 4 consumer warps, 2 px / thread
-using FwdW3 = Cfg<32, 8, 64, 24, 256, 3>;   // 2-slot ring, 3 CTAs / SM
-using FwdW4 = Cfg<32, 8, 64, 24, 128, 3>;
-using FwdW5 = Cfg<32, 16, 64, 32, 512, 1>;  // 16 consumer warps, one CTA / SM
-using FwdW6 = Cfg<32, 16, 64, 32, 256, 1>;
 using FWD_DEFAULT = FwdE6;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
-using BwdB = Cfg<32, 8, 64, 24, 128, 3>;   //  58 KB: 3 CTAs / SM, 2 px / thread
 using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
-using BwdD = Cfg<32, 16, 64, 32, 512, 2>;  //  91 KB: 2 CTAs / SM, 1 px / thread
 using BwdE = Cfg<32, 8, 64, 32, 256, 3>;   //  70 KB: 3 CTAs / SM, taller box
 using BwdF = Cfg<32, 8, 64, 28, 256, 3>;   //  64 KB
-using BwdG = Cfg<32, 16, 64, 36, 256, 2>;  // 104 KB: 2 CTAs / SM
-using BwdH = Cfg<32, 16, 64, 40, 256, 2>;  // 110 KB: 2 CTAs / SM
-using BwdI = Cfg<32, 16, 64, 36, 512, 2>;  // 104 KB: 2 CTAs / SM, 1 px / thread
 using BWD_DEFAULT = BwdF;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
 
 int env_int(const char* name) {
@@ -1777,9 +1364,6 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
         // shared / L1 gather wavefronts per pixel, not by HBM (profiles/r01_kernel_table.md).
         const int cfg = env_int("MEMC_FI_FWD_CFG");
         if (cfg == 32) return launch_fwd_chunked<FwdK3>(stream, a);
-        if (cfg == 33) return launch_fwd_chunked<FwdK4>(stream, a);
-        if (cfg == 34) return launch_fwd_chunked<FwdK5>(stream, a);
-        if (cfg == 30) return launch_fwd_chunked<FwdK1>(stream, a);
         if (cfg == 31) return launch_fwd_chunked<FwdK2>(stream, a);
         if (cfg == 9) return 0;  // generic kernel
         return launch_fwd_chunked<FwdK3>(stream, a);
@@ -1794,44 +1378,11 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
     if (a.C == 3) {
         int r = 0;
         switch (env_int("MEMC_FI_FWD_CFG")) {
-            case 1: r = launch_fwd<3, FwdA>(stream, a); break;
-            case 2: r = launch_fwd<3, FwdB>(stream, a); break;
-            case 3: r = launch_fwd<3, FwdC>(stream, a); break;
-            case 4: r = launch_fwd<3, FwdD>(stream, a); break;
             case 5: r = launch_fwd<3, FwdE>(stream, a); break;
-            case 10: r = launch_fwd<3, FwdF>(stream, a); break;
-            case 12: r = launch_fwd_pl<3, FwdL1, false>(stream, a); break;
             case 19: r = launch_fwd<3, FwdE6>(stream, a); break;
             case 50: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;
             case 51: r = launch_fwd_patch<3, 72, 22, 6, true>(stream, a); break;
-            case 52: r = launch_fwd_patch<3, 72, 24, 5, true>(stream, a); break;
-            case 53: r = launch_fwd_patch<3, 72, 22, 5, false>(stream, a); break;
-            case 60: r = launch_fwd<3, FwdH1>(stream, a); break;
-            case 61: r = launch_fwd<3, FwdH2>(stream, a); break;
-            case 62: r = launch_fwd<3, FwdQ1>(stream, a); break;
-            case 63: r = launch_fwd<3, FwdQ2>(stream, a); break;
-            case 17: r = launch_fwd<3, FwdE2>(stream, a); break;
-            case 18: r = launch_fwd<3, FwdE3>(stream, a); break;
-            case 20: r = launch_fwd2<3, FwdE, false>(stream, a); break;
-            case 21: r = launch_fwd2<3, FwdE, true>(stream, a); break;
-            case 22: r = launch_fwd2<3, FwdC, true>(stream, a); break;
-            case 23: r = launch_fwd2<3, FwdF, true>(stream, a); break;
-            case 24: r = launch_fwd2<3, FwdB, true>(stream, a); break;
-            case 13: r = launch_fwd_pl<3, FwdL2, true>(stream, a); break;
-            case 14: r = launch_fwd_pl<3, FwdL3, false>(stream, a); break;
-            case 15: r = launch_fwd_pl<3, FwdL4, false>(stream, a); break;
-            case 16: r = launch_fwd_pl<3, FwdL3, true>(stream, a); break;
-            case 11: r = launch_fwd<3, FwdG>(stream, a); break;
             case 70: r = launch_fwd_ws<3, FwdW1, 3, 5>(stream, a); break;
-            case 80: r = launch_fwd_wr<3, FwdW1, 3, 5>(stream, a); break;
-            case 81: r = launch_fwd_wr<3, FwdW3, 3, 5>(stream, a); break;
-            case 82: r = launch_fwd_wr<3, FwdW3, 2, 3>(stream, a); break;
-            case 83: r = launch_fwd_wr<3, FwdW5, 3, 5>(stream, a); break;
-            case 71: r = launch_fwd_ws<3, FwdW2, 3, 5>(stream, a); break;
-            case 72: r = launch_fwd_ws<3, FwdW3, 2, 3>(stream, a); break;
-            case 73: r = launch_fwd_ws<3, FwdW4, 2, 3>(stream, a); break;
-            case 74: r = launch_fwd_ws<3, FwdW5, 3, 5>(stream, a); break;
-            case 75: r = launch_fwd_ws<3, FwdW6, 3, 5>(stream, a); break;
             case 9: r = launch_fwd<3, FWD_DEFAULT>(stream, a); break;
             default: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;  // best of the sweeps
         }
@@ -1862,14 +1413,9 @@ int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {
     if (a.C == 3 && ow) {
         switch (env_int("MEMC_FI_BWD_CFG")) {
             case 1: return launch_bwd<3, true, BwdA>(stream, a);
-            case 2: return launch_bwd<3, true, BwdB>(stream, a);
             case 3: return launch_bwd<3, true, BwdC>(stream, a);
-            case 4: return launch_bwd<3, true, BwdD>(stream, a);
             case 5: return launch_bwd<3, true, BwdE>(stream, a);
             case 6: return launch_bwd<3, true, BwdF>(stream, a);
-            case 7: return launch_bwd<3, true, BwdG>(stream, a);
-            case 8: return launch_bwd<3, true, BwdH>(stream, a);
-            case 9: return launch_bwd<3, true, BwdI>(stream, a);
             default: return launch_bwd<3, true, BWD_DEFAULT>(stream, a);
         }
     }

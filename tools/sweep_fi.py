@@ -12,9 +12,8 @@ from tools.kbench import timeit, fi_calls, _peak
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--out", default="gpurun_out/sweep_fi.json")
-ap.add_argument("--fwd", default="5,17,18")
-ap.add_argument("--bwd", default="0,5,6")
-ap.add_argument("--bwd-int", action="store_true")
+ap.add_argument("--fwd", default="0,5,19,51,70")
+ap.add_argument("--bwd", default="0,1,3,5")
 args = ap.parse_args()
 lib.load()
 peak, _ = _peak()
@@ -58,13 +57,5 @@ for cfg in [int(c) for c in args.bwd.split(",") if c != ""]:
     except Exception as e:
         r = {"op": "bwd", "cfg": cfg, "error": str(e)[:200]}
     rows.append(r); print(json.dumps(r), flush=True)
-if args.bwd_int:
-    os.environ["MEMC_TMA_DBG"] = "16"
-    for cfg in (1, 2, 4):
-        os.environ["MEMC_FI_BWD_CFG"] = str(cfg)
-        t = timeit(bwd, args.iters)
-        r = {"op": "bwd-int-atomics-TIMING-ONLY", "cfg": cfg, "ms": t * 1e3, "frac": px * 180 / t / 1e9 / peak}
-        rows.append(r); print(json.dumps(r), flush=True)
-    os.environ["MEMC_TMA_DBG"] = "0"
 os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
 json.dump(rows, open(args.out, "w"), indent=1)
