@@ -31,11 +31,15 @@ struct ScArgs {
 constexpr int BX = 32, BY = 8;
 
 // Two output pixels per thread (rows h and h + BY): twice the independent loads in flight.
+// FS = 4 (the size every shipped model uses): loops unrolled, the 2 x 4 filter values of a pixel
+// are loaded once into registers instead of once per channel and tap.
+template <int FS>
 __global__ void __launch_bounds__(BX* BY) sc_fwd_kernel(const ScArgs p) {
+    constexpr int MAXFS = FS > 0 ? FS : 1;
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h0 = blockIdx.y * (2 * BY) + threadIdx.y;
     const int b = blockIdx.z;
-    const int fs = p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
+    const int fs = FS > 0 ? FS : p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
     if (w >= Wo || h0 >= Ho) return;
     const int h1 = min(h0 + BY, Ho - 1);          // second row (clamped: recomputed, not stored, if out of range)
     const bool two = h0 + BY < Ho;
@@ -47,15 +51,36 @@ __global__ void __launch_bounds__(BX* BY) sc_fwd_kernel(const ScArgs p) {
     const float* img1 = p.in1p + b * p.in1.b + h1 * p.in1.h + w;
     float* ob0 = p.outp + b * p.out.b + h0 * p.out.h + w;
     float* ob1 = p.outp + b * p.out.b + h1 * p.out.h + w;
+    float v0[MAXFS], v1[MAXFS], z0[MAXFS], z1[MAXFS];
+    if (FS > 0) {
+#pragma unroll
+        for (int k = 0; k < FS; ++k) {
+            v0[k] = ldg_stream(vp0 + k * p.vert.c); v1[k] = ldg_stream(vp1 + k * p.vert.c);
+            z0[k] = ldg_stream(hp0 + k * p.horiz.c); z1[k] = ldg_stream(hp1 + k * p.horiz.c);
+        }
+    }
     for (int c = 0; c < p.C; ++c, img0 += p.in1.c, img1 += p.in1.c) {
         float acc0 = 0.f, acc1 = 0.f;
-        for (int y = 0; y < fs; ++y) {
-            const float vy0 = __ldg(vp0 + y * p.vert.c), vy1 = __ldg(vp1 + y * p.vert.c);
-            const float* row0 = img0 + y * p.in1.h;
-            const float* row1 = img1 + y * p.in1.h;
-            for (int x = 0; x < fs; ++x) {  // (t1*t2)*t3 as the reference
-                acc0 += __ldg(row0 + x) * vy0 * __ldg(hp0 + x * p.horiz.c);
-                acc1 += __ldg(row1 + x) * vy1 * __ldg(hp1 + x * p.horiz.c);
+        if (FS > 0) {
+#pragma unroll
+            for (int y = 0; y < FS; ++y) {
+                const float* row0 = img0 + y * p.in1.h;
+                const float* row1 = img1 + y * p.in1.h;
+#pragma unroll
+                for (int x = 0; x < FS; ++x) {  // (t1*t2)*t3 as the reference
+                    acc0 += __ldg(row0 + x) * v0[y] * z0[x];
+                    acc1 += __ldg(row1 + x) * v1[y] * z1[x];
+                }
+            }
+        } else {
+            for (int y = 0; y < fs; ++y) {
+                const float vy0 = __ldg(vp0 + y * p.vert.c), vy1 = __ldg(vp1 + y * p.vert.c);
+                const float* row0 = img0 + y * p.in1.h;
+                const float* row1 = img1 + y * p.in1.h;
+                for (int x = 0; x < fs; ++x) {
+                    acc0 += __ldg(row0 + x) * vy0 * __ldg(hp0 + x * p.horiz.c);
+                    acc1 += __ldg(row1 + x) * vy1 * __ldg(hp1 + x * p.horiz.c);
+                }
             }
         }
         stg_stream(ob0 + c * p.out.c, acc0);
@@ -63,13 +88,14 @@ __global__ void __launch_bounds__(BX* BY) sc_fwd_kernel(const ScArgs p) {
     }
 }
 
-// filter gradients: own pixel, registers
-template <bool OVERWRITE>
+// filter gradients: own pixel, registers.  FS = 4: one pass over the 16 taps of a channel feeds
+// all eight accumulators (each accumulator still sums in the generic kernel's order).
+template <bool OVERWRITE, int FS>
 __global__ void __launch_bounds__(BX* BY) sc_bwd_filters_kernel(const ScArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;
-    const int fs = p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
+    const int fs = FS > 0 ? FS : p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
     if (w >= Wo || h >= Ho) return;
     const float* vp = p.vertp + b * p.vert.b + h * p.vert.h + w;
     const float* hp = p.horizp + b * p.horiz.b + h * p.horiz.h + w;
@@ -77,6 +103,38 @@ __global__ void __launch_bounds__(BX* BY) sc_bwd_filters_kernel(const ScArgs p) 
     const float* go = p.goutp + b * p.out.b + h * p.out.h + w;
     float* g2 = p.gi2p + b * p.gi2.b + h * p.gi2.h + w;
     float* g3 = p.gi3p + b * p.gi3.b + h * p.gi3.h + w;
+    if (FS > 0) {
+        constexpr int N = FS > 0 ? FS : 1;
+        float v[N], z[N], a2[N], a3[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            v[k] = ldg_stream(vp + k * p.vert.c);
+            z[k] = ldg_stream(hp + k * p.horiz.c);
+            a2[k] = a3[k] = 0.f;
+        }
+        for (int c = 0; c < p.C; ++c) {
+            const float gov = ldg_stream(go + c * p.out.c);
+            float t[N][N];
+#pragma unroll
+            for (int y = 0; y < N; ++y)
+#pragma unroll
+                for (int x = 0; x < N; ++x) t[y][x] = __ldg(img0 + c * p.in1.c + y * p.in1.h + x);
+#pragma unroll
+            for (int y = 0; y < N; ++y)  // d/d vert[y] = sum_c go_c sum_x in1[c,h+y,w+x] horiz[x]
+#pragma unroll
+                for (int x = 0; x < N; ++x) a2[y] += gov * t[y][x] * z[x];
+#pragma unroll
+            for (int x = 0; x < N; ++x)  // d/d horiz[x]
+#pragma unroll
+                for (int y = 0; y < N; ++y) a3[x] += gov * t[y][x] * v[y];
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (OVERWRITE) { stg_stream(g2 + k * p.gi2.c, a2[k]); stg_stream(g3 + k * p.gi3.c, a3[k]); }
+            else { g2[k * p.gi2.c] += a2[k]; g3[k * p.gi3.c] += a3[k]; }
+        }
+        return;
+    }
     for (int y = 0; y < fs; ++y) {  // d/d vert[y] = sum_c go_c sum_x in1[c,h+y,w+x] horiz[x]
         float acc = 0.f;
         for (int c = 0; c < p.C; ++c) {
@@ -99,20 +157,64 @@ __global__ void __launch_bounds__(BX* BY) sc_bwd_filters_kernel(const ScArgs p) 
     }
 }
 
-// image gradient as a gather over the INPUT extent
-template <bool OVERWRITE>
+// image gradient as a gather over the INPUT extent.  FS = 4: unrolled; the product
+// vert[y] * horiz[x] of a source pixel cannot be hoisted (the reference multiplies
+// (go * vert) * horiz), but its two factors are loaded once for all channels.
+template <bool OVERWRITE, int FS>
 __global__ void __launch_bounds__(BX* BY) sc_bwd_image_kernel(const ScArgs p) {
     const int X = blockIdx.x * BX + threadIdx.x;
     const int Y = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;
     if (X >= p.W || Y >= p.H) return;
-    const int fs = p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
+    const int fs = FS > 0 ? FS : p.fs, Ho = p.H - fs + 1, Wo = p.W - fs + 1;
     const int y0 = max(0, Y - Ho + 1), y1 = min(fs - 1, Y);  // 0 <= Y-y <= Ho-1
     const int x0 = max(0, X - Wo + 1), x1 = min(fs - 1, X);
     const float* vb = p.vertp + b * p.vert.b;
     const float* hb = p.horizp + b * p.horiz.b;
     const float* gob = p.goutp + b * p.out.b;
     float* g1 = p.gi1p + b * p.gi1.b + Y * p.gi1.h + X;
+    if (FS > 0 && p.C <= 4) {
+        constexpr int N = FS > 0 ? FS : 1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // base pointers at source pixel (Y, X); tap (y, x) sits y rows up and x columns left
+        const float* vq = vb + (int64_t)Y * p.vert.h + X;
+        const float* zq = hb + (int64_t)Y * p.horiz.h + X;
+        const float* gq = gob + (int64_t)Y * p.out.h + X;
+        const int vh = (int)p.vert.h, zh = (int)p.horiz.h, gh = (int)p.out.h;
+        const int vc = (int)p.vert.c, zc = (int)p.horiz.c, gc = (int)p.out.c;  // plane strides fit 31 bits per frame
+        const bool interior = y0 == 0 && y1 == N - 1 && x0 == 0 && x1 == N - 1;
+        if (interior) {
+#pragma unroll
+            for (int y = 0; y < N; ++y)
+#pragma unroll
+                for (int x = 0; x < N; ++x) {
+                    const float vv = __ldg(vq + y * vc - y * vh - x);
+                    const float zz = __ldg(zq + x * zc - y * zh - x);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < p.C) acc[c] += __ldg(gq + c * gc - y * gh - x) * vv * zz;
+                }
+        } else {
+#pragma unroll
+            for (int y = 0; y < N; ++y)
+#pragma unroll
+                for (int x = 0; x < N; ++x) {
+                    if (y < y0 || y > y1 || x < x0 || x > x1) continue;
+                    const float vv = __ldg(vq + y * vc - y * vh - x);
+                    const float zz = __ldg(zq + x * zc - y * zh - x);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < p.C) acc[c] += __ldg(gq + c * gc - y * gh - x) * vv * zz;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < p.C) {
+                if (OVERWRITE) stg_stream(g1 + c * p.gi1.c, acc[c]);
+                else g1[c * p.gi1.c] += acc[c];
+            }
+        return;
+    }
     for (int c = 0; c < p.C; ++c) {
         float acc = 0.f;
         for (int y = y0; y <= y1; ++y)
@@ -132,7 +234,8 @@ static int sc_forward(cudaStream_t stream, const ScArgs& a, int flags) {
     const int Ho = a.H - a.fs + 1, Wo = a.W - a.fs + 1;
     if (a.B <= 0 || a.C <= 0 || Ho <= 0 || Wo <= 0) return 0;
     dim3 block(BX, BY, 1), grid((Wo + BX - 1) / BX, (Ho + 2 * BY - 1) / (2 * BY), a.B);
-    sc_fwd_kernel<<<grid, block, 0, stream>>>(a);
+    if (a.fs == 4) sc_fwd_kernel<4><<<grid, block, 0, stream>>>(a);
+    else sc_fwd_kernel<0><<<grid, block, 0, stream>>>(a);
     count_launch();
     return check_launch("SeparableConv forward");
 }
@@ -144,12 +247,20 @@ static int sc_backward(cudaStream_t stream, const ScArgs& a, int flags) {
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     dim3 block(BX, BY, 1);
     dim3 gout((Wo + BX - 1) / BX, (Ho + BY - 1) / BY, a.B), gin((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
-    if (ow) {
-        sc_bwd_filters_kernel<true><<<gout, block, 0, stream>>>(a);
-        sc_bwd_image_kernel<true><<<gin, block, 0, stream>>>(a);
+    if (a.fs == 4) {
+        if (ow) {
+            sc_bwd_filters_kernel<true, 4><<<gout, block, 0, stream>>>(a);
+            sc_bwd_image_kernel<true, 4><<<gin, block, 0, stream>>>(a);
+        } else {
+            sc_bwd_filters_kernel<false, 4><<<gout, block, 0, stream>>>(a);
+            sc_bwd_image_kernel<false, 4><<<gin, block, 0, stream>>>(a);
+        }
+    } else if (ow) {
+        sc_bwd_filters_kernel<true, 0><<<gout, block, 0, stream>>>(a);
+        sc_bwd_image_kernel<true, 0><<<gin, block, 0, stream>>>(a);
     } else {
-        sc_bwd_filters_kernel<false><<<gout, block, 0, stream>>>(a);
-        sc_bwd_image_kernel<false><<<gin, block, 0, stream>>>(a);
+        sc_bwd_filters_kernel<false, 0><<<gout, block, 0, stream>>>(a);
+        sc_bwd_image_kernel<false, 0><<<gin, block, 0, stream>>>(a);
     }
     count_launch(2);
     return check_launch("SeparableConv backward");

@@ -30,3 +30,28 @@ elif op == "fp_fwd":
         lib.call("memc_b200_flow_projection_forward", lib.stream_ptr(flow), B, H, W, 1, S(flow), S(count), S(out),
                  P(flow), P(count), P(out), flags)
 torch.cuda.synchronize()
+if op in ("ip_bwd", "sc_bwd", "sc_fwd"):
+    H, W = 1080, 1920
+    B = 4
+    in1, flow, _, gout = synth.filter_interpolation_case(B, 3, H, W, seed=0, device="cuda")
+    st = lib.stream_ptr(in1)
+    if op == "ip_bwd":
+        g1, g2 = torch.empty_like(in1), torch.empty_like(flow)
+        for _ in range(3):
+            lib.call("memc_b200_interpolation_backward", st, B, 3, H, W, S(in1), S(flow), S(gout), S(g1), S(g2), P(in1),
+                     P(flow), P(gout), P(g1), P(g2), flags)
+    else:
+        fs = 4
+        Ho, Wo = H - fs + 1, W - fs + 1
+        v, hz = torch.randn(B, fs, Ho, Wo, device="cuda"), torch.randn(B, fs, Ho, Wo, device="cuda")
+        out = torch.empty(B, 3, Ho, Wo, device="cuda")
+        go = torch.randn_like(out)
+        g1, g2, g3 = torch.empty_like(in1), torch.empty_like(v), torch.empty_like(hz)
+        for _ in range(3):
+            if op == "sc_fwd":
+                lib.call("memc_b200_separable_conv_forward", st, B, 3, H, W, fs, S(in1), S(v), S(hz), S(out), P(in1), P(v),
+                         P(hz), P(out), flags)
+            else:
+                lib.call("memc_b200_separable_conv_backward", st, B, 3, H, W, fs, S(in1), S(v), S(hz), S(go), S(g1), S(g2),
+                         S(g3), P(in1), P(v), P(hz), P(go), P(g1), P(g2), P(g3), flags)
+    torch.cuda.synchronize()
