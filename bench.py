@@ -20,6 +20,8 @@ than the 126 MB L2, so no explicit L2 flush is needed between steps.
              inside the timed region; `roofline_fwd` is the same for the forward kernel
              (96 B/px), the north_star's >= 70 % target
   cpu_baseline  the reference's own my_lib.c (oracle/_ref) on the host cores, bounded sample
+  other_ops  (N = 1) the other ops of the path, device-timed the same way: FlowProjection (BASELINE
+             configs[2]), the C = 64 context warp of MEMC_Net_star, the fused two-warp + blend call site
 
 --impl reference times the reference's CPU implementation (oracle/_ref/libmemc_ref_cpu.so,
 else the oracle port) on the host cores for the same metric; rank 0 only.
@@ -332,6 +334,49 @@ def run_ours(args, rank, world, local_rank):
                          "mpx_s_per_gpu": px_step / t_fwd / 1e6},
     }
 
+    # ---- the other ops of the hot path (the C = 64 context warp, the fused call
+    # site), one line each: device-timed like `value`, inputs far larger than L2, rank 0 at N = 1 only
+    if rank == 0 and world == 1 and not args.no_extra:
+        def timed(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) * 1e-3 / n
+
+        def entry(name, px, bytes_px, t):
+            return {"op": name, "ms": t * 1e3, "mpx_s": px / t / 1e6, "alg_bytes_per_px": bytes_px,
+                    "gbs": px * bytes_px / t / 1e9, "frac": px * bytes_px / t / 1e9 / peak}
+
+        other = []
+        FB = 16
+        for kind, fl in (("smooth", synth.smooth_flow(FB, H, W, 6.0, seed=1, device=dev)),
+                         ("convergent (atomic-contention)", synth.radial_flow(FB, H, W, 0.9, device=dev))):
+            cnt, prj = torch.empty(FB, 1, H, W, device=dev), torch.empty_like(fl)
+            t = timed(lambda: lib.call("memc_b200_flow_projection_forward", st, FB, H, W, 1, S(fl), S(cnt), S(prj), P(fl),
+                                       P(cnt), P(prj), lib.OVERWRITE))
+            other.append(entry("FlowProjection splat + hole-fill 1920x1080, batch 16, %s flow" % kind, FB * H * W, 20, t))
+            del cnt, prj
+        c_in, c_flow, c_filt, _ = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
+        c_out = torch.empty_like(c_in)
+        t = timed(lambda: lib.call("memc_b200_filter_interpolation_forward", st, 1, 64, H, W, FS, S(c_in), S(c_flow), S(c_filt),
+                                   S(c_out), P(c_in), P(c_flow), P(c_filt), P(c_out), lib.OVERWRITE))
+        other.append(entry("FilterInterpolation forward 1920x1080, C=64 context features, batch 1", H * W, (2 * 64 + 18) * 4, t))
+        del c_in, c_flow, c_filt, c_out
+        in1b, flowb, filtb, _ = synth.filter_interpolation_case(B, C, H, W, FS, seed=7, device=dev)
+        occ = [torch.rand(B, 1, H, W, device=dev) for _ in range(2)]
+        t = timed(lambda: lib.call("memc_b200_filter_interpolation_blend_forward", st, B, C, H, W, FS, S(in1), S(flow), S(filt),
+                                   S(in1b), S(flowb), S(filtb), S(occ[0]), S(occ[1]), S(out), P(in1), P(flow), P(filt),
+                                   P(in1b), P(flowb), P(filtb), P(occ[0]), P(occ[1]), P(out), lib.OVERWRITE))
+        other.append(entry("fused FilterInterpolate (two warps + occlusion blend) 1920x1080, batch 4", B * H * W,
+                           (2 * (C + 2 + FS * FS) + 2 + C) * 4, t))
+        result["other_ops"] = other
+
     if t_gather is not None:
         result["output_allgather"] = {"ms": t_gather * 1e3, "bytes_per_rank": out.numel() * 4,
                                       "note": "NCCL all-gather of the output batch, timed alone; not part of value"}
@@ -355,6 +400,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_ops lines")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -5,11 +5,11 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/bench_under_ncu.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fi_bwd_tma -s 3 -c 1 -o $O/bench_fi_bwd -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_bwd.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ncu_bwd.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fi_fwd_patch -s 3 -c 1 -o $O/bench_fi_fwd -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_fwd.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ncu_fwd.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fp_pipeline -s 1 -c 1 -o $O/fp_pipeline -f \
     python tools/run_one.py fp_fwd 16 > $O/ncu_fp.log 2>&1
 FLOW=contention timeout 300 ncu --set full --clock-control none -k regex:fp_pipeline -s 1 -c 1 -o $O/fp_pipeline_contention -f \
