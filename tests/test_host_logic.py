@@ -69,6 +69,21 @@ def test_no_cpu_fallback(built_lib):
         FilterInterpolationModule()(z(1, 3, 8, 8), z(1, 2, 8, 8), z(1, 16, 8, 8))
     with pytest.raises(MemcB200Error):
         FlowProjectionModule(False)(z(1, 2, 8, 8))
+    from memc_b200 import fused
+    with pytest.raises(MemcB200Error):  # the fused call site has no CPU path either
+        fused.FilterInterpolate(z(1, 3, 8, 8), z(1, 3, 8, 8), [z(1, 2, 8, 8)] * 2, [z(1, 16, 8, 8)] * 2, [z(1, 1, 8, 8)] * 2, 16)
+
+
+def test_tools_do_not_touch_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may execute anything under oracle/: the development
+    tools must not (the legacy-kernel comparison lives in tests/legacy_bench.py)."""
+    import os
+    from tests.conftest import ROOT
+    tdir = os.path.join(ROOT, "tools")
+    for f in os.listdir(tdir):
+        if f.endswith((".py", ".sh")):
+            src = open(os.path.join(tdir, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src and "oracle/_ref" not in src, f
 
 
 def test_missing_library_fails_loudly(monkeypatch, built_lib):
