@@ -1087,22 +1087,27 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
         }
         // Taps outer, channels inner: gradinput3[t] is complete after its channel loop and is
         // stored at once (no 16-register accumulator array), the filter tap is read when needed.
-        float gov[C], gq[C][4], q[C][4];
+        float gov[C], q[C][4];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             gov[c] = s_gout[(c * TH + yl) * TW + xl];
-            gq[c][0] = gov[c] * (1.0f - a) * (1.0f - bt);
-            gq[c][1] = gov[c] * a * (1.0f - bt);
-            gq[c][2] = gov[c] * (1.0f - a) * bt;
-            gq[c][3] = gov[c] * a * bt;
             q[c][0] = q[c][1] = q[c][2] = q[c][3] = 0.f;
         }
-        {
-            // one window row per iteration, NOT unrolled across rows: keeps ~12 loads in flight
-            // instead of 64 and the kernel at <= 64 registers (more resident warps)
+        // top rows (j = 0, 1) feed the TL / TR quadrants, bottom rows (j = 2, 3) BL / BR: two static
+        // halves, each a two-iteration row loop that is NOT unrolled (keeps ~12 loads in flight
+        // instead of 64); only the half's own quadrant weights are live in its loop
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float wy = half ? bt : (1.0f - bt);
+            float gq[C][2];  // gradoutput x bilinear weight of the (left, right) quadrant of this half
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                gq[c][0] = gov[c] * (1.0f - a) * wy;
+                gq[c][1] = gov[c] * a * wy;
+            }
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-                const bool top = j < 2;
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * half + jj;
                 const int roff = (ly + j) * SW + lx;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1113,13 +1118,11 @@ __device__ __forceinline__ void bwd_compute_tile(const FiArgs& p, const float* s
                     for (int c = 0; c < C; ++c) {
                         const int o = roff + c * SH * SW + i;
                         const float v = s_img[o];
-                        const float gsel = top ? gq[c][h] : gq[c][2 + h];
+                        const float gsel = gq[c][h];
                         if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn(gsel * w * scale));
                         else atomicAdd(&s_acc[o], gsel * w);
                         a3 = fmaf(gsel, v, a3);
-                        const float nq = fmaf(v, w, top ? q[c][h] : q[c][2 + h]);
-                        q[c][h] = top ? nq : q[c][h];
-                        q[c][2 + h] = top ? q[c][2 + h] : nq;
+                        q[c][2 * half + h] = fmaf(v, w, q[c][2 * half + h]);
                     }
                     float* dst = g3 + (int64_t)(j * 4 + i) * p.gi3.c;
                     if (OVERWRITE) stg_stream(dst, a3);
@@ -1205,24 +1208,26 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     tma::mbar_wait(&bars[1], 0, 12);
     tma::mbar_wait(&bars[2], 0, 13);
 
-    // ---- per-tile fixed-point scale
-    float mloc = 0.f;
+    // ---- per-tile fixed-point scale.  |x| of a float orders like its bit pattern, and NaN patterns
+    // sort above +Inf, so the maxima are integer maxima of (bits & 0x7fffffff): NaN propagates.
+    unsigned mbits = 0u;
 #pragma unroll
     for (int k = 0; k < K::PPT; ++k) {
         int xl, yl;
         tile_pixel<K>(k, lane, warp, xl, yl);
         const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
         if (g.valid && x0 + xl < W && y0 + yl < H) {
-            float mg = 0.f, mw = 0.f;
+            unsigned mg = 0u, mw = 0u;
 #pragma unroll
-            for (int c = 0; c < C; ++c) mg = fmaxf_nan(mg, fabsf(s_gout[(c * TH + yl) * TW + xl]));
+            for (int c = 0; c < C; ++c) mg = max(mg, __float_as_uint(s_gout[(c * TH + yl) * TW + xl]) & 0x7fffffffu);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) mw = fmaxf_nan(mw, fabsf(s_filt[(t * TH + yl) * TW + xl]));
-            mloc = fmaxf_nan(mloc, mg * mw);
+            for (int t = 0; t < 16; ++t) mw = max(mw, __float_as_uint(s_filt[(t * TH + yl) * TW + xl]) & 0x7fffffffu);
+            // Inf * 0 = NaN is fine here: any non-finite tile takes the float path
+            mbits = max(mbits, __float_as_uint(__uint_as_float(mg) * __uint_as_float(mw)) & 0x7fffffffu);
         }
     }
-    {   // non-negative floats (and NaN, which sorts above +Inf) order like their bit patterns
-        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mloc));
+    {
+        const unsigned mb = __reduce_max_sync(0xffffffffu, mbits);
         if (lane == 0 && mb) atomicMax(s_maxbits, mb);
     }
     __syncthreads();
@@ -1248,8 +1253,12 @@ fi_bwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     // ---- flush the accumulation box: one TMA reduce-add per tile (clipped to the image by the TMA)
     __syncthreads();
     if (scale > 0.f) {  // fixed point -> fp32 in place
-        int* ai = reinterpret_cast<int*>(s_acc);
-        for (int i = tid; i < C * SH * SW; i += NT) s_acc[i] = (float)ai[i] * inv_scale;
+        int4* ai = reinterpret_cast<int4*>(s_acc);
+        float4* af = reinterpret_cast<float4*>(s_acc);
+        for (int i = tid; i < C * SH * SW / 4; i += NT) {
+            const int4 q = ai[i];
+            af[i] = make_float4((float)q.x * inv_scale, (float)q.y * inv_scale, (float)q.z * inv_scale, (float)q.w * inv_scale);
+        }
     }
     tma::fence_proxy_async();  // generic-proxy writes to s_acc -> visible to the async proxy
     __syncthreads();

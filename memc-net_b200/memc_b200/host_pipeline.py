@@ -7,6 +7,11 @@ SMs busy at once).  This is the public API bench.py's `e2e` number goes through.
 
     pipe = FilterInterpolationHostPipeline(device, streams=3)
     out, (gi1, gi2, gi3) = pipe.forward_backward(h_in1, h_flow, h_filt, h_gout, outputs=...)
+
+Back-to-back batches: `forward_backward(..., wait=False)` does not join the ring with the caller's
+stream, so the first upload of the next batch overlaps the last download of this one (a batch of B
+frames otherwise costs B + 1 transfer slots: nothing to download during the first upload, nothing
+to upload during the last download); call `pipe.join()` before reading the host results.
 """
 import torch
 
@@ -18,15 +23,24 @@ class FilterInterpolationHostPipeline(object):
         self.device = torch.device(device)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(streams)))]
         self.module = FilterInterpolationModule()
+        self._primed = False  # the ring has been ordered after the caller's stream at least once
 
     @staticmethod
     def alloc_outputs(h_in1, h_flow, h_filt):
         """Pinned host buffers for (output, gradinput1, gradinput2, gradinput3)."""
         return tuple(torch.empty_like(t, device="cpu").pin_memory() for t in (h_in1, h_in1, h_flow, h_filt))
 
-    def forward_backward(self, h_in1, h_flow, h_filt, h_gout, outputs=None):
+    def join(self):
+        """Make the caller's current stream wait for everything the ring has been given."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def forward_backward(self, h_in1, h_flow, h_filt, h_gout, outputs=None, wait=True):
         """All arguments are pinned CPU tensors [B, ...]; returns pinned CPU results.  Every frame's
-        inputs cross H2D and every frame's output + three gradients cross D2H on every call."""
+        inputs cross H2D and every frame's output + three gradients cross D2H on every call.
+        wait=False: the caller must not touch the host buffers of this batch until `join()` +
+        a synchronisation of its stream (frames of consecutive batches keep their stream order)."""
         for t in (h_in1, h_flow, h_filt, h_gout):
             if t.is_cuda or not t.is_pinned():
                 raise ValueError("host pipeline expects pinned CPU tensors")
@@ -35,8 +49,10 @@ class FilterInterpolationHostPipeline(object):
         h_out, h_g1, h_g2, h_g3 = outputs
         B = h_in1.size(0)
         cur = torch.cuda.current_stream(self.device)
-        for s in self.streams:
-            s.wait_stream(cur)
+        if wait or not self._primed:
+            for s in self.streams:
+                s.wait_stream(cur)
+            self._primed = True
         for b in range(B):
             s = self.streams[b % len(self.streams)]
             with torch.cuda.stream(s):
@@ -50,6 +66,6 @@ class FilterInterpolationHostPipeline(object):
                 h_g1[b:b + 1].copy_(g1, non_blocking=True)
                 h_g2[b:b + 1].copy_(g2, non_blocking=True)
                 h_g3[b:b + 1].copy_(g3, non_blocking=True)
-        for s in self.streams:
-            cur.wait_stream(s)
+        if wait:
+            self.join()
         return h_out, (h_g1, h_g2, h_g3)

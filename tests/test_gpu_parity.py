@@ -243,6 +243,18 @@ def test_host_pipeline_matches_direct_call(L):
     assert float((h1 - g1.cpu()).abs().max()) <= 1e-5 and torch.equal(h2, g2.cpu()) and torch.equal(h3, g3.cpu())
     with pytest.raises(ValueError):
         pipe.forward_backward(t[0], hs[1], hs[2], hs[3])   # device tensor where a pinned host tensor is expected
+    # back-to-back batches without joining in between (wait=False): distinct output buffers per batch
+    t2 = synth.filter_interpolation_case(B, C, H, W, seed=22, device="cuda")
+    hs2 = [x.cpu().pin_memory() for x in t2]
+    o1 = pipe.alloc_outputs(hs[0], hs[1], hs[2])
+    o2 = pipe.alloc_outputs(hs[0], hs[1], hs[2])
+    pipe.forward_backward(*hs, outputs=o1, wait=False)
+    pipe.forward_backward(*hs2, outputs=o2, wait=False)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert torch.equal(o1[0], h_out) and torch.equal(o1[2], h2) and torch.equal(o1[3], h3)
+    o = FilterInterpolationModule()(t2[0], t2[1], t2[2])
+    assert torch.equal(o2[0], o.cpu())
 
 
 def test_filter_interpolation_backward_float_accum_flag(L):
