@@ -54,6 +54,7 @@ FI_SHAPES = [  # B, C, H, W, fs, sigma
     (1, 2, 16, 16, 2, 1.0), (1, 3, 24, 24, 6, 40.0), (1, 64, 16, 24, 4, 2.0), (1, 1, 1, 1, 4, 0.0),
     (2, 3, 96, 128, 4, 4.0), (1, 3, 128, 256, 4, 20.0), (1, 64, 64, 128, 4, 3.0), (1, 3, 70, 260, 4, 1.0),
     (2, 3, 37, 100, 4, 2.0), (1, 4, 50, 196, 4, 6.0), (1, 1, 33, 96, 4, 1.5), (1, 2, 130, 132, 4, 60.0),
+    (2, 6, 40, 100, 4, 3.0), (1, 9, 70, 132, 4, 12.0),   # C > 4: channel-chunked forward (last chunk ragged)
 ]
 
 
@@ -276,7 +277,9 @@ def test_filter_interpolation_backward_float_accum_flag(L):
     torch.cuda.synchronize()
     ref = res["generic"]
     small = ref.abs() < 1e-3                      # cells that only received tiny contributions
-    rel = lambda a: float(((a - ref).abs() / ref.abs().clamp_min(1e-12))[small & (ref != 0)].max())
+    # relative error with a 1e-10 absolute floor: the tiny contributions are ~1e-5, so fp32 summation-order noise
+    # is ~1e-12 while the fixed point's quantum here is ~1e-4 -- cells whose tiny terms cancel cannot flake the test
+    rel = lambda a: float((((a - ref).abs() - 1e-10).clamp_min(0) / ref.abs().clamp_min(1e-12))[small & (ref != 0)].max())
     assert float((res["fixed"] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())   # absolute bound holds
     assert rel(res["float"]) < 1e-3                                                     # relative precision kept
     assert float((res["float"] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
