@@ -188,6 +188,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     lib.load()
     distributed = world > 1
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if distributed and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
 
