@@ -75,12 +75,7 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View 
 // right / bottom image border (R == L or Bm == T) do not follow the box pattern: they go straight
 // to global memory, as do sources whose corner cell misses the staged box.
 //
-// CORNER = true (persistent pipeline): the destination planes hold the corner histogram itself;
-// the box is dumped as it is, out-of-box sources add their one corner cell, and the 2x2 filter
-// (with the border repeats) is applied by the averaging pass.
-//
 // Precondition: a __syncthreads() separates this call from the CTA's previous use of `s`.
-template <bool CORNER>
 __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], const float (&fy)[PPT], int x0, int y0,
                                            float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -155,14 +150,6 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
             atomicAdd(&s.box[1][uy][ux], __float2int_rn(-fy[k] * scale));
             atomicAdd(&s.box[2][uy][ux], 1);
         }
-        if (CORNER) {
-            if (__builtin_expect(!in_box, 0)) {
-                red_add(ox + (int64_t)T[k] * out_h + L[k], -fx[k]);
-                red_add(oy + (int64_t)T[k] * out_h + L[k], -fy[k]);
-                red_add(cn + (int64_t)T[k] * cnt_h + L[k], 1.0f);
-            }
-            continue;
-        }
         const bool last_col = L[k] == W - 1, last_row = T[k] == H - 1;
         if (__builtin_expect(!in_box || last_col || last_row, 0)) {
             const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
@@ -182,37 +169,31 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
     __syncthreads();
     // ---- flush the touched corner cells: four cells per 128-bit vector reduction
     // (REDG.E.ADD.F32x4), all-zero vectors skipped; a warp walks rows, its lanes the vectors of a
-    // row.  !CORNER: the 2x2 box filter is applied on the way out; output cells beyond the image
+    // row.  The 2x2 box filter is applied on the way out; output cells beyond the image
     // are dropped (their taps were sent directly above).
     {
         const int ax0 = max(s.bb[0], bx) - bx, ax1 = min(s.bb[1], bx + SW - 1) - bx;
         const int ay0 = max(s.bb[2], by) - by, ay1 = min(s.bb[3], by + SH - 1) - by;
         if (ax0 <= ax1 && ay0 <= ay1) {
-            const int cx1 = CORNER ? ax1 : min(ax1 + 1, W - 1 - bx), cy1 = CORNER ? ay1 : min(ay1 + 1, H - 1 - by);
+            const int cx1 = min(ax1 + 1, W - 1 - bx), cy1 = min(ay1 + 1, H - 1 - by);
             const int v0 = ax0 >> 2, v1 = cx1 >> 2;  // vector columns (ux = 4 v <= SW)
             for (int uy = ay0 + (tid >> 5); uy <= cy1; uy += NT / 32)
                 for (int v = v0 + lane; v <= v1; v += 32) {
                     const int ux = v << 2;
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
-                        int q[4];
-                        if (CORNER) {
-                            const int4 t = *reinterpret_cast<const int4*>(&s.box[pl][uy][ux]);
-                            q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
-                        } else {
-                            int a[2][5];
+                        int q[4], a[2][5];
 #pragma unroll
-                            for (int rr = 0; rr < 2; ++rr) {
-                                const int yy = uy - 1 + rr;
-                                const bool row_ok = (unsigned)yy < (unsigned)SH;
-                                a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
-                                int4 t = make_int4(0, 0, 0, 0);
-                                if (row_ok && ux < SW) t = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
-                                a[rr][1] = t.x; a[rr][2] = t.y; a[rr][3] = t.z; a[rr][4] = t.w;
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int yy = uy - 1 + rr;
+                            const bool row_ok = (unsigned)yy < (unsigned)SH;
+                            a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
+                            int4 t = make_int4(0, 0, 0, 0);
+                            if (row_ok && ux < SW) t = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
+                            a[rr][1] = t.x; a[rr][2] = t.y; a[rr][3] = t.z; a[rr][4] = t.w;
                         }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
                         if ((q[0] | q[1] | q[2] | q[3]) == 0) continue;
                         const float sc = pl == 2 ? 1.0f : inv_scale;
                         const float4 val = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
@@ -236,7 +217,7 @@ __global__ void __launch_bounds__(NT, 4) fp_splat_kernel(const FpArgs p, const i
     float fx[PPT], fy[PPT];
     load_flow(p.flowp, p.flow, x0, y0, b, p.W, p.H, fx, fy);
     float* ox = p.outp + (int64_t)b * p.out.b;
-    splat_tile<false>(s, fx, fy, x0, y0, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b, p.out.h, p.count.h, p.W, p.H);
+    splat_tile(s, fx, fy, x0, y0, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b, p.out.h, p.count.h, p.W, p.H);
 }
 
 // average + occupancy bit masks.  One CTA = one 128 x 32 pixel block:
@@ -656,7 +637,7 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
         if (it.type == 0) {
             if (!(p.dbg & 1)) {
                 float* acc = p.scratch + (int64_t)(it.frame % 3) * 3 * plane;
-                splat_tile<false>(s, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W, p.H);
+                splat_tile(s, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W, p.H);
             }
         } else if (it.type == 1) {
             if (!(p.dbg & 2)) pipe_average_tile(p, rw, it.tile, it.frame);
