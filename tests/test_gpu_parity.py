@@ -187,8 +187,8 @@ def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape, monkeyp
     order as the generic kernel, so the two must agree bit for bit (forward)."""
     from memc_b200 import synth
     B, C, H, W, sigma = shape
-    if C > 4:  # the channel-chunked variant is opt-in
-        monkeypatch.setenv("MEMC_FI_FWD_CFG", "30")
+    if C == 7:  # C > 4 takes the channel-chunked kernel (8x4 patches); also cover its row-segment configuration
+        monkeypatch.setenv("MEMC_FI_FWD_CFG", "31")
     t1, t2, t3, _ = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=9, device="cuda")
     outs = []
     for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
