@@ -5,11 +5,18 @@ paths NEXT TO the unchanged `my_package` API.
         = occlusion[0] * FilterInterpolationModule()(ref0, offset[0], filter[0])
         + occlusion[1] * FilterInterpolationModule()(ref2, offset[1], filter[1])
 
-is the static method of the same name in networks/MEMC_Net.py:258-264 and
+    FlowProjectPair(flow_a, flow_b)
+        = (FlowProject(flow_a), FlowProject(flow_b))     the bidirectional pair of networks/MEMC_Net.py:109-113
+
+`FilterInterpolate` is the static method of the same name in networks/MEMC_Net.py:258-264 and
 networks/MEMC_Net_star.py:272-278 (their sixth argument `filter_size2` is unused there and optional
 here), so a network can rebind it:  `MEMC_Net.FilterInterpolate = staticmethod(fused.FilterInterpolate)`.
 
-Forward: one kernel warps both references and blends them in registers
+`FlowProjectPair` runs both directions as ONE FlowProjection call on the concatenated batch (frames are
+independent, so each half equals the separate call; with 2 x B >= 3 frames the persistent pipeline has twice the
+frames to overlap), and returns the two halves as views.
+
+`FilterInterpolate` forward: one kernel warps both references and blends them in registers
 (memc_b200_filter_interpolation_blend_forward), bit-identical to the composition.  Backward: composed
 from the plain ops (FilterInterpolation backward per reference; the two warps are recomputed for the
 occlusion gradients), so training code keeps working.  CUDA only: like every op of this package it
@@ -84,3 +91,15 @@ class _FilterInterpolateBlend(Function):
 def FilterInterpolate(ref0, ref2, offset, filter, occlusion, filter_size2=None):  # noqa: A002 (reference's names)
     """Drop-in for the networks' static method (networks/MEMC_Net.py:258-264)."""
     return _FilterInterpolateBlend.apply(ref0, offset[0], filter[0], occlusion[0], ref2, offset[1], filter[1], occlusion[1])
+
+
+def FlowProjectPair(flow_a, flow_b, requires_grad=None):
+    """(FlowProject(flow_a), FlowProject(flow_b)) of networks/MEMC_Net.py:109-113, 252-256 in one call.
+    fill-hole follows the reference rule (on iff the inputs do not require grad, FlowProjectionLayer.py:15)."""
+    from my_package.functions.FlowProjectionLayer import FlowProjectionLayer
+    if flow_a.shape != flow_b.shape:
+        raise _lib.MemcB200Error("FlowProjectPair: shapes differ %s %s" % (tuple(flow_a.shape), tuple(flow_b.shape)))
+    rg = (flow_a.requires_grad or flow_b.requires_grad) if requires_grad is None else requires_grad
+    both = FlowProjectionLayer(rg)(torch.cat((_lib.check_tensor(flow_a, "flow_a"), _lib.check_tensor(flow_b, "flow_b")), dim=0))
+    B = flow_a.size(0)
+    return both[:B], both[B:]

@@ -372,6 +372,26 @@ def test_fused_filter_interpolate_equals_composition(L, shape):
         close(a, host(b), tol=2e-5, what="fused grad " + name)
 
 
+@pytest.mark.parametrize("B", [1, 3])
+def test_fused_flow_project_pair_equals_two_calls(L, B):
+    """memc_b200.fused.FlowProjectPair == two FlowProjectionModule calls (networks/MEMC_Net.py:109-113): counts
+    equal, outputs equal up to the fp32 summation order, gradients flow to both inputs."""
+    from memc_b200 import fused, synth
+    from my_package.modules.FlowProjectionModule import FlowProjectionModule
+    H, W = 96, 160
+    fa, fb = synth.smooth_flow(B, H, W, 5.0, seed=1, device="cuda"), synth.tear_flow(B, H, W, 8.0, seed=2, device="cuda")
+    with torch.no_grad():
+        pa, pb = fused.FlowProjectPair(fa, fb)
+        qa, qb = FlowProjectionModule(False)(fa), FlowProjectionModule(False)(fb)
+    close(pa, host(qa), what="pair a"), close(pb, host(qb), what="pair b")
+    ga, gb = fa.clone().requires_grad_(), fb.clone().requires_grad_()
+    pa, pb = fused.FlowProjectPair(ga, gb)
+    (pa.sum() + 2.0 * pb.sum()).backward()
+    ha, hb = fa.clone().requires_grad_(), fb.clone().requires_grad_()
+    (FlowProjectionModule(True)(ha).sum() + 2.0 * FlowProjectionModule(True)(hb).sum()).backward()
+    close(ga.grad, host(ha.grad), what="pair grad a"), close(gb.grad, host(hb.grad), what="pair grad b")
+
+
 # ------------------------------------------------------------------------ FlowProjection
 FP_SHAPES = [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0), (2, 96, 160, 6.0), (1, 70, 260, 1.0)]
 
