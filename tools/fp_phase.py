@@ -1,5 +1,5 @@
 """FlowProjection pipeline phase timing (development): MEMC_FP_DBG skips phases (results invalid)."""
-import os, sys, json
+import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "memc-net_b200")):
