@@ -160,3 +160,35 @@ def test_python_loop_flow_projection_small():
     out, count = cpu.flow_projection_forward(flow, fillhole=1)
     pout, pcount = pyloop.flow_projection_forward(flow, fillhole=1)
     assert np.array_equal(count, pcount) and np.array_equal(out, pout)
+
+
+def test_flow_projection_is_a_box_filter_of_the_corner_histogram():
+    """The identity the fast FlowProjection kernels rest on (flow_projection_fast.cu): every valid source adds the
+    SAME value to the cells (L..R) x (T..Bm), R = min(L+1, W-1), Bm = min(T+1, H-1) (my_lib.c:1491-1524), so the
+    splat equals a 2x2 box filter of the corner histogram A[T][L] += value, with the last column / row of A counted
+    twice where the clamp repeats a cell.  Checked against the oracle incl. targets on the right / bottom border."""
+    B, H, W = 2, 19, 27
+    rng = _rng(5)
+    flow = (rng.standard_normal((B, 2, H, W)) * 4).astype(np.float32)
+    flow[0, 0, :, -1] = 0.0                       # x2 == W-1 exactly: L == R
+    flow[1, 1, -1, :] = 0.0                       # y2 == H-1 exactly: T == Bm
+    out, count = cpu.flow_projection_forward(flow, 0, "f64")
+    for b in range(B):
+        ys, xs = np.mgrid[0:H, 0:W]
+        x2 = (xs.astype(np.float32) + flow[b, 0]).astype(np.float32)
+        y2 = (ys.astype(np.float32) + flow[b, 1]).astype(np.float32)
+        valid = (x2 >= 0) & (y2 >= 0) & (x2 <= W - 1) & (y2 <= H - 1)
+        L, T = x2[valid].astype(np.int64), y2[valid].astype(np.int64)
+        A = np.zeros((3, H, W))
+        np.add.at(A[0], (T, L), -flow[b, 0][valid].astype(np.float64))
+        np.add.at(A[1], (T, L), -flow[b, 1][valid].astype(np.float64))
+        np.add.at(A[2], (T, L), 1.0)
+        wx = np.ones(W); wx[-1] = 2.0             # a corner in the last column hits its own cell twice
+        wy = np.ones(H); wy[-1] = 2.0
+        Aw = A * wx[None, None, :]
+        hsum = Aw.copy(); hsum[:, :, 1:] += A[:, :, :-1]          # cell x <- A[x] (* wx) + A[x-1]
+        cells = hsum * wy[None, :, None]
+        cells[:, 1:, :] += hsum[:, :-1, :]                          # cell y <- h[y] (* wy) + h[y-1]
+        assert np.array_equal(cells[2], count[b, 0].astype(np.float64))
+        avg = np.where(cells[2] > 0, cells[:2] / np.maximum(cells[2], 1), 0.0)
+        assert np.abs(avg - out[b]).max() <= 1e-9
