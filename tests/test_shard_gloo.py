@@ -71,6 +71,54 @@ def test_shard_and_gather_world2(batch):
     assert dict(ret) == {0: 1, 1: 1}
 
 
+def _video_worker(rank, world, port, path, h, w, n, ret):
+    """Each rank interpolates ITS share of the frame pairs of one YUV clip (memc_b200.video); the mid frames
+    are gathered as tensors and rank 0 checks them against the single-process run."""
+    import numpy as np
+    from memc_b200 import video
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = lambda x: 0.25 * x[0] + 0.75 * x[1]               # stand-in for the network (frames independent)
+        rd = video.YUV420Reader(path, h, w)
+        pairs = video.frame_pairs(n, 2)
+        mine = video.shard_pairs(pairs, rank, world)
+        mids = [m for _, _, m in video.interpolate_pairs(model, rd.read, mine, "cpu")]
+        local = torch.from_numpy(np.stack(mids)) if mids else torch.empty(0, h, w, 3, dtype=torch.uint8)
+        full = shard.gather_frames(local, len(pairs))
+        if rank == 0:
+            ref = [m for _, _, m in video.interpolate_pairs(model, rd.read, pairs, "cpu")]
+            assert torch.equal(full, torch.from_numpy(np.stack(ref)))
+        rd.close()
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_video_driver_world2(tmp_path):
+    import numpy as np
+    from memc_b200 import video
+    h, w, n = 32, 48, 9
+    rng = np.random.default_rng(3)
+    path = str(tmp_path / "clip.yuv")
+    wr = video.YUV420Writer(path)
+    for _ in range(n):
+        wr.write(rng.integers(64, 192, size=(h, w, 3), dtype=np.uint8))
+    wr.close()
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_video_worker, args=(r, world, port, path, h, w, n, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: 1, 1: 1}
+
+
 def test_compat_shim_makes_reference_networks_importable(built_lib):
     """With the shim, the reference's own networks/MEMC_Net*.py import OUR my_package unchanged
     (skipped where the reference tree is absent, e.g. on the GPU box)."""
