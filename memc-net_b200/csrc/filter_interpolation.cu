@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(BX* BY) fi_bwd_direct_kernel(const FiArgs p) {
     stg_stream(g2 + p.gi2.c, dy);
 }
 
-static int fi_forward(cudaStream_t stream, const FiArgs& a, int flags) {
+static int fi_forward(cudaStream_t stream, const FiArgs& a_in, int flags) {
+    FiArgs a = a_in;
+    a.flags = flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     if (a.fs <= 0) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {

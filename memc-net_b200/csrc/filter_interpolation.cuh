@@ -17,8 +17,6 @@ struct FiArgs {
     float* gi2p;
     float* gi3p;
     int flags;            // MEMC_B200_* flags of the call
-    int dbg;              // development switches (MEMC_TMA_DBG), 0 in production
-    long long* prof;      // development: per-CTA phase timestamps (MEMC_TMA_DBG & 64), else null
 };
 
 // fast path (filter_interpolation_tma.cu): returns 1 if it took the call, 0 if its layout

@@ -28,7 +28,6 @@
 // down to a multiple of 4 pixels.
 #include "filter_interpolation.cuh"
 #include "tma_utils.cuh"
-#include <stdlib.h>
 
 namespace memc {
 
@@ -118,43 +117,6 @@ __device__ __forceinline__ bool tile_box(const float* s_flow, int* s_bb, int x0,
     bx = max(0, min(bx, W - K::SW)) & ~3;  // W >= SW and W % 4 == 0 are launch preconditions
     by = max(0, min(by, H - K::SH));       // H >= SH is a launch precondition
     return any_valid;
-}
-
-// development-only phase timestamps (thread 0 of the first 256 CTAs, first 8 tiles each)
-__device__ __forceinline__ void prof_mark(const FiArgs& p, int tile_i, int k) {
-    if (p.prof && threadIdx.x == 0 && blockIdx.x < 256 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0 && tile_i < 8)
-        p.prof[((long long)blockIdx.x * 8 + tile_i) * 6 + k] = clock64();
-}
-
-// Same bounding box computed by ONE warp (each lane walks TW*TH/32 pixels): no block barrier and
-// no shared atomics between the flow tile landing and the image TMA being issued.
-template <class K>
-__device__ __forceinline__ void tile_box_warp(const float* s_flow, int x0, int y0, int W, int H, int lane, int& bx,
-                                              int& by) {
-    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
-#pragma unroll
-    for (int k = 0; k < K::TW * K::TH / 32; ++k) {
-        const int idx = k * 32 + lane;
-        const int yl = idx / K::TW, xl = idx % K::TW;
-        const FiGeom g = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * K::TW + xl], s_flow[(K::TH + yl) * K::TW + xl]);
-        if (g.valid && x0 + xl < W && y0 + yl < H) {
-            mnx = min(mnx, g.ix); mxx = max(mxx, g.ix);
-            mny = min(mny, g.iy); mxy = max(mxy, g.iy);
-        }
-    }
-    mnx = warp_min(mnx); mxx = warp_max(mxx); mny = warp_min(mny); mxy = warp_max(mxy);
-    if (mnx > mxx) {  // nothing valid: any legal origin
-        bx = 0;
-        by = 0;
-        return;
-    }
-    bx = mnx - 1;
-    by = mny - 1;
-    const int need_w = mxx - mnx + 4 + 3, need_h = mxy - mny + 4;
-    if (need_w > K::SW) bx += (need_w - K::SW) / 2;
-    if (need_h > K::SH) by += (need_h - K::SH) / 2;
-    bx = max(0, min(bx, W - K::SW)) & ~3;
-    by = max(0, min(by, H - K::SH));
 }
 
 // ====================================================================================
@@ -306,7 +268,6 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
         tma::fence_barrier_init();
     }
     __syncthreads();
-    prof_mark(p, 0, 0);
     if (tid == 0) {
         tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
         tma::load_4d(sm + lay.off_flow, &m_flow, x0, y0, 0, b, &bars[0]);
@@ -315,22 +276,16 @@ fi_fwd_tma_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_const
     }
 
     tma::mbar_wait(&bars[0], 0, 1);
-    prof_mark(p, 0, 1);
     int bx, by;
     const bool any_valid = tile_box<K>(s_flow, s_bb, x0, y0, W, H, lane, warp, bx, by);
-    prof_mark(p, 0, 2);
-    const bool skip_img = (p.dbg & 4) != 0;  // development switch: serve every tap from global
-    if (skip_img) { bx = -100000; by = -100000; }
-    if (tid == 0 && any_valid && !skip_img) {
+    if (tid == 0 && any_valid) {
         tma::mbar_expect_tx(&bars[2], C * SH * SW * 4);
         tma::load_4d(sm + lay.off_img, &m_img, bx, by, 0, b, &bars[2]);
     }
     tma::mbar_wait(&bars[1], 0, 2);
-    if (any_valid && !skip_img) tma::mbar_wait(&bars[2], 0, 3);
-    prof_mark(p, 0, 3);
+    if (any_valid) tma::mbar_wait(&bars[2], 0, 3);
 
     fwd_compute_tile<C, K>(p, s_filt, s_flow, s_img, x0, y0, b, bx, by, lane, warp);
-    prof_mark(p, 0, 4);
 }
 
 bool make_maps(const FiArgs& a, bool bwd, int TW, int TH, int SW, int SH, CUtensorMap* m);  // m[5]
@@ -789,145 +744,6 @@ int launch_fwd_patch(cudaStream_t stream, const FiArgs& a) {
     return check_launch("FilterInterpolation forward (TMA, 8x4 patches)") == 0 ? 1 : -1;
 }
 
-// ------------------------------------------------------------------------------------
-// forward, WARP-SPECIALISED persistent ring.  The one-tile-per-CTA kernel spends 60 % of a CTA's
-// life waiting (flow TMA -> bounding box -> image TMA; profiles/r01_fi_fwd_phase_timeline.txt) and
-// its shared-memory data pipe idles a third of the time.  Here a CTA keeps walking tiles
-// blockIdx.x, +grid, ... and splits its warps by role:
-//
-//   producer warp   waits for a free ring slot, issues the filter-tile TMA, computes the tile's
-//                   bounding box from the (long since landed) flow tile with its 32 lanes, issues
-//                   the data-dependent image-box TMA, prefetches a later flow tile
-//   consumer warps  wait for "slot full", compute their pixels of the tile exactly like the
-//                   one-tile kernel (fwd_compute_tile), hand the slot back -- no block-wide barrier
-//
-// Slots: NS x (filter tile + image box), NFS x flow tile (small: prefetched further ahead).
-// The chain  release(i-NS) -> filter(i) + image(i) landed  has NS-1 tile-compute times of slack.
-// ------------------------------------------------------------------------------------
-template <class K, int C, int NS, int NFS>
-struct WsLayout {
-    static constexpr int FILT_B = 16 * K::TH * K::TW * 4, FLOW_B = 2 * K::TH * K::TW * 4, IMG_B = C * K::SH * K::SW * 4;
-    static constexpr int OFF_FILT = 0, OFF_IMG = NS * FILT_B, OFF_FLOW = OFF_IMG + NS * IMG_B;
-    static constexpr int OFF_BAR = OFF_FLOW + NFS * FLOW_B;  // full_flow[NFS], full_filt[NS], full_img[NS], empty[NS]
-    static constexpr int OFF_BOX = OFF_BAR + (NFS + 3 * NS) * 8;
-    static constexpr int TOTAL = OFF_BOX + NS * 8;
-    static_assert(FILT_B % 128 == 0 && FLOW_B % 128 == 0 && IMG_B % 128 == 0, "TMA destinations are 128-byte aligned");
-};
-
-template <int C, class K, int NS, int NFS>
-__global__ void __launch_bounds__(K::NT + 32, K::MINB)
-fi_fwd_ws_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                 const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p, const int tiles_x,
-                 const int tiles_y, const int n_tiles) {
-    using L = WsLayout<K, C, NS, NFS>;
-    constexpr int NCW = K::NT / 32;  // consumer warps; warp NCW is the producer
-    constexpr int LF = NFS - NS;     // flow look-ahead (tiles)
-    static_assert(LF >= 1, "flow ring must be deeper than the data ring");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    uint64_t* full_flow = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
-    uint64_t* full_filt = full_flow + NFS;
-    uint64_t* full_img = full_filt + NS;
-    uint64_t* empty = full_img + NS;
-    volatile int* s_box = reinterpret_cast<volatile int*>(sm + L::OFF_BOX);  // [NS][2]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    const int n = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-    const int W = p.W, H = p.H;
-    const int per_frame = tiles_x * tiles_y;
-    auto tile_origin = [&](int i, int& x0, int& y0, int& b) {
-        const int t = (int)blockIdx.x + i * G;
-        b = t / per_frame;
-        const int r = t - b * per_frame;
-        const int ty = r / tiles_x;
-        x0 = (r - ty * tiles_x) * K::TW;
-        y0 = ty * K::TH;
-    };
-
-    if (tid == 0) {
-        for (int k = 0; k < NFS; ++k) tma::mbar_init(&full_flow[k], 1);
-        for (int k = 0; k < NS; ++k) {
-            tma::mbar_init(&full_filt[k], 1);
-            tma::mbar_init(&full_img[k], 1);
-            tma::mbar_init(&empty[k], NCW);
-        }
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (n == 0) return;
-
-    if (warp == NCW) {
-        // ================================ producer ================================
-        auto issue_flow = [&](int i) {  // lane 0
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            tma::mbar_expect_tx(&full_flow[i % NFS], L::FLOW_B);
-            tma::load_4d(sm + L::OFF_FLOW + (i % NFS) * L::FLOW_B, &m_flow, x0, y0, 0, b, &full_flow[i % NFS]);
-        };
-        if (lane == 0)
-            for (int i = 0; i < LF && i < n; ++i) issue_flow(i);
-        for (int i = 0; i < n; ++i) {
-            const int s = i % NS, fsl = i % NFS;
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            // bounding box first: it only needs the flow tile, not the slot
-            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 61);
-            int bx, by;
-            tile_box_warp<K>(reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B), x0, y0, W, H, lane, bx, by);
-            if (i >= NS) tma::mbar_wait(&empty[s], ((i / NS) - 1) & 1, 62);  // tile i-NS released the slot
-            if (lane == 0) {
-                tma::mbar_expect_tx(&full_filt[s], L::FILT_B);
-                tma::load_4d(sm + L::OFF_FILT + s * L::FILT_B, &m_filt, x0, y0, 0, b, &full_filt[s]);
-                s_box[2 * s] = bx;
-                s_box[2 * s + 1] = by;
-                tma::mbar_expect_tx(&full_img[s], L::IMG_B);  // release: publishes s_box to the waiters
-                tma::load_4d(sm + L::OFF_IMG + s * L::IMG_B, &m_img, bx, by, 0, b, &full_img[s]);
-                // flow slot (i+LF) % NFS was last read for tile i+LF-NFS = i-NS: released above
-                if (i + LF < n) issue_flow(i + LF);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ================================ consumers ================================
-        for (int i = 0; i < n; ++i) {
-            const int s = i % NS, fsl = i % NFS;
-            int x0, y0, b;
-            tile_origin(i, x0, y0, b);
-            tma::mbar_wait(&full_flow[fsl], (i / NFS) & 1, 63);
-            tma::mbar_wait(&full_filt[s], (i / NS) & 1, 64);
-            tma::mbar_wait(&full_img[s], (i / NS) & 1, 65);
-            const int bx = s_box[2 * s], by = s_box[2 * s + 1];
-            fwd_compute_tile<C, K>(p, reinterpret_cast<const float*>(sm + L::OFF_FILT + s * L::FILT_B),
-                                   reinterpret_cast<const float*>(sm + L::OFF_FLOW + fsl * L::FLOW_B),
-                                   reinterpret_cast<const float*>(sm + L::OFF_IMG + s * L::IMG_B), x0, y0, b, bx, by, lane,
-                                   warp);
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(&empty[s]);
-        }
-    }
-}
-
-template <int C, class K, int NS, int NFS>
-int launch_fwd_ws(cudaStream_t stream, const FiArgs& a) {
-    if (a.W < K::SW || a.H < K::SH) return 0;
-    CUtensorMap m[5];
-    if (!make_maps(a, false, K::TW, K::TH, K::SW, K::SH, m)) return 0;
-    constexpr size_t smem = (size_t)WsLayout<K, C, NS, NFS>::TOTAL + 128;
-    if (!ensure_dynamic_smem(fi_fwd_ws_kernel<C, K, NS, NFS>, smem)) return 0;
-    int dev = 0, n_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) return 0;
-    const int tiles_x = (a.W + K::TW - 1) / K::TW, tiles_y = (a.H + K::TH - 1) / K::TH;
-    const long long n_tiles = (long long)tiles_x * tiles_y * a.B;
-    if (n_tiles > 0x7fffffffLL) return 0;
-    const int grid = (int)(n_tiles < (long long)n_sm * K::MINB ? n_tiles : (long long)n_sm * K::MINB);
-    fi_fwd_ws_kernel<C, K, NS, NFS><<<grid, K::NT + 32, smem, stream>>>(m[0], m[1], m[2], a, tiles_x, tiles_y, (int)n_tiles);
-    count_launch();
-    return check_launch("FilterInterpolation forward (warp-specialised TMA ring)") == 0 ? 1 : -1;
-}
-
 // ====================================================================================
 // backward
 // ====================================================================================
@@ -1319,88 +1135,32 @@ int launch_bwd(cudaStream_t stream, const FiArgs& a) {
     return check_launch("FilterInterpolation backward (TMA)") == 0 ? 1 : -1;
 }
 
-// tile configurations.  *_DEFAULT is what production uses; the others are selectable with
-// MEMC_FI_FWD_CFG / MEMC_FI_BWD_CFG (C == 3 only) for tools/kbench.py sweeps.
+// tile configurations (sweeps: profiles/r01_fi_tile_sweep.md)
 //                  TW  TH  SW  SH   NT  MINB
-using FwdE = Cfg<32, 8, 64, 24, 128, 5>;   //  37 KB: 5 CTAs / SM
-using FwdE6 = Cfg<32, 8, 64, 24, 128, 6>;  //  same, registers capped at 80: 6 CTAs / SM
-using FwdK2 = Cfg<32, 16, 64, 32, 256, 2>;  // channel-chunked,  102 KB: 2 CTAs / SM
+using FwdE6 = Cfg<32, 8, 64, 24, 128, 6>;         // row segments, 37 KB, registers capped at 80: 6 CTAs / SM
 using FwdK3 = Cfg<32, 16, 72, 32, 256, 2, true>;  // channel-chunked, 8x4 patches, box pitch 72: 110 KB
-using FwdW1 = Cfg<32, 8, 64, 24, 256, 2>;   // warp-specialised ring: 8 consumer warps, 1 px / thread
-using FWD_DEFAULT = FwdE6;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
-using BwdA = Cfg<32, 8, 64, 24, 256, 3>;   //  58 KB: 3 CTAs / SM, 1 px / thread
-using BwdC = Cfg<32, 16, 64, 32, 256, 2>;  //  91 KB: 2 CTAs / SM
-using BwdE = Cfg<32, 8, 64, 32, 256, 3>;   //  70 KB: 3 CTAs / SM, taller box
-using BwdF = Cfg<32, 8, 64, 28, 256, 3>;   //  64 KB
-using BWD_DEFAULT = BwdF;  // best of the sweep (profiles/r01_fi_tile_sweep.md)
-
-int env_int(const char* name) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : 0;
-}
+using FWD_DEFAULT = FwdE6;
+using BwdF = Cfg<32, 8, 64, 28, 256, 3>;          // 64 KB: 3 CTAs / SM, 1 px / thread
+using BWD_DEFAULT = BwdF;
 
 }  // namespace
 
-// development: phase timeline of the forward kernels (MEMC_TMA_DBG & 64); prints cycle averages
-static void prof_report(cudaStream_t stream, long long* dev) {
-    cudaStreamSynchronize(stream);
-    static long long host[256 * 8 * 6];
-    cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
-    const char* names[5] = {"start->flow landed", "bbox", "->filter+image landed", "compute", "(next tile start)"};
-    for (int t = 0; t < 8; ++t) {
-        double sum[5] = {0, 0, 0, 0, 0};
-        int n = 0;
-        for (int c = 0; c < 256; ++c) {
-            const long long* e = host + (c * 8 + t) * 6;
-            if (!e[0] || !e[4]) continue;
-            for (int k = 0; k < 4; ++k) sum[k] += (double)(e[k + 1] - e[k]);
-            if (t + 1 < 8 && e[6]) sum[4] += (double)(e[6] - e[4]);
-            ++n;
-        }
-        if (!n) continue;
-        fprintf(stderr, "memc_b200 prof tile#%d (n=%d):", t, n);
-        for (int k = 0; k < 5; ++k) fprintf(stderr, "  %s %.0f cyc", names[k], sum[k] / n);
-        fprintf(stderr, "\n");
-    }
-}
+int fi_backward_rows(cudaStream_t stream, const FiArgs& a, bool overwrite);  // filter_interpolation_bwd_rows.cu
 
-int fi_forward_fast(cudaStream_t stream, const FiArgs& a_in) {
-    FiArgs a = a_in;
-    a.dbg = env_int("MEMC_TMA_DBG");
-    if (a.fs == 4 && a.C > CB && a.W % 4 == 0 && a.B <= 65535) {
-        // C > 4 (64-channel context warps): channel-chunked TMA variant, 8x4 patches.  0.88 ms per
-        // 1080p frame at C = 64 vs 1.11 ms for the generic kernel: both are bound by the 16*C
-        // shared / L1 gather wavefronts per pixel, not by HBM (profiles/r01_kernel_table.md).
-        const int cfg = env_int("MEMC_FI_FWD_CFG");
-        if (cfg == 32) return launch_fwd_chunked<FwdK3>(stream, a);
-        if (cfg == 31) return launch_fwd_chunked<FwdK2>(stream, a);
-        if (cfg == 9) return 0;  // generic kernel
-        return launch_fwd_chunked<FwdK3>(stream, a);
-    }
-    if (a.dbg & 64) {
-        static long long* dev = nullptr;
-        if (!dev) cudaMalloc(reinterpret_cast<void**>(&dev), 256 * 8 * 6 * sizeof(long long));
-        cudaMemsetAsync(dev, 0, 256 * 8 * 6 * sizeof(long long), stream);
-        a.prof = dev;
-    }
-    if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
-    if (a.C == 3) {
-        int r = 0;
-        switch (env_int("MEMC_FI_FWD_CFG")) {
-            case 5: r = launch_fwd<3, FwdE>(stream, a); break;
-            case 19: r = launch_fwd<3, FwdE6>(stream, a); break;
-            case 50: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;
-            case 51: r = launch_fwd_patch<3, 72, 22, 6, true>(stream, a); break;
-            case 70: r = launch_fwd_ws<3, FwdW1, 3, 5>(stream, a); break;
-            case 9: r = launch_fwd<3, FWD_DEFAULT>(stream, a); break;
-            default: r = launch_fwd_patch<3, 72, 22, 6, false>(stream, a); break;  // best of the sweeps
-        }
-        if (a.prof && r == 1) prof_report(stream, a.prof);
-        return r;
-    }
+// Kernel selection.  `variant` = MEMC_B200_VARIANT field of the call's flags: 0 is production, the others keep
+// earlier kernels reachable for A/B measurements (tools/kbench.py) and cross-checks in the tests.
+int fi_forward_fast(cudaStream_t stream, const FiArgs& a) {
+    const int variant = (a.flags >> 16) & 0xff;
+    if (a.fs != 4 || a.C < 1 || a.W % 4 || a.B > 65535) return 0;
+    if (a.C > CB)  // e.g. the 64-channel context warps of MEMC_Net_star: channel-chunked kernel
+        return variant == 1 ? 0 : launch_fwd_chunked<FwdK3>(stream, a);
     switch (a.C) {
         case 1: return launch_fwd<1, FWD_DEFAULT>(stream, a);
         case 2: return launch_fwd<2, FWD_DEFAULT>(stream, a);
+        case 3:
+            if (variant == 1) return launch_fwd<3, FWD_DEFAULT>(stream, a);       // row segments
+            if (variant == 2) return launch_fwd_patch<3, 72, 22, 6, true>(stream, a);  // patches + TMA-staged output
+            return launch_fwd_patch<3, 72, 22, 6, false>(stream, a);              // 8x4 patches
         case 4: return launch_fwd<4, FWD_DEFAULT>(stream, a);
     }
     return 0;
@@ -1414,24 +1174,17 @@ int fi_blend_forward_fast(cudaStream_t stream, const FiArgs& a0, const FiArgs& a
     return launch_blend_patch<3, 72, 22, 5>(stream, a0, a1, bl);
 }
 
-int fi_backward_fast(cudaStream_t stream, const FiArgs& a_in, bool ow) {
-    FiArgs a = a_in;
-    a.dbg = env_int("MEMC_TMA_DBG");
-    if (a.dbg & 8) return 0;  // development: generic backward
+int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool ow) {
+    const int variant = (a.flags >> 16) & 0xff;
     if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
-    if (a.C == 3 && ow) {
-        switch (env_int("MEMC_FI_BWD_CFG")) {
-            case 1: return launch_bwd<3, true, BwdA>(stream, a);
-            case 3: return launch_bwd<3, true, BwdC>(stream, a);
-            case 5: return launch_bwd<3, true, BwdE>(stream, a);
-            case 6: return launch_bwd<3, true, BwdF>(stream, a);
-            default: return launch_bwd<3, true, BWD_DEFAULT>(stream, a);
-        }
+    if (variant != 1) {  // production: (pixel, tap row) lanes
+        const int r = fi_backward_rows(stream, a, ow);
+        if (r != 0) return r;
     }
-    switch (a.C) {
+    switch (a.C) {  // round-1 kernel: one pixel per lane
         case 1: return ow ? launch_bwd<1, true, BWD_DEFAULT>(stream, a) : launch_bwd<1, false, BWD_DEFAULT>(stream, a);
         case 2: return ow ? launch_bwd<2, true, BWD_DEFAULT>(stream, a) : launch_bwd<2, false, BWD_DEFAULT>(stream, a);
-        case 3: return launch_bwd<3, false, BWD_DEFAULT>(stream, a);
+        case 3: return ow ? launch_bwd<3, true, BWD_DEFAULT>(stream, a) : launch_bwd<3, false, BWD_DEFAULT>(stream, a);
         case 4: return ow ? launch_bwd<4, true, BWD_DEFAULT>(stream, a) : launch_bwd<4, false, BWD_DEFAULT>(stream, a);
     }
     return 0;

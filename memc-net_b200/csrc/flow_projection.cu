@@ -163,7 +163,7 @@ static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return 0;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     if (!(flags & MEMC_B200_NO_FAST)) {
-        const int r = fp_forward_fast(stream, a, ow, (flags & MEMC_B200_NO_ZERO) != 0);
+        const int r = fp_forward_fast(stream, a, ow, (flags & MEMC_B200_NO_ZERO) != 0, (flags >> 16) & 0xff);
         if (r != 0) return r < 0 ? -1 : 0;
     }
     if (ow && !(flags & MEMC_B200_NO_ZERO)) {

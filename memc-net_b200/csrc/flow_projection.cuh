@@ -17,7 +17,7 @@ struct FpArgs {
 
 // fast path (flow_projection_fast.cu): 1 = handled, 0 = layout preconditions not met (caller
 // runs the generic kernels), -1 = error
-int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero);
+int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, int variant);
 // average (+ fill-hole) over frames [b0, b0 + nb) with the generic kernels (flow_projection.cu)
 int fp_average_fill(cudaStream_t stream, const FpArgs& a, int b0, int nb, bool do_average);
 

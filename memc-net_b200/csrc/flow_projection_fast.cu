@@ -21,7 +21,6 @@
 //         all-zero vectors skipped).  Targets outside the box fall back to global atomics.
 #include "flow_projection.cuh"
 #include <limits.h>
-#include <stdlib.h>
 
 namespace memc {
 
@@ -35,6 +34,7 @@ struct __align__(128) Smem {
     int box[3][SH][SW];  // x, y (fixed point) and count: 36 KB
     int bb[4];
     unsigned maxbits;
+    int kmax;  // largest number of sources of this tile that share one corner cell
 };
 
 __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
@@ -82,6 +82,7 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
     if (tid == 0) {
         s.bb[0] = INT_MAX; s.bb[1] = INT_MIN; s.bb[2] = INT_MAX; s.bb[3] = INT_MIN;
         s.maxbits = 0u;
+        s.kmax = 0;
     }
     {   // zero the box
         int4* z = reinterpret_cast<int4*>(&s.box[0][0][0]);
@@ -128,14 +129,32 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
         bx = max(0, min(bx, W - SW)) & ~3;
         by = max(0, min(by, H - SH));
     }
+    // ---- count first: the hit counts are integers anyway, and the value the atomic returns tells how
+    // many sources of this tile share a corner cell.  K = the largest such multiplicity bounds every
+    // corner-cell sum by K * M and every 2x2-filtered output cell by 4 * K * M, so the fixed-point scale
+    // can spend the bits a worst-case bound (all TW*TH sources on one cell) would waste: on a smooth
+    // field K is 2..4 and a contribution is rounded to ~M * 2^-27 instead of M * 2^-21 -- below the
+    // rounding of the reference's own fp32 atomics (tests/test_gpu_at_size.py prints both).
+    bool in_box[PPT];
+    int kloc = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int ux = L[k] - bx, uy = T[k] - by;
+        in_box[k] = ok[k] && (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+        if (in_box[k]) kloc = max(kloc, atomicAdd(&s.box[2][uy][ux], 1) + 1);
+    }
+    kloc = __reduce_max_sync(0xffffffffu, kloc);
+    if (lane == 0 && kloc) atomicMax(&s.kmax, kloc);
+    __syncthreads();
     // fixed-point scale (see header); valid pixels have finite flows, so M is finite
     const float M = __uint_as_float(s.maxbits);
     float scale = 1.0f, inv_scale = 1.0f;
     if (M > 0.f) {
         int ex;
         frexpf(M, &ex);
-        constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;
-        const int e = max(-120, min(31 - ex - LOG2_PX, 120));
+        constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;  // every source is in exactly one cell
+        const int log2_4k = 32 - __clz(4 * max(s.kmax, 1) - 1);       // ceil(log2(4 K))
+        const int e = max(-120, min(31 - ex - min(LOG2_PX, log2_4k), 120));
         scale = ldexpf(1.0f, e);
         inv_scale = ldexpf(1.0f, -e);
     }
@@ -144,21 +163,19 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
     for (int k = 0; k < PPT; ++k) {
         if (!ok[k]) continue;
         const int ux = L[k] - bx, uy = T[k] - by;
-        const bool in_box = (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
-        if (in_box) {
+        if (in_box[k]) {
             atomicAdd(&s.box[0][uy][ux], __float2int_rn(-fx[k] * scale));
             atomicAdd(&s.box[1][uy][ux], __float2int_rn(-fy[k] * scale));
-            atomicAdd(&s.box[2][uy][ux], 1);
         }
         const bool last_col = L[k] == W - 1, last_row = T[k] == H - 1;
-        if (__builtin_expect(!in_box || last_col || last_row, 0)) {
+        if (__builtin_expect(!in_box[k] || last_col || last_row, 0)) {
             const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     // in the box: only the clamped repeats are missing from the 2x2 pattern
-                    if (in_box && !((i == 1 && last_col) || (j == 1 && last_row))) continue;
+                    if (in_box[k] && !((i == 1 && last_col) || (j == 1 && last_row))) continue;
                     const int cx = i ? R : L[k], cy = j ? Bm : T[k];
                     red_add(ox + (int64_t)cy * out_h + cx, -fx[k]);
                     red_add(oy + (int64_t)cy * out_h + cx, -fy[k]);
@@ -387,7 +404,6 @@ struct FpPipe {
     unsigned* colmask;  // [B][cm_stride]  (Ht x W words used)
     int64_t rs_stride, cs_stride, rm_stride, cm_stride;  // per-frame strides, multiples of 32 words
     int Wt, Ht, Wt32, Ht32, nS_x, nS_y, nA_x, nA_y;
-    int dbg;  // development (MEMC_FP_DBG): 1 skip splat, 2 skip average, 4 skip fill -- timing only
 };
 
 // thread 0: spin until *counter >= target (acquire); a lost producer becomes a launch error
@@ -635,14 +651,14 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
             }
         }
         if (it.type == 0) {
-            if (!(p.dbg & 1)) {
+            {
                 float* acc = p.scratch + (int64_t)(it.frame % 3) * 3 * plane;
                 splat_tile(s, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W, p.H);
             }
         } else if (it.type == 1) {
-            if (!(p.dbg & 2)) pipe_average_tile(p, rw, it.tile, it.frame);
+            pipe_average_tile(p, rw, it.tile, it.frame);
         } else if (it.type == 2) {
-            if (!(p.dbg & 4)) pipe_fill_tile(p, rw, it.tile, it.frame);
+            pipe_fill_tile(p, rw, it.tile, it.frame);
         }
         if (tid == 0) s_q[slot] = decode_item(p, nS, nA, total, fetched);
         __syncthreads();  // s_q[slot] published; this item is done with shared memory and with its global writes
@@ -689,8 +705,6 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
     p.Wt32 = (p.Wt + 31) / 32; p.Ht32 = (p.Ht + 31) / 32;
     p.nS_x = (a.W + TW - 1) / TW; p.nS_y = (a.H + TH - 1) / TH;
     p.nA_x = (a.W + 127) / 128; p.nA_y = p.Ht;
-    p.dbg = 0;
-    if (const char* e = getenv("MEMC_FP_DBG")) p.dbg = atoi(e);
     p.rs_stride = (int64_t)pad32((size_t)a.H * p.Wt32);
     p.cs_stride = (int64_t)pad32((size_t)p.Ht32 * a.W);
     p.rm_stride = (int64_t)pad32((size_t)a.H * p.Wt);
@@ -723,10 +737,8 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
 
 }  // namespace
 
-int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero) {
-    int dbg = 0;
-    if (const char* e = getenv("MEMC_TMA_DBG")) dbg = atoi(e);
-    if (dbg & 32) return 0;  // development: generic path
+int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, int variant) {
+    // variant (MEMC_B200_VARIANT field of the flags): 0 production, 1 = frame-by-frame launches even for B >= 3
     if (a.W < SW || a.H < SH || a.W % 4) return 0;
     // dense frames only: per-frame memset and the 128-bit averaging pass want contiguous planes
     const int64_t plane = (int64_t)a.H * a.W;
@@ -735,7 +747,7 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     if (a.out.b % 4 || a.count.b % 4) return 0;
     // the library produces every element: persistent pipeline (from 3 frames on; below that its phases
     // cannot overlap across frames and the per-frame launches are quicker: 43 vs 58 us at B = 1, 720p)
-    if (overwrite && a.B >= 3 && !(dbg & 128)) {
+    if (overwrite && a.B >= 3 && variant != 1) {
         const int r = fp_forward_pipeline(stream, a);
         if (r != 0) return r;
     }

@@ -87,6 +87,31 @@ __device__ __forceinline__ void store_4d(const CUtensorMap* map, int c0, int c1,
         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
         : "memory");
 }
+// 5-D variants (the tap-split filter / gradinput3 maps of the backward, make_map_taps below)
+__device__ __forceinline__ void load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                        uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void store_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                         const void* smem_src) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group"
+        " [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src))
+        : "memory");
+}
+__device__ __forceinline__ void reduce_add_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                              const void* smem_src) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group"
+        " [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src))
+        : "memory");
+}
 // 4-D tile prefetch global -> L2 only (no shared memory, no completion tracking)
 __device__ __forceinline__ void prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
@@ -140,6 +165,33 @@ inline bool make_map_nchw(CUtensorMap* map, const float* base, int B, int C, int
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// A [B,16,H,W] tensor of 4x4 tap planes (plane t = 4 j + i: tap row j, tap column i) as a rank-5 map with the
+// plane index split into its two digits and the ROW digit innermost after x:
+//     dims (W, j, i, H, B), strides (4 sc, sc, sh, sb), box (bw, 4, 4, bh, 1)
+// A box lands in shared memory as [y][i][j][x]: the word of (y, i, j, x) is ((y*4 + i)*4 + j)*bw + x, so with
+// bw == 8 the four tap ROWS of 8 neighbouring pixels are 32 consecutive words -- one conflict-free wavefront for
+// a warp whose lanes are (pixel, tap row) pairs.  (The strides are not monotonic; the TMA does not care.)
+inline bool make_map_taps(CUtensorMap* map, const float* base, int B, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                          int bw, int bh, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+    if (H == 1) sh = W;
+    if (B == 1) sb = 16 * sc;
+    if (sh % 4 || sc % 4 || sb % 4) return false;
+    if (sh < W || sc <= 0 || sb <= 0) return false;
+    if (bw > 256 || bh > 256 || (bw * 4) % 16) return false;
+    const cuuint64_t gdim[5] = {(cuuint64_t)W, 4u, 4u, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstr[4] = {(cuuint64_t)sc * 16, (cuuint64_t)sc * 4, (cuuint64_t)sh * 4, (cuuint64_t)sb * 4};
+    for (int i = 0; i < 4; ++i)
+        if (gstr[i] >= (1ull << 40)) return false;
+    const cuuint32_t box[5] = {(cuuint32_t)bw, 4u, 4u, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -17,6 +17,11 @@ NO_FAST = 2    # MEMC_B200_NO_FAST
 NO_ZERO = 4    # MEMC_B200_NO_ZERO
 FLOAT_ACCUM = 8  # MEMC_B200_FLOAT_ACCUM
 
+
+def variant(n):
+    """MEMC_B200_VARIANT(n): select a non-production kernel variant (A/B measurements, cross-checks)."""
+    return (int(n) & 0xFF) << 16
+
 _lib = None
 
 

@@ -182,22 +182,53 @@ def test_filter_interpolation_vs_reference_cuda_kernels(L, shape):
 
 @pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0),
                                    (1, 64, 96, 160, 4.0), (2, 7, 64, 128, 2.0), (1, 5, 40, 100, 12.0)])
-def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape, monkeypatch):
+def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
     """The TMA path stages data differently but performs the SAME fp32 operations in the same
     order as the generic kernel, so the two must agree bit for bit (forward)."""
     from memc_b200 import synth
     B, C, H, W, sigma = shape
-    if C == 7:  # C > 4 takes the channel-chunked kernel (8x4 patches); also cover its row-segment configuration
-        monkeypatch.setenv("MEMC_FI_FWD_CFG", "31")
     t1, t2, t3, _ = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=9, device="cuda")
     outs = []
-    for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
+    # production kernel, the row-segment / TMA-staged-output variants (MEMC_B200_VARIANT), the generic kernel
+    for flags in (L.OVERWRITE, L.OVERWRITE | L.variant(1), L.OVERWRITE | L.variant(2), L.OVERWRITE | L.NO_FAST):
         o = torch.empty_like(t1)
         L.call("memc_b200_filter_interpolation_forward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
                L.strides_of(t2), L.strides_of(t3), L.strides_of(o), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(o), flags)
         outs.append(o)
     torch.cuda.synchronize()
-    assert torch.equal(outs[0], outs[1])
+    for o in outs[:-1]:
+        assert torch.equal(o, outs[-1])
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0),
+                                   (1, 1, 33, 96, 1.5), (1, 2, 130, 132, 60.0), (3, 3, 64, 64, 3.0), (1, 3, 8, 16, 1.0),
+                                   (1, 3, 1080, 1920, 6.0)])
+@pytest.mark.parametrize("overwrite", [True, False])
+def test_filter_interpolation_backward_kernels_agree(L, shape, overwrite):
+    """The production backward ((pixel, tap row) lanes), the round-1 kernel (MEMC_B200_VARIANT(1)) and the generic
+    kernel on the same input, OVERWRITE and the reference's += contract (prefilled gradients): gradinput2/3
+    differ only by the summation order of <= 16 x C products, gradinput1 by the fixed-point rounding."""
+    from memc_b200 import synth
+    B, C, H, W, sigma = shape
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=13, device="cuda")
+    base = L.OVERWRITE if overwrite else 0
+    res = []
+    for flags in (base, base | L.variant(1), base | L.NO_FAST):
+        if overwrite:
+            g1, g2, g3 = torch.full_like(t1, 7.0), torch.full_like(t2, 7.0), torch.full_like(t3, 7.0)  # garbage
+        else:
+            g1, g2, g3 = torch.full_like(t1, 0.5), torch.full_like(t2, 0.5), torch.full_like(t3, 0.5)
+        L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(tg), L.strides_of(g1), L.strides_of(g2),
+               L.strides_of(g3), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(tg), L.ptr(g1), L.ptr(g2), L.ptr(g3), flags)
+        res.append((g1, g2, g3))
+    torch.cuda.synchronize()
+    for k, name in enumerate(("gradinput1", "gradinput2", "gradinput3")):
+        gen = res[2][k]
+        scale = max(1.0, float(gen.abs().max()))
+        for which, r in (("rows", res[0]), ("round-1", res[1])):
+            err = float((r[k] - gen).abs().max())
+            assert err <= TOL * scale, "%s %s: %.3e vs generic (scale %.3g)" % (which, name, err, scale)
 
 
 def test_filter_interpolation_backward_propagates_nonfinite_gradients(L):
@@ -498,19 +529,18 @@ def test_flow_projection_pipeline_many_frames(L, shape, fillhole):
         close(out, eo, tol=5e-5, what="pipeline %s fillhole=%d" % (shape, fillhole))
 
 
-def test_flow_projection_pipeline_equals_per_frame_path(L, monkeypatch):
+def test_flow_projection_pipeline_equals_per_frame_path(L):
     """Same call through the persistent pipeline and through the per-frame launches
-    (MEMC_TMA_DBG=128): count bit-equal, output equal up to the fp32 summation order."""
+    (MEMC_B200_VARIANT(1)): count bit-equal, output equal up to the fp32 summation order."""
     from memc_b200 import synth
     S, P = L.strides_of, L.ptr
     B, H, W = 6, 270, 480
     t = synth.smooth_flow(B, H, W, 6.0, seed=3, device="cuda")
     res = []
-    for dbg in ("0", "128"):
-        monkeypatch.setenv("MEMC_TMA_DBG", dbg)
+    for var in (0, 1):
         count, out = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(t)
         assert L.call("memc_b200_flow_projection_forward", L.stream_ptr(t), B, H, W, 1, S(t), S(count), S(out), P(t),
-                      P(count), P(out), L.OVERWRITE) == 0
+                      P(count), P(out), L.OVERWRITE | L.variant(var)) == 0
         res.append((count, out))
     assert torch.equal(res[0][0], res[1][0])
     assert float((res[0][1] - res[1][1]).abs().max()) <= TOL
