@@ -20,8 +20,16 @@ than the 126 MB L2, so no explicit L2 flush is needed between steps.
              inside the timed region; `roofline_fwd` is the same for the forward kernel
              (96 B/px), the north_star's >= 70 % target
   cpu_baseline  the reference's own my_lib.c (oracle/_ref) on the host cores, bounded sample
-  other_ops  (N = 1) the other ops of the path, device-timed the same way: FlowProjection (BASELINE
-             configs[2]), the C = 64 context warp of MEMC_Net_star, the fused two-warp + blend call site
+  other_ops  (N = 1) the other ops of the path, device-timed the same way: FlowProjection forward in four
+             flow regimes (BASELINE configs[2]) and backward, the C = 64 context warp of MEMC_Net_star,
+             the fused call sites, Interpolation and SeparableConv forward / backward
+  legacy_gpu (N = 1) the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref), same inputs, same
+             harness, with the zero fills their contract needs -- a labelled baseline leg, outside `value`
+  networks   the reference's own MEMC_Net_s / MEMC_Net_star (random init, inference) on this my_package,
+             frames sharded over the ranks (BASELINE configs[3] / configs[4] frame sizes), next to the same
+             network on the reference kernels: frames/s of both and max-abs / PSNR between them
+  N > 1      `value` (no data-path collective), `value_with_gather` (the output batch all-gathered frame by
+             frame over NCCL, overlapped with the next frame's compute) and the gather timed alone
 
 --impl reference times the reference's CPU implementation (oracle/_ref/libmemc_ref_cpu.so,
 else the oracle port) on the host cores for the same metric; rank 0 only.
@@ -157,7 +165,7 @@ def run_reference(args, rank):
     threads = cpu_threads()
     frames = host_frames(min(threads, B))
     kind = "port"
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         cpu_reference_step(frames, threads)
     t_total = 0.0
     for _ in range(args.steps):
@@ -168,9 +176,10 @@ def run_reference(args, rank):
     sample = "%d 1920x1080 frames per step (the %d-frame batch, replicated), one frame per host thread" % (threads, B)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "device": "host CPU, %s my_lib.c via oracle/_ref" % kind},
+        "config": {"workload": WORKLOAD},
+        "device": "host CPU, %s my_lib.c via oracle/_ref" % kind,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -27,13 +27,13 @@
 //   * the image / accumulation boxes are made of 4-row slabs and only the slabs the tile's windows
 //     touch are loaded, zeroed, converted and flushed (TMA reduce-add per slab): a third less box traffic;
 //   * filter taps and gradoutput are read from shared memory ONCE, into the registers of the lane that
-//     uses them; the fixed-point bound M = max|gradoutput| * max|filter| over the tile comes from those
+//     uses them; the fixed-point bound M (max over pixels of max|gradoutput| * max|filter tap|) comes from those
 //     registers (round 1 re-read the 16 + C planes for it);
-//   * boxes may hang over the image edge (TMA zero-fills loads and clips reductions), so there is no
-//     minimum image size.
+//   * the warp geometry (validity, integer target, alpha / beta, fast-path test) is evaluated once per pixel in
+//     the row-segment view (lane = x) and handed to the pixel's 4 tap-row lanes with 3 shuffles: with 4 lanes per
+//     pixel every per-pixel instruction costs 4 issue slots, and geometry was a third of the first version;
 // Fixed-point accumulation of gradinput1: as in round 1 (per-tile power-of-two scale, K = TW*TH, clamped
-// taps bypass the box, non-finite tiles and MEMC_B200_FLOAT_ACCUM take fp32 shared atomics); the bound
-// M is now the product of the tile maxima (>= the old per-pixel maximum of products, never smaller).
+// taps bypass the box, non-finite tiles and MEMC_B200_FLOAT_ACCUM take fp32 shared atomics).
 #include "filter_interpolation.cuh"
 #include "tma_utils.cuh"
 
@@ -41,16 +41,18 @@ namespace memc {
 
 namespace {
 
-constexpr int TW = 32, TH = 8, NT = 256;  // 8 warps; warp w owns tile row w as 4 groups of 8 pixels
-constexpr int GW = 8;                     // pixels per group: lane = (p = lane & 7, j = lane >> 3)
-constexpr int SW = 72;                    // box pitch (words)
-constexpr int SLAB_H = 4, NSLAB = 7;      // the box is up to 7 slabs of 4 rows
-constexpr int STRIP = TH * 16 * GW;       // floats per filter strip [y][i][j][x]
+constexpr int TW = 32;      // tile width; warp w owns tile row w as 4 groups of 8 pixels
+constexpr int GW = 8;       // pixels per group: lane = (p = lane & 7, j = lane >> 3)
+constexpr int SW = 72;      // box pitch (words)
+constexpr int SLAB_H = 4;   // the box is made of slabs of 4 rows
 
-template <int C>
+// C channels, TH tile rows (= warps), NSLAB slabs at most, MINB resident CTAs per SM
+template <int C, int TH_, int NSLAB_, int MINB_>
 struct Lay {
-    static constexpr int CH = SLAB_H * SW;  // channel stride inside a slab (words) = 288 = 0 mod 32
-    static constexpr int SLAB = C * CH;     // words per slab [c][4][72]
+    static constexpr int TH = TH_, NSLAB = NSLAB_, MINB = MINB_, NT = 32 * TH_;
+    static constexpr int STRIP = TH * 16 * GW;  // floats per filter strip [y][i][j][x]
+    static constexpr int CH = SLAB_H * SW;      // channel stride inside a slab (words) = 288 = 0 mod 32
+    static constexpr int SLAB = C * CH;         // words per slab [c][4][72]
     static constexpr int OFF_GOUT = 4 * STRIP * 4;
     static constexpr int OFF_FLOW = OFF_GOUT + C * TH * TW * 4;
     static constexpr int OFF_BAR = OFF_FLOW + 2 * TH * TW * 4;
@@ -64,12 +66,21 @@ __device__ __forceinline__ int box_off(int r, int col, int slab_words) {  // row
     return (r >> 2) * slab_words + (r & 3) * SW + col;
 }
 
-template <int C, bool OVERWRITE, bool INT_ACC>
-__device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, const float* s_gout, float* s_flow,
-                                             const float* s_img, float* s_acc, const float (&wt)[4][4],
-                                             const float (&go)[4][C], float scale, int x0, int y0, int b, int bx, int by,
-                                             int box_rows, int lane, int warp) {
-    using Y = Lay<C>;
+// Geometry of a pixel as the (pixel, tap row) lanes need it, computed ONCE per pixel by the lane that owns the
+// pixel in the row-segment view (lane = x) and handed to the pixel's 4 tap-row lanes with shuffles:
+//   code >= 0   fast: window inside the staged box and the image, code = (ly << 8) | lx (box coordinates of tap (0,0))
+//   code == -1  valid, but the window touches the image border or leaves the box: per-tap path
+//   code == -2  invalid flow / outside the image: contributes nothing (my_lib_kernel.cu:1256)
+struct PxGeo {
+    int code, ix, iy;
+    float alpha, beta;
+};
+
+template <class Y, int C, bool OVERWRITE, bool INT_ACC>
+__device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, float* s_flow, const float* s_img, float* s_acc,
+                                             const PxGeo& me, const float (&wt)[4][4], const float (&go)[4][C], float scale,
+                                             int x0, int y0, int b, int bx, int by, int box_rows, int lane, int warp) {
+    constexpr int TH = Y::TH, STRIP = Y::STRIP;
     const int W = p.W, H = p.H;
     const int pl = lane & 7, j = lane >> 3;
     const int y = y0 + warp;
@@ -79,27 +90,30 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
     const bool top = j < 2;
 #pragma unroll  // wt[g][] / go[g][] live in registers: g must be a compile-time index
     for (int g = 0; g < 4; ++g) {
-        const int xl = GW * g + pl, x = x0 + xl;
-        const bool inside = x < W && y < H;
-        const FiGeom geo = fi_geometry(x, y, W, H, s_flow[warp * TW + xl], s_flow[(TH + warp) * TW + xl]);
+        const int src = GW * g + pl, xl = src, x = x0 + xl;
+        const int code = __shfl_sync(0xffffffffu, me.code, src);
+        const float a = __shfl_sync(0xffffffffu, me.alpha, src), bt = __shfl_sync(0xffffffffu, me.beta, src);
+        int Lc = 0, T = 0;
+        if (__builtin_expect(__any_sync(0xffffffffu, code == -1), 0)) {  // rare: someone needs full coordinates
+            Lc = __shfl_sync(0xffffffffu, me.ix, src) - 1;
+            T = __shfl_sync(0xffffffffu, me.iy, src) - 1;
+        }
         float a3[4] = {0.f, 0.f, 0.f, 0.f};
-        float dx = 0.f, dy = 0.f;
-        if (inside && geo.valid) {  // my_lib_kernel.cu:1256: an invalid pixel contributes nothing
-            const float a = geo.alpha, bt = geo.beta;
+        float ql[C], qr[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ql[c] = qr[c] = 0.f;
+        if (code != -2) {
             const float wy = top ? (1.0f - bt) : bt;
-            float gl[C], gr[C], ql[C], qr[C];
+            float gl[C], gr[C], gls[C], grs[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 gl[c] = go[g][c] * (1.0f - a) * wy;  // gradoutput x bilinear weight of this row's left / right quadrant
                 gr[c] = go[g][c] * a * wy;
-                ql[c] = qr[c] = 0.f;
+                gls[c] = gl[c] * scale;              // fixed-point copies (scale is a power of two: exact)
+                grs[c] = gr[c] * scale;
             }
-            const int Lc = geo.ix - 1, T = geo.iy - 1;
-            const int lx = Lc - bx, ly = T - by;
-            const bool fast = (unsigned)lx <= (unsigned)(SW - 4) && ly >= 0 && ly + 3 < box_rows && Lc >= 0 &&
-                              Lc + 3 <= W - 1 && T >= 0 && T + 3 <= H - 1;
-            if (__builtin_expect(fast, 1)) {
-                const int off = box_off(ly + j, lx, Y::SLAB);
+            if (__builtin_expect(code >= 0, 1)) {
+                const int off = box_off((code >> 8) + j, code & 255, Y::SLAB);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float w = wt[g][i];
@@ -108,10 +122,9 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
                     for (int c = 0; c < C; ++c) {
                         const int o = off + c * Y::CH + i;
                         const float v = s_img[o];
-                        const float gs = i < 2 ? gl[c] : gr[c];
-                        if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn(gs * w * scale));
-                        else atomicAdd(&s_acc[o], gs * w);
-                        acc3 = fmaf(gs, v, acc3);
+                        if (INT_ACC) atomicAdd(&s_acci[o], __float2int_rn((i < 2 ? gls[c] : grs[c]) * w));
+                        else atomicAdd(&s_acc[o], (i < 2 ? gl[c] : gr[c]) * w);
+                        acc3 = fmaf(i < 2 ? gl[c] : gr[c], v, acc3);
                         if (i < 2) ql[c] = fmaf(v, w, ql[c]);
                         else qr[c] = fmaf(v, w, qr[c]);
                     }
@@ -137,7 +150,7 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
                         const float v = in_box ? s_img[o0 + c * Y::CH] : __ldg(in1b + c * p.in1.c + (int64_t)cy * p.in1.h + cx);
                         const float gs = i < 2 ? gl[c] : gr[c];
                         if (to_box) {
-                            if (INT_ACC) atomicAdd(&s_acci[o0 + c * Y::CH], __float2int_rn(gs * w * scale));
+                            if (INT_ACC) atomicAdd(&s_acci[o0 + c * Y::CH], __float2int_rn((i < 2 ? gls[c] : grs[c]) * w));
                             else atomicAdd(&s_acc[o0 + c * Y::CH], gs * w);
                         } else {
                             red_add(g1b + c * p.gi1.c + (int64_t)cy * p.gi1.h + cx, gs * w);
@@ -149,9 +162,14 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
                     a3[i] = acc3;
                 }
             }
-            // flow gradient, this row's share (the reference's gamma = 1 - beta / 1 - alpha, my_lib_kernel.cu:1358-1495):
-            //   d/dx = sum_c go (gam_y (TR - TL) + (1 - gam_y)(BR - BL)),  d/dy = sum_c go (gam_x (BL - TL) + (1 - gam_x)(BR - TR))
-            const float gam_y = 1.0f - bt, gam_x = 1.0f - a;
+        }
+        // ---- flow gradient (the reference's gamma = 1 - beta / 1 - alpha, my_lib_kernel.cu:1358-1495):
+        //   d/dx = sum_c go (gam_y (TR - TL) + (1 - gam_y)(BR - BL)),  d/dy = sum_c go (gam_x (BL - TL) + (1 - gam_x)(BR - TR))
+        // The 4 tap rows of a pixel sit in lanes p, p + 8, p + 16, p + 24.
+        const float gam_y = 1.0f - bt, gam_x = 1.0f - a;
+        float dx = 0.f, dy = 0.f;
+        if (INT_ACC) {
+            // finite tile: every row adds its share (two shuffles per component)
             const float wyg = top ? gam_y : (1.0f - gam_y);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -159,12 +177,24 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
                 dy = fmaf(go[g][c], gam_x * ql[c] + (1.0f - gam_x) * qr[c], dy);
             }
             dy = top ? -dy : dy;
+            dx += __shfl_xor_sync(0xffffffffu, dx, 8);
+            dy += __shfl_xor_sync(0xffffffffu, dy, 8);
+            dx += __shfl_xor_sync(0xffffffffu, dx, 16);
+            dy += __shfl_xor_sync(0xffffffffu, dy, 16);
+        } else {
+            // non-finite gradients / MEMC_B200_FLOAT_ACCUM: the quadrant sums first, then the reference's expression
+            // as written, so that Inf / NaN land exactly where the reference puts them (+Inf - Inf must not appear)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float hl = ql[c] + __shfl_xor_sync(0xffffffffu, ql[c], 8);   // TL (top lanes) / BL (bottom lanes)
+                const float hr = qr[c] + __shfl_xor_sync(0xffffffffu, qr[c], 8);   // TR / BR
+                const float ol = __shfl_xor_sync(0xffffffffu, hl, 16), orr = __shfl_xor_sync(0xffffffffu, hr, 16);
+                const float TL = top ? hl : ol, TR = top ? hr : orr, BL = top ? ol : hl, BR = top ? orr : hr;
+                dx = fmaf(go[g][c], gam_y * (TR - TL) + (1.0f - gam_y) * (BR - BL), dx);
+                dy = fmaf(go[g][c], gam_x * (BL - TL) + (1.0f - gam_x) * (BR - TR), dy);
+            }
         }
-        // the 4 tap rows of a pixel sit in lanes p, p + 8, p + 16, p + 24
-        dx += __shfl_xor_sync(0xffffffffu, dx, 8);
-        dy += __shfl_xor_sync(0xffffffffu, dy, 8);
-        dx += __shfl_xor_sync(0xffffffffu, dx, 16);
-        dy += __shfl_xor_sync(0xffffffffu, dy, 16);
+        if (code == -2) dx = dy = 0.f;  // (alpha / beta of an invalid pixel may be NaN)
         // gradinput3 of taps (j, 0..3): staged over the filter words this lane read into wt[g][] earlier
         // (all zero for an invalid pixel: stored as such with OVERWRITE, added as such under the += contract)
         {
@@ -173,12 +203,11 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
             for (int i = 0; i < 4; ++i) f[i * 4 * GW] = a3[i];
         }
         if (OVERWRITE) {
-            __syncwarp();  // every lane of the pixel has read its flow
-            if (j == 0) {
+            if (j == 0) {  // nobody reads the flow tile any more (geometry lives in registers)
                 s_flow[warp * TW + xl] = dx;
                 s_flow[(TH + warp) * TW + xl] = dy;
             }
-        } else if (j == 0 && inside && geo.valid) {  // assigned for valid pixels only (my_lib_kernel.cu:1424,1495)
+        } else if (j == 0 && code != -2) {  // assigned for valid pixels only (my_lib_kernel.cu:1424,1495)
             float* g2 = p.gi2p + b * p.gi2.b + (int64_t)y * p.gi2.h + x;
             g2[0] = dx;
             g2[p.gi2.c] = dy;
@@ -186,13 +215,13 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, con
     }
 }
 
-template <int C, bool OVERWRITE>
-__global__ void __launch_bounds__(NT, 3)
+template <class Y, int C, bool OVERWRITE>
+__global__ void __launch_bounds__(Y::NT, Y::MINB)
 fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_gout,
                    const __grid_constant__ CUtensorMap m_filt, const __grid_constant__ CUtensorMap m_img,
                    const __grid_constant__ CUtensorMap m_gi1, const __grid_constant__ CUtensorMap m_gi2,
                    const __grid_constant__ CUtensorMap m_gi3, const __grid_constant__ FiArgs p) {
-    using Y = Lay<C>;
+    constexpr int TH = Y::TH, NT = Y::NT, NSLAB = Y::NSLAB, STRIP = Y::STRIP;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
     float* s_filt = reinterpret_cast<float*>(sm);                       // 4 x [TH][4 i][4 j][8]
@@ -200,7 +229,7 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     float* s_flow = reinterpret_cast<float*>(sm + Y::OFF_FLOW);         // [2][TH][TW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Y::OFF_BAR);      // 0 flow, 1 gout, 2 filter, 3 image
     int* s_bb = reinterpret_cast<int*>(bars + 4);
-    unsigned* s_max = reinterpret_cast<unsigned*>(s_bb + 4);            // [0] max |gradoutput| bits, [1] max |filter| bits
+    unsigned* s_max = reinterpret_cast<unsigned*>(s_bb + 4);            // bits of max |gradoutput * filter tap|
     const float* s_img = reinterpret_cast<const float*>(sm + Y::OFF_IMG);
     float* s_acc = reinterpret_cast<float*>(sm + Y::OFF_ACC);
 
@@ -212,7 +241,7 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     if (tid == 0) {
         for (int k = 0; k < 4; ++k) tma::mbar_init(&bars[k], 1);
         s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
-        s_max[0] = s_max[1] = 0u;
+        s_max[0] = 0u;
         tma::fence_barrier_init();
     }
     __syncthreads();
@@ -226,21 +255,18 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
         for (int g = 0; g < 4; ++g) tma::load_5d(s_filt + g * STRIP, &m_filt, x0 + GW * g, 0, 0, y0, b, &bars[2]);
     }
 
-    // ---- bounding box of the tile's source windows (every tap-row lane of a pixel computes the same geometry)
+    // ---- geometry, once per pixel (row-segment view: lane = x), and the bounding box of the source windows
     tma::mbar_wait(&bars[0], 0, 21);
+    PxGeo me;
+    bool me_valid;
     {
-        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int xl = GW * g + pl;
-            const FiGeom geo = fi_geometry(x0 + xl, y0 + warp, W, H, s_flow[warp * TW + xl], s_flow[(TH + warp) * TW + xl]);
-            if (geo.valid && x0 + xl < W && y0 + warp < H) {
-                mnx = min(mnx, geo.ix); mxx = max(mxx, geo.ix);
-                mny = min(mny, geo.iy); mxy = max(mxy, geo.iy);
-            }
-        }
-        mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
-        mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+        const FiGeom geo = fi_geometry(x0 + lane, y0 + warp, W, H, s_flow[warp * TW + lane], s_flow[(TH + warp) * TW + lane]);
+        me_valid = geo.valid && x0 + lane < W && y0 + warp < H;
+        me.ix = geo.ix; me.iy = geo.iy; me.alpha = geo.alpha; me.beta = geo.beta;
+        const int mnx = __reduce_min_sync(0xffffffffu, me_valid ? geo.ix : INT_MAX);
+        const int mxx = __reduce_max_sync(0xffffffffu, me_valid ? geo.ix : INT_MIN);
+        const int mny = __reduce_min_sync(0xffffffffu, me_valid ? geo.iy : INT_MAX);
+        const int mxy = __reduce_max_sync(0xffffffffu, me_valid ? geo.iy : INT_MIN);
         if (lane == 0 && mnx <= mxx) {
             atomicMin(&s_bb[0], mnx); atomicMax(&s_bb[1], mxx);
             atomicMin(&s_bb[2], mny); atomicMax(&s_bb[3], mxy);
@@ -252,20 +278,28 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     if (any_valid) {
         // windows span [min ix - 1, max ix + 2] x [min iy - 1, max iy + 2]; a span larger than the box centres it
         // (what it misses takes the per-tap path); x origin rounded down to 4 pixels (TMA: 16-byte coordinates).
-        // The box may hang over the image edge: the TMA zero-fills loads and clips reductions there.
+        // The box is kept INSIDE the image: a TMA reduce-add at negative coordinates is an illegal instruction on
+        // sm_100a (tools/tma_probe.cu, tests 5 and 8), unlike loads, which zero-fill.
+        const int need_w = s_bb[1] - s_bb[0] + 4 + 3, need_h = s_bb[3] - s_bb[2] + 4;
+        nslab = min(min(NSLAB, H / SLAB_H), (need_h + SLAB_H - 1) / SLAB_H);  // launch precondition: H >= SLAB_H
         bx = s_bb[0] - 1;
         by = s_bb[2] - 1;
-        const int need_w = s_bb[1] - s_bb[0] + 4 + 3, need_h = s_bb[3] - s_bb[2] + 4;
         if (need_w > SW) bx += (need_w - SW) / 2;
-        if (need_h > NSLAB * SLAB_H) by += (need_h - NSLAB * SLAB_H) / 2;
-        bx &= ~3;
-        nslab = min(NSLAB, (need_h + SLAB_H - 1) / SLAB_H);
+        if (need_h > nslab * SLAB_H) by += (need_h - nslab * SLAB_H) / 2;
+        bx = max(0, min(bx, W - SW)) & ~3;  // W >= SW and W % 4 == 0 are launch preconditions
+        by = max(0, min(by, H - nslab * SLAB_H));
     }
     const int box_rows = nslab * SLAB_H;
     if (tid == 0 && any_valid) {
         tma::mbar_expect_tx(&bars[3], nslab * Y::SLAB * 4);
         for (int s = 0; s < nslab; ++s)
             tma::load_4d(sm + Y::OFF_IMG + s * Y::SLAB * 4, &m_img, bx, by + SLAB_H * s, 0, b, &bars[3]);
+    }
+    {
+        const int Lc = me.ix - 1, T = me.iy - 1, lx = Lc - bx, ly = T - by;
+        const bool fast = (unsigned)lx <= (unsigned)(SW - 4) && ly >= 0 && ly + 3 < box_rows && Lc >= 0 && Lc + 3 <= W - 1 &&
+                          T >= 0 && T + 3 <= H - 1;
+        me.code = !me_valid ? -2 : fast ? ((ly << 8) | lx) : -1;
     }
     // zero the slabs in use while the image flies (int 0 and float 0 share the bit pattern)
     {
@@ -277,10 +311,11 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     tma::mbar_wait(&bars[1], 0, 22);
     tma::mbar_wait(&bars[2], 0, 23);
     float wt[4][4], go[4][C];
-    unsigned mw = 0u, mg = 0u;
+    unsigned mbits = 0u;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const float* f = s_filt + g * STRIP + (warp * 16 + j) * GW + pl;
+        unsigned mw = 0u, mg = 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             wt[g][i] = f[i * 4 * GW];
@@ -291,21 +326,19 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
             go[g][c] = s_gout[(c * TH + warp) * TW + GW * g + pl];
             mg = max(mg, __float_as_uint(go[g][c]) & 0x7fffffffu);
         }
+        // |x| of a float orders like its bit pattern and NaN patterns sort above +Inf: integer maxima, NaN propagates;
+        // Inf * 0 = NaN is fine, any non-finite tile takes the float path.  The maximum over the 4 tap-row lanes of a
+        // pixel is the pixel's max_c |gradoutput| * max_t |filter tap|: >= every contribution of that pixel.
+        mbits = max(mbits, __float_as_uint(__uint_as_float(mg) * __uint_as_float(mw)) & 0x7fffffffu);
     }
-    // |x| of a float orders like its bit pattern and NaN patterns sort above +Inf: integer maxima, NaN propagates
-    mw = __reduce_max_sync(0xffffffffu, mw);
-    mg = __reduce_max_sync(0xffffffffu, mg);
-    if (lane == 0) {
-        if (mg) atomicMax(&s_max[0], mg);
-        if (mw) atomicMax(&s_max[1], mw);
-    }
-    __syncthreads();  // maxima complete; accumulation slabs zeroed
+    mbits = __reduce_max_sync(0xffffffffu, mbits);
+    if (lane == 0 && mbits) atomicMax(&s_max[0], mbits);
+    __syncthreads();  // maximum complete; accumulation slabs zeroed
     float scale = 0.f, inv_scale = 0.f;
     {
-        const unsigned bg = s_max[0], bw = s_max[1];
-        const float M = __uint_as_float(bg) * __uint_as_float(bw);  // >= every |gq * w| of the tile
-        const bool finite = bg < 0x7f800000u && bw < 0x7f800000u && M < __uint_as_float(0x7f800000u);
-        if (finite && M > 0.f && !(p.flags & MEMC_B200_FLOAT_ACCUM)) {
+        const unsigned mb = s_max[0];
+        const float M = __uint_as_float(mb);
+        if (mb < 0x7f800000u && M > 0.f && !(p.flags & MEMC_B200_FLOAT_ACCUM)) {
             int ex;
             frexpf(M, &ex);  // M < 2^ex
             constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;  // a cell gets <= 1 unclamped tap per pixel
@@ -317,9 +350,9 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     if (any_valid) tma::mbar_wait(&bars[3], 0, 24);
 
     if (scale > 0.f)
-        compute_rows<C, OVERWRITE, true>(p, s_filt, s_gout, s_flow, s_img, s_acc, wt, go, scale, x0, y0, b, bx, by, box_rows, lane, warp);
+        compute_rows<Y, C, OVERWRITE, true>(p, s_filt, s_flow, s_img, s_acc, me, wt, go, scale, x0, y0, b, bx, by, box_rows, lane, warp);
     else
-        compute_rows<C, OVERWRITE, false>(p, s_filt, s_gout, s_flow, s_img, s_acc, wt, go, 1.0f, x0, y0, b, bx, by, box_rows, lane, warp);
+        compute_rows<Y, C, OVERWRITE, false>(p, s_filt, s_flow, s_img, s_acc, me, wt, go, 1.0f, x0, y0, b, bx, by, box_rows, lane, warp);
 
     // ---- flush: slabs of gradinput1 by TMA reduce-add, gradinput3 strips and the gradinput2 tile by TMA store
     __syncthreads();
@@ -334,6 +367,7 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     tma::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
     __syncthreads();
     if (tid == 0) {
+        // stores / reductions that hang over the right or bottom image edge are clipped by the TMA (tma_probe tests 9-11)
         for (int s = 0; s < nslab; ++s) tma::reduce_add_4d(&m_gi1, bx, by + SLAB_H * s, 0, b, s_acc + s * Y::SLAB);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -346,9 +380,9 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     }
 }
 
-template <int C, bool OW>
+template <class Y, int C, bool OW>
 int launch_rows(cudaStream_t stream, const FiArgs& a) {
-    using Y = Lay<C>;
+    constexpr int TH = Y::TH;
     CUtensorMap m[7];
     const CUtensorMapL2promotion p128 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B, p256 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  pnone = CU_TENSOR_MAP_L2_PROMOTION_NONE;
@@ -361,23 +395,37 @@ int launch_rows(cudaStream_t stream, const FiArgs& a) {
         !tma::make_map_taps(&m[6], a.gi3p, a.B, a.H, a.W, a.gi3.b, a.gi3.c, a.gi3.h, GW, TH, pnone))
         return 0;
     constexpr size_t smem = (size_t)Y::TOTAL + 128;
-    if (!ensure_dynamic_smem(fi_bwd_rows_kernel<C, OW>, smem)) return 0;
+    if (!ensure_dynamic_smem(fi_bwd_rows_kernel<Y, C, OW>, smem)) return 0;
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
-    fi_bwd_rows_kernel<C, OW><<<grid, NT, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);
+    fi_bwd_rows_kernel<Y, C, OW><<<grid, Y::NT, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);
     count_launch();
     return check_launch("FilterInterpolation backward (TMA, tap-row lanes)") == 0 ? 1 : -1;
+}
+
+template <int C>
+int launch_rows_c(cudaStream_t stream, const FiArgs& a, bool ow, int variant) {
+    //                       TH NSLAB MINB
+    using Y8 = Lay<C, 8, 7, 3>;  // 32x8 tile, 256 threads, 70 KB (C = 3): 3 CTAs / SM
+    using Y6 = Lay<C, 6, 5, 4>;  // 32x6 tile, 192 threads, 50 KB: 4 CTAs / SM
+    using Y4 = Lay<C, 4, 4, 5>;  // 32x4 tile, 128 threads, 38 KB: 5 CTAs / SM
+    using Y12 = Lay<C, 12, 7, 2>;  // 32x12 tile, 384 threads, 80 KB: 2 CTAs / SM
+    if (variant == 4) return ow ? launch_rows<Y12, C, true>(stream, a) : launch_rows<Y12, C, false>(stream, a);
+    if (variant == 2) return ow ? launch_rows<Y6, C, true>(stream, a) : launch_rows<Y6, C, false>(stream, a);
+    if (variant == 3) return ow ? launch_rows<Y4, C, true>(stream, a) : launch_rows<Y4, C, false>(stream, a);
+    return ow ? launch_rows<Y8, C, true>(stream, a) : launch_rows<Y8, C, false>(stream, a);
 }
 
 }  // namespace
 
 // 1 = handled, 0 = layout preconditions not met (caller falls back), -1 = launch error
 int fi_backward_rows(cudaStream_t stream, const FiArgs& a, bool ow) {
-    if (a.fs != 4 || a.C < 1 || a.C > 4 || a.W % 4 || a.B > 65535) return 0;
+    if (a.fs != 4 || a.C < 1 || a.C > 4 || a.W % 4 || a.B > 65535 || a.W < SW || a.H < SLAB_H) return 0;
+    const int variant = (a.flags >> 16) & 0xff;
     switch (a.C) {
-        case 1: return ow ? launch_rows<1, true>(stream, a) : launch_rows<1, false>(stream, a);
-        case 2: return ow ? launch_rows<2, true>(stream, a) : launch_rows<2, false>(stream, a);
-        case 3: return ow ? launch_rows<3, true>(stream, a) : launch_rows<3, false>(stream, a);
-        case 4: return ow ? launch_rows<4, true>(stream, a) : launch_rows<4, false>(stream, a);
+        case 1: return launch_rows_c<1>(stream, a, ow, 0);
+        case 2: return launch_rows_c<2>(stream, a, ow, 0);
+        case 3: return launch_rows_c<3>(stream, a, ow, variant);
+        case 4: return launch_rows_c<4>(stream, a, ow, 0);
     }
     return 0;
 }
