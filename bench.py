@@ -185,6 +185,242 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+# ------------------------------------------------------------------ other ops, legacy kernels, networks
+def _timed(torch, fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b_.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b_) * 1e-3 / n
+
+
+def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
+    """-> (other_ops, legacy_gpu).  Every op of the path at BASELINE sizes, ours through the C ABI (OVERWRITE mode:
+    the library zero-fills what it scatters into, inside the timed call) and -- when oracle/_ref/libmemc_ref_gpu.so
+    travelled -- the reference's kernels with the memsets their contract requires (functions/*.py zero-fill every
+    output and gradient).  The legacy leg is a labelled BASELINE: it never contributes to `value`."""
+    S, P = lib.strides_of, lib.ptr
+    in1, flow, filt, gout, out, g1, g2, g3 = main_tensors
+    try:
+        from oracle import ref
+        have_ref = ref.available_gpu()
+    except Exception:
+        ref, have_ref = None, False
+    other, legacy = [], []
+
+    def entry(name, px, bytes_px, t, t_leg=None):
+        other.append({"op": name, "ms": t * 1e3, "mpx_s": px / t / 1e6, "alg_bytes_per_px": bytes_px,
+                      "gbs": px * bytes_px / t / 1e9, "frac": px * bytes_px / t / 1e9 / peak})
+        if t_leg is not None:
+            legacy.append({"op": name, "legacy_ms": t_leg * 1e3, "legacy_mpx_s": px / t_leg / 1e6,
+                           "legacy_frac": px * bytes_px / t_leg / 1e9 / peak, "ours_ms": t * 1e3, "speedup": t_leg / t})
+
+    # --- FilterInterpolation C = 3, the bench batch (legacy arm only: ours is the main line)
+    if have_ref:
+        def l_fwd():
+            out.zero_()
+            ref.gpu_filter_interpolation_forward(in1, flow, filt, out)
+
+        def l_bwd():
+            g1.zero_(); g2.zero_(); g3.zero_()
+            ref.gpu_filter_interpolation_backward(in1, flow, filt, gout, (g1, g2, g3))
+
+        def o_fwd():
+            lib.call("memc_b200_filter_interpolation_forward", st, B, C, H, W, FS, S(in1), S(flow), S(filt), S(out),
+                     P(in1), P(flow), P(filt), P(out), lib.OVERWRITE)
+
+        def o_bwd():
+            lib.call("memc_b200_filter_interpolation_backward", st, B, C, H, W, FS, S(in1), S(flow), S(filt), S(gout),
+                     S(g1), S(g2), S(g3), P(in1), P(flow), P(filt), P(gout), P(g1), P(g2), P(g3), lib.OVERWRITE)
+
+        px = B * H * W
+        for name, bpp, fo, fl in (("FilterInterpolation forward 1920x1080, C=3, batch 4", BYTES_FWD, o_fwd, l_fwd),
+                                  ("FilterInterpolation backward 1920x1080, C=3, batch 4 (incl. zero fills)", BYTES_BWD, o_bwd, l_bwd)):
+            to, tl = _timed(torch, fo), _timed(torch, fl, 5)
+            legacy.append({"op": name, "legacy_ms": tl * 1e3, "legacy_mpx_s": px / tl / 1e6, "legacy_frac": px * bpp / tl / 1e9 / peak,
+                           "ours_ms": to * 1e3, "speedup": tl / to})
+
+    # --- FlowProjection forward (splat + average + fill-hole), BASELINE configs[2]: four flow regimes; backward
+    FB = 16
+    regimes = (("smooth", lambda: synth.smooth_flow(FB, H, W, 6.0, seed=1, device=dev)),
+               ("uniform +-32 px", lambda: synth.uniform_flow(FB, H, W, 32.0, seed=2, device=dev)),
+               ("convergent (atomic-contention)", lambda: synth.radial_flow(FB, H, W, 0.9, device=dev)),
+               ("divergent (holes)", lambda: synth.radial_flow(FB, H, W, -0.5, device=dev)))
+    for kind, make in regimes:
+        fl = make()
+        cnt, prj = torch.empty(FB, 1, H, W, device=dev), torch.empty_like(fl)
+        t = _timed(torch, lambda: lib.call("memc_b200_flow_projection_forward", st, FB, H, W, 1, S(fl), S(cnt), S(prj), P(fl),
+                                           P(cnt), P(prj), lib.OVERWRITE))
+        tl = None
+        if have_ref:
+            def l_fp():
+                cnt.zero_(); prj.zero_()
+                ref.gpu_flow_projection_forward(fl, 1, (cnt, prj))
+            tl = _timed(torch, l_fp, 3)
+        entry("FlowProjection splat + hole-fill 1920x1080, batch 16, %s flow" % kind, FB * H * W, 20, t, tl)
+        if kind == "smooth":
+            go_, gi_ = torch.randn_like(fl), torch.empty_like(fl)
+            t = _timed(torch, lambda: lib.call("memc_b200_flow_projection_backward", st, FB, H, W, S(fl), S(cnt), S(go_), S(gi_),
+                                               P(fl), P(cnt), P(go_), P(gi_), lib.OVERWRITE))
+            tl = None
+            if have_ref:
+                def l_fpb():
+                    gi_.zero_()
+                    ref.gpu_flow_projection_backward(fl, cnt, go_, gi_)
+                tl = _timed(torch, l_fpb, 3)
+            entry("FlowProjection backward 1920x1080, batch 16", FB * H * W, 28, t, tl)
+            del go_, gi_
+        del fl, cnt, prj
+    torch.cuda.empty_cache()
+
+    # --- the 64-channel context warp of MEMC_Net_star, forward and backward
+    c_in, c_flow, c_filt, c_go = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
+    c_out = torch.empty_like(c_in)
+    t = _timed(torch, lambda: lib.call("memc_b200_filter_interpolation_forward", st, 1, 64, H, W, FS, S(c_in), S(c_flow), S(c_filt),
+                                       S(c_out), P(c_in), P(c_flow), P(c_filt), P(c_out), lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        def l_c64():
+            c_out.zero_()
+            ref.gpu_filter_interpolation_forward(c_in, c_flow, c_filt, c_out)
+        tl = _timed(torch, l_c64, 3)
+    entry("FilterInterpolation forward 1920x1080, C=64 context features, batch 1", H * W, (2 * 64 + 18) * 4, t, tl)
+    cg = [torch.empty_like(c_in), torch.empty_like(c_flow), torch.empty_like(c_filt)]
+    t = _timed(torch, lambda: lib.call("memc_b200_filter_interpolation_backward", st, 1, 64, H, W, FS, S(c_in), S(c_flow), S(c_filt),
+                                       S(c_go), S(cg[0]), S(cg[1]), S(cg[2]), P(c_in), P(c_flow), P(c_filt), P(c_go),
+                                       P(cg[0]), P(cg[1]), P(cg[2]), lib.OVERWRITE), 5)
+    tl = None
+    if have_ref:
+        def l_c64b():
+            for x in cg:
+                x.zero_()
+            ref.gpu_filter_interpolation_backward(c_in, c_flow, c_filt, c_go, cg)
+        tl = _timed(torch, l_c64b, 3)
+    entry("FilterInterpolation backward 1920x1080, C=64 context features, batch 1", H * W, (3 * 64 + 36) * 4, t, tl)
+    del c_in, c_flow, c_filt, c_go, c_out, cg
+    torch.cuda.empty_cache()
+
+    # --- fused call site: two warps + occlusion blend (networks/MEMC_Net.py:258-264)
+    in1b, flowb, filtb, _ = synth.filter_interpolation_case(B, C, H, W, FS, seed=7, device=dev)
+    occ = [torch.rand(B, 1, H, W, device=dev) for _ in range(2)]
+    t = _timed(torch, lambda: lib.call("memc_b200_filter_interpolation_blend_forward", st, B, C, H, W, FS, S(in1), S(flow), S(filt),
+                                       S(in1b), S(flowb), S(filtb), S(occ[0]), S(occ[1]), S(out), P(in1), P(flow), P(filt),
+                                       P(in1b), P(flowb), P(filtb), P(occ[0]), P(occ[1]), P(out), lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        w0, w1 = torch.empty_like(in1), torch.empty_like(in1)
+
+        def l_blend():
+            w0.zero_(); w1.zero_()
+            ref.gpu_filter_interpolation_forward(in1, flow, filt, w0)
+            ref.gpu_filter_interpolation_forward(in1b, flowb, filtb, w1)
+            return occ[0] * w0 + occ[1] * w1
+        tl = _timed(torch, l_blend, 3)
+        del w0, w1
+    entry("fused FilterInterpolate (two warps + occlusion blend) 1920x1080, batch 4", B * H * W,
+          (2 * (C + 2 + FS * FS) + 2 + C) * 4, t, tl)
+    del in1b, flowb, filtb, occ
+
+    # --- Interpolation (plain bilinear warp) and SeparableConv, forward and backward
+    t = _timed(torch, lambda: lib.call("memc_b200_interpolation_forward", st, B, C, H, W, S(in1), S(flow), S(out),
+                                       P(in1), P(flow), P(out), lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        def l_ip():
+            out.zero_()
+            ref.gpu_interpolation_forward(in1, flow, out)
+        tl = _timed(torch, l_ip, 3)
+    entry("Interpolation forward 1920x1080, C=3, batch 4", B * H * W, (2 * C + 2) * 4, t, tl)
+    t = _timed(torch, lambda: lib.call("memc_b200_interpolation_backward", st, B, C, H, W, S(in1), S(flow), S(gout), S(g1), S(g2),
+                                       P(in1), P(flow), P(gout), P(g1), P(g2), lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        def l_ipb():
+            g1.zero_(); g2.zero_()
+            ref.gpu_interpolation_backward(in1, flow, gout, (g1, g2))
+        tl = _timed(torch, l_ipb, 3)
+    entry("Interpolation backward 1920x1080, C=3, batch 4", B * H * W, (3 * C + 4) * 4, t, tl)
+    sfs = 4
+    Ho, Wo = H - sfs + 1, W - sfs + 1
+    sv, sh_ = torch.randn(B, sfs, Ho, Wo, device=dev), torch.randn(B, sfs, Ho, Wo, device=dev)
+    so, sgo = torch.empty(B, C, Ho, Wo, device=dev), torch.randn(B, C, Ho, Wo, device=dev)
+    sg = [torch.empty_like(in1), torch.empty_like(sv), torch.empty_like(sh_)]
+    t = _timed(torch, lambda: lib.call("memc_b200_separable_conv_forward", st, B, C, H, W, sfs, S(in1), S(sv), S(sh_), S(so),
+                                       P(in1), P(sv), P(sh_), P(so), lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        def l_sc():
+            so.zero_()
+            ref.gpu_separable_conv_forward(in1, sv, sh_, so)
+        tl = _timed(torch, l_sc, 3)
+    entry("SeparableConv forward 1920x1080, C=3, fs=4, batch 4", B * Ho * Wo, (2 * C + 2 * sfs) * 4, t, tl)
+    t = _timed(torch, lambda: lib.call("memc_b200_separable_conv_backward", st, B, C, H, W, sfs, S(in1), S(sv), S(sh_), S(sgo),
+                                       S(sg[0]), S(sg[1]), S(sg[2]), P(in1), P(sv), P(sh_), P(sgo), P(sg[0]), P(sg[1]), P(sg[2]),
+                                       lib.OVERWRITE))
+    tl = None
+    if have_ref:
+        def l_scb():
+            for x in sg:
+                x.zero_()
+            ref.gpu_separable_conv_backward(in1, sv, sh_, sgo, sg)
+        tl = _timed(torch, l_scb, 3)
+    entry("SeparableConv backward 1920x1080, C=3, fs=4, batch 4", B * Ho * Wo, (3 * C + 4 * sfs) * 4, t, tl)
+    return other, (legacy if have_ref else {"unavailable": "oracle/_ref/libmemc_ref_gpu.so did not travel"})
+
+
+def networks_leg(torch, dist, dev, rank, world):
+    """BASELINE configs[3] / configs[4]: the reference's own MEMC_Net_s (720p frames, padded 1344x768 like
+    demo_HD720p.py) and MEMC_Net_star (1080p, padded 1984x1152), random init, inference, frames sharded over the
+    ranks (4 resp. 8 frame pairs per GPU = batch 32 / 64 on 8 GPUs).  The SAME network object runs on this
+    my_package and on the reference's kernels (oracle/refnet.py): frames/s of both, max-abs and PSNR between them."""
+    try:
+        from oracle import ref, refnet
+        if not (refnet.available() and ref.available_gpu()):
+            return {"unavailable": "reference networks / kernels not staged (make -C oracle ref)"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+    rows = []
+    for name, per_gpu, hh, ww, micro in (("MEMC_Net_s", 4, 768, 1344, 4), ("MEMC_Net_star", 8, 1152, 1984, 2)):
+        net = refnet.build_network(name, seed=0, device=dev, motion=4.0)
+        frames = refnet.synthetic_frames(per_gpu, hh, ww, seed=1 + rank, device=dev)   # this rank's shard
+
+        def run(impl):
+            outs = []
+            for k in range(0, per_gpu, micro):
+                outs.append(refnet.run(net, frames[:, k:k + micro].contiguous(), impl)["rectified"])
+            return torch.cat(outs, 0)
+
+        res, times = {}, {}
+        for impl in ("ours", "ref"):
+            run(impl)                                   # warm-up (cuDNN autotune, allocator)
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res[impl] = run(impl)
+            e1.record()
+            torch.cuda.synchronize()
+            times[impl] = e0.elapsed_time(e1) * 1e-3
+        cmp_ = refnet.compare(res["ours"], res["ref"])
+        tt = torch.tensor([times["ours"], times["ref"], cmp_["max_abs"], -cmp_["psnr_db"]], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_o, t_r, mx, npsnr = (float(x) for x in tt.tolist())
+        rows.append({"network": name, "frame": "%dx%d" % (ww, hh), "frame_pairs_per_gpu": per_gpu, "global_batch": per_gpu * world,
+                     "frames_per_s": per_gpu * world / t_o, "frames_per_s_reference_kernels": per_gpu * world / t_r,
+                     "speedup_whole_network": t_r / t_o, "max_abs_vs_reference_kernels": mx, "psnr_db_vs_reference_kernels": -npsnr,
+                     "output_range": cmp_["range"], "weights": "random init (torch.manual_seed(0)), eval, no_grad"})
+        del net, frames, res
+        torch.cuda.empty_cache()
+    return rows
+
+
 # ------------------------------------------------------------------------------- ours
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -195,6 +431,8 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (this package has no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from memc_b200.host_pipeline import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: NUMA-local staging buffers per rank
     lib.load()
     distributed = world > 1
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -295,28 +533,59 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop()
         clocks["window"] = "warm-up + timed steps + e2e steps (+ identical untimed steps up to 1.5 s)"
 
-    # ---- optional exchange: all-gather of the output batch over NCCL / NVLink, timed ALONE
-    # after the timed region -- the path itself has no data-path collective (frames are independent)
-    t_gather = None
+    # ---- the exchange SURVEY section 8(e) names: an all-gather of the OUTPUT batch over NCCL / NVLink.  The path itself
+    # has no data-path collective (frames are independent), so `value` above is compute only; here the same step is
+    # timed (ii) with the gather issued frame by frame on NCCL's stream while the next frame computes, and (iii) the
+    # gather of the whole batch alone.
+    t_gather = t_with = None
+    n_with = max(3, min(args.steps, 50))
     if distributed:
-        bufs = [torch.empty_like(out) for _ in range(world)]
+        flat = torch.empty(world * out.numel(), device=dev)
         for _ in range(2):
-            dist.all_gather(bufs, out)
+            dist.all_gather_into_tensor(flat, out.view(-1))
         barrier()
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0.record()
         for _ in range(5):
-            dist.all_gather(bufs, out)
+            dist.all_gather_into_tensor(flat, out.view(-1))
         q1.record()
         torch.cuda.synchronize()
         t_gather = q0.elapsed_time(q1) * 1e-3 / 5
-        del bufs
+        del flat
+        fbufs = [torch.empty(world * out[0].numel(), device=dev) for _ in range(B)]
+        fr = [tuple(t[f:f + 1] for t in (in1, flow, filt, gout, out, g1, g2, g3)) for f in range(B)]
+
+        def step_with_gather():
+            works = []
+            for f in range(B):
+                a1, a2, a3, ag, ao, b1, b2, b3 = fr[f]
+                lib.call("memc_b200_filter_interpolation_forward", st, 1, C, H, W, FS, S(a1), S(a2), S(a3), S(ao),
+                         P(a1), P(a2), P(a3), P(ao), lib.OVERWRITE)
+                works.append(dist.all_gather_into_tensor(fbufs[f], ao.view(-1), async_op=True))  # NCCL stream; compute goes on
+                b1.zero_()
+                lib.call("memc_b200_filter_interpolation_backward", st, 1, C, H, W, FS, S(a1), S(a2), S(a3), S(ag),
+                         S(b1), S(b2), S(b3), P(a1), P(a2), P(a3), P(ag), P(b1), P(b2), P(b3), FL)
+            for w_ in works:
+                w_.wait()
+
+        for _ in range(3):
+            step_with_gather()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(n_with):
+            step_with_gather()
+        q1.record()
+        torch.cuda.synchronize()
+        t_with = q0.elapsed_time(q1) * 1e-3 / n_with
+        barrier()
+        del fbufs
 
     # ---- max over ranks
     if distributed:
-        tt = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd], device=dev, dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd, t_gather, t_with], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, t_fwd, t_bwd = (float(x) for x in tt.tolist())
+        t_dev, t_e2e, t_fwd, t_bwd, t_gather, t_with = (float(x) for x in tt.tolist())
 
     px_step = B * H * W
     value = world * px_step * args.steps / t_dev / 1e6
@@ -335,12 +604,14 @@ def run_ours(args, rank, world, local_rank):
                    "flow": "smooth (sigma 6 px low-res field + 0.25 px jitter), softmax kernels"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": t_e2e * 1e3,
+                "ms_per_step": t_e2e * 1e3, "h2d_gbs_per_rank": h2d / t_e2e / 1e9, "d2h_gbs_per_rank": d2h / t_e2e / 1e9,
+                "numa": numa,
                 "api": "memc_b200.host_pipeline.FilterInterpolationHostPipeline (my_package Module + autograd, "
                        "one stream per frame, batches back to back)"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "FilterInterpolation backward", "bound": "hbm", "achieved": ach_b, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic.get("fi_bwd_bytes_per_launch"),
+                     "traffic_source": "profiles/traffic.json: dram__bytes_read+write of one ncu --set full capture of this kernel on this workload",
                      "bytes_per_launch": px_step * BYTES_BWD, "ms_per_launch": t_bwd * 1e3},
         "roofline_fwd": {"kernel": "FilterInterpolation forward", "bound": "hbm", "achieved": ach_f, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_f / peak, "traffic": traffic.get("fi_fwd_bytes_per_launch"),
@@ -348,52 +619,30 @@ def run_ours(args, rank, world, local_rank):
                          "mpx_s_per_gpu": px_step / t_fwd / 1e6},
     }
 
-    # ---- the other ops of the hot path (SURVEY section 8 rows a3-a7, the C = 64 context warp, the fused call
-    # site), one line each: device-timed like `value`, inputs far larger than L2, rank 0 at N = 1 only
+    # ---- the other ops of the hot path (SURVEY section 8 rows a3-a11, the C = 64 context warp, the fused call
+    # sites), one line each: device-timed like `value`, inputs far larger than L2, rank 0 at N = 1 only; next to
+    # them `legacy_gpu`: the reference's own kernels recompiled for sm_100a on the same inputs and harness
     if rank == 0 and world == 1 and not args.no_extra:
-        def timed(fn, n=10):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(n):
-                fn()
-            b_.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b_) * 1e-3 / n
-
-        def entry(name, px, bytes_px, t):
-            return {"op": name, "ms": t * 1e3, "mpx_s": px / t / 1e6, "alg_bytes_per_px": bytes_px,
-                    "gbs": px * bytes_px / t / 1e9, "frac": px * bytes_px / t / 1e9 / peak}
-
-        other = []
-        FB = 16
-        for kind, fl in (("smooth", synth.smooth_flow(FB, H, W, 6.0, seed=1, device=dev)),
-                         ("convergent (atomic-contention)", synth.radial_flow(FB, H, W, 0.9, device=dev))):
-            cnt, prj = torch.empty(FB, 1, H, W, device=dev), torch.empty_like(fl)
-            t = timed(lambda: lib.call("memc_b200_flow_projection_forward", st, FB, H, W, 1, S(fl), S(cnt), S(prj), P(fl),
-                                       P(cnt), P(prj), lib.OVERWRITE))
-            other.append(entry("FlowProjection splat + hole-fill 1920x1080, batch 16, %s flow" % kind, FB * H * W, 20, t))
-            del cnt, prj
-        c_in, c_flow, c_filt, _ = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
-        c_out = torch.empty_like(c_in)
-        t = timed(lambda: lib.call("memc_b200_filter_interpolation_forward", st, 1, 64, H, W, FS, S(c_in), S(c_flow), S(c_filt),
-                                   S(c_out), P(c_in), P(c_flow), P(c_filt), P(c_out), lib.OVERWRITE))
-        other.append(entry("FilterInterpolation forward 1920x1080, C=64 context features, batch 1", H * W, (2 * 64 + 18) * 4, t))
-        del c_in, c_flow, c_filt, c_out
-        in1b, flowb, filtb, _ = synth.filter_interpolation_case(B, C, H, W, FS, seed=7, device=dev)
-        occ = [torch.rand(B, 1, H, W, device=dev) for _ in range(2)]
-        t = timed(lambda: lib.call("memc_b200_filter_interpolation_blend_forward", st, B, C, H, W, FS, S(in1), S(flow), S(filt),
-                                   S(in1b), S(flowb), S(filtb), S(occ[0]), S(occ[1]), S(out), P(in1), P(flow), P(filt),
-                                   P(in1b), P(flowb), P(filtb), P(occ[0]), P(occ[1]), P(out), lib.OVERWRITE))
-        other.append(entry("fused FilterInterpolate (two warps + occlusion blend) 1920x1080, batch 4", B * H * W,
-                           (2 * (C + 2 + FS * FS) + 2 + C) * 4, t))
-        result["other_ops"] = other
+        result["other_ops"], result["legacy_gpu"] = other_ops_and_legacy(torch, lib, synth, dev, st, peak,
+                                                                         (in1, flow, filt, gout, out, g1, g2, g3))
+    if not args.no_networks:
+        nets = networks_leg(torch, dist if distributed else None, dev, rank, world)
+        if rank == 0 and nets is not None:
+            result["networks"] = nets
 
     if t_gather is not None:
-        result["output_allgather"] = {"ms": t_gather * 1e3, "bytes_per_rank": out.numel() * 4,
-                                      "note": "NCCL all-gather of the output batch, timed alone; not part of value"}
+        recv = (world - 1) * out.numel() * 4
+        result["value_with_gather"] = world * px_step / t_with / 1e6
+        result["gather"] = {
+            "what": "NCCL all_gather_into_tensor of the output batch [B,3,H,W] fp32 (SURVEY 8e)",
+            "bytes_sent_per_rank": out.numel() * 4, "bytes_received_per_rank": recv,
+            "alone_ms": t_gather * 1e3, "alone_gbs_received_per_rank": recv / t_gather / 1e9,
+            "alone_frac_of_nvlink5_900gbs": recv / t_gather / 1e9 / 900.0,
+            "with_gather_ms_per_step": t_with * 1e3, "compute_only_ms_per_step": t_dev / args.steps * 1e3,
+            "with_gather_steps": n_with,
+            "how": "per frame: forward -> all_gather_into_tensor(async_op=True) on NCCL's stream -> zero + backward; "
+                   "the step ends when every frame's gather has landed",
+            "gather_bound_ms_at_900gbs": recv / 900e9 * 1e3}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = cpu_threads()
@@ -414,7 +663,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extra", action="store_true", help="skip the other_ops lines")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_ops / legacy_gpu lines")
+    ap.add_argument("--no-networks", action="store_true", help="skip the reference-network leg (BASELINE configs[3]/[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

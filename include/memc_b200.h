@@ -13,7 +13,8 @@
  *        - all tensors fp32, 4-D NCHW, w-stride 1; strides are in ELEMENTS (int);
  *        - the caller owns every buffer and ZERO-FILLS every output / gradient buffer
  *          before the call; the library allocates nothing and frees nothing;
- *        - work is enqueued asynchronously on `stream`; no synchronisation;
+ *        - work is enqueued asynchronously on `stream`; no synchronisation; the launch goes to the device that
+ *          owns the operands (made current for the call and restored), `stream` must belong to it;
  *        - returns 0 on success, -1 on a launch failure or a layout the kernels cannot
  *          take (w-stride != 1);  `nElement` is accepted and ignored, as in the reference.
  *      Beyond the reference: batch/channel offsets are computed in 64 bits, so tensors
@@ -73,6 +74,10 @@ MEMC_B200_API const char *memc_b200_build_info(void);   /* "sm_100a nvcc <ver> .
 /* number of kernel launches (incl. memsets) the library has issued since load, for
  * bench.py's gpu_launches accounting */
 MEMC_B200_API unsigned long long memc_b200_launch_count(void);
+/* The only memory the library allocates is stream-ordered scratch from a private per-device pool (FlowProjection's
+ * accumulators / occupancy masks, the unfused blend fallback); up to 1 GiB stays cached between calls.  This hands
+ * all of it back to the driver.  0 = ok. */
+MEMC_B200_API int memc_b200_scratch_trim(void);
 
 /* ====================================================================================
  * (1) reference-named launchers

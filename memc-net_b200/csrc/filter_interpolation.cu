@@ -224,6 +224,8 @@ static int fi_forward(cudaStream_t stream, const FiArgs& a_in, int flags) {
     a.flags = flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     if (a.fs <= 0) return -1;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {
         const int r = fi_forward_fast(stream, a);
         if (r != 0) return r < 0 ? -1 : 0;
@@ -240,6 +242,8 @@ static int fi_backward(cudaStream_t stream, const FiArgs& a_in, int flags) {
     a.flags = flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
     if (a.fs <= 0) return -1;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     if (ow && !(flags & MEMC_B200_NO_ZERO) && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {
@@ -278,6 +282,8 @@ static int fi_blend_forward(cudaStream_t stream, const FiArgs& a0, const FiArgs&
                             const float* occ1, View v1, int flags) {
     if (a0.B <= 0 || a0.C <= 0 || a0.H <= 0 || a0.W <= 0) return 0;
     if (a0.fs <= 0) return -1;
+    DeviceGuard guard(a0.in1p);
+    if (!guard.ok) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {
         const int r = fi_blend_forward_fast(stream, a0, a1, occ0, v0, occ1, v1);
         if (r != 0) return r < 0 ? -1 : 0;

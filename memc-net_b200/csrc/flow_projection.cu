@@ -161,6 +161,8 @@ int fp_average_fill(cudaStream_t stream, const FpArgs& a, int b0, int nb, bool d
 
 static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    DeviceGuard guard(a.flowp);
+    if (!guard.ok) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     if (!(flags & MEMC_B200_NO_FAST)) {
         const int r = fp_forward_fast(stream, a, ow, (flags & MEMC_B200_NO_ZERO) != 0, (flags >> 16) & 0xff);
@@ -187,6 +189,8 @@ static int fp_forward(cudaStream_t stream, const FpArgs& a, int flags) {
 
 static int fp_backward(cudaStream_t stream, const FpArgs& a, int flags) {
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    DeviceGuard guard(a.flowp);
+    if (!guard.ok) return -1;
     dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + 2 * BY - 1) / (2 * BY), a.B);
     if (flags & MEMC_B200_OVERWRITE) fp_bwd_kernel<true><<<grid, block, 0, stream>>>(a);
     else fp_bwd_kernel<false><<<grid, block, 0, stream>>>(a);

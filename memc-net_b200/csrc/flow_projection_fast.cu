@@ -21,6 +21,7 @@
 //         all-zero vectors skipped).  Targets outside the box fall back to global atomics.
 #include "flow_projection.cuh"
 #include <limits.h>
+#include <mutex>
 
 namespace memc {
 
@@ -685,16 +686,31 @@ size_t pad32(size_t n) { return (n + 31) & ~(size_t)31; }
 int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
     const size_t smem = sizeof(Smem);
     if (!ensure_dynamic_smem(fp_pipeline_kernel, smem)) return 0;
-    int dev = 0, n_sm = 0, coop = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop || n_sm <= 0) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fp_pipeline_kernel, NT, smem) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        return 0;
+    // device properties and occupancy are looked up once per device (this sits on the launch-bound small-frame path)
+    struct DevInfo { int n_sm, per_sm; };
+    static DevInfo info[64] = {};
+    static std::mutex info_mutex;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    int n_sm, per_sm;
+    {
+        std::lock_guard<std::mutex> lock(info_mutex);
+        if (info[dev].n_sm == 0) {
+            int sm = 0, coop = 0, occ = 0;
+            cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            if (!coop || sm <= 0 ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_pipeline_kernel, NT, smem) != cudaSuccess || occ < 1) {
+                cudaGetLastError();
+                info[dev] = DevInfo{-1, 0};
+            } else {
+                info[dev] = DevInfo{sm, occ > 4 ? 4 : occ};
+            }
+        }
+        n_sm = info[dev].n_sm;
+        per_sm = info[dev].per_sm;
     }
-    per_sm = per_sm > 4 ? 4 : per_sm;
+    if (n_sm <= 0) return 0;
     const int64_t plane = (int64_t)a.H * a.W;
     FpPipe p;
     p.B = a.B; p.H = a.H; p.W = a.W; p.fillhole = a.fillhole;
@@ -725,11 +741,16 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
     count_launch();
     if (rc == 1) {
         void* args[] = {&p};
+        // a context with fewer SMs than the device (MPS thread percentage, green contexts) refuses the cooperative
+        // grid: not an error of the op -- hand the call to the frame-by-frame path (rc 0)
         if (cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fp_pipeline_kernel), dim3(n_sm * per_sm), dim3(NT), args,
-                                        smem, stream) != cudaSuccess)
-            rc = -1;
-        count_launch();
-        if (check_launch("FlowProjection forward (persistent pipeline)")) rc = -1;
+                                        smem, stream) != cudaSuccess) {
+            cudaGetLastError();
+            rc = 0;
+        } else {
+            count_launch();
+            if (check_launch("FlowProjection forward (persistent pipeline)")) rc = -1;
+        }
     }
     scratch_free(stream, blk);
     return rc;

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(BX* BY, 4) ip_bwd_kernel(const IpArgs p) {
 static int ip_forward(cudaStream_t stream, const IpArgs& a, int flags) {
     (void)flags;
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);
     if (a.C == 3) ip_fwd_kernel<3><<<grid, block, 0, stream>>>(a);
     else ip_fwd_kernel<0><<<grid, block, 0, stream>>>(a);
@@ -117,6 +119,8 @@ static int ip_forward(cudaStream_t stream, const IpArgs& a, int flags) {
 
 static int ip_backward(cudaStream_t stream, const IpArgs& a, int flags) {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return 0;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     if (ow && !(flags & MEMC_B200_NO_ZERO) && zero_fill(stream, a.gi1p, a.gi1, a.B, a.C, a.H, a.W) != 0) return -1;
     dim3 block(BX, BY, 1), grid((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);

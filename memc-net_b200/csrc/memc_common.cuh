@@ -31,8 +31,20 @@ static inline bool vec4_ok(View v, const void* p, int W) {
            ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
 }
 
-extern unsigned long long g_launches;  // memc_b200_launch_count()
-static inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+void count_launch(int n = 1);  // runtime.cu: atomic counter behind memc_b200_launch_count()
+
+// The launchers run on whatever device OWNS the operands, not on whatever device happens to be current: the
+// guard makes that device current for the duration of the call and restores the caller's on exit (a tensor on
+// cuda:1 with cuda:0 current would otherwise be launched on GPU 0 against GPU-1 pointers).  `ok` is false when
+// the pointer is not device memory (the entry points then return -1, as for any layout they cannot take).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false, ok = true;
+    explicit DeviceGuard(const void* ptr);
+    ~DeviceGuard();
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // reference convention: print and return -1 on a launch error (my_lib_kernel.cu:1558-1564)
 static inline int check_launch(const char* what) {

@@ -1,10 +1,41 @@
 // runtime.cu -- library info, launch accounting and the strided zero-fill used by the
 // MEMC_B200_OVERWRITE entry points.
 #include "memc_common.cuh"
+#include <atomic>
+#include <mutex>
 
 namespace memc {
 
-unsigned long long g_launches = 0;
+// Process-global state is limited to this file and is thread-safe: ctypes releases the GIL around every call, so
+// autograd's per-device worker threads, DataParallel replicas or a multi-threaded host pipeline may be inside the
+// library at the same time.
+static std::atomic<unsigned long long> g_launches{0};
+static std::mutex g_mutex;  // guards the smem-attribute table and the lazy creation of the scratch pools
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+DeviceGuard::DeviceGuard(const void* ptr) {
+    if (!ptr) return;  // empty tensors: nothing will be launched
+    cudaPointerAttributes attr;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaPointerGetAttributes(&attr, ptr) != cudaSuccess ||
+        (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        ok = false;
+        return;
+    }
+    if (attr.type == cudaMemoryTypeDevice && attr.device != prev) {
+        if (cudaSetDevice(attr.device) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            return;
+        }
+        switched = true;
+    }
+}
+
+DeviceGuard::~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+}
 
 __global__ void __launch_bounds__(256) zero_rows_kernel(float* p, View v, int C, int H, int W) {
     // grid: (ceil(W/256), H, B*C)
@@ -21,6 +52,7 @@ bool ensure_dynamic_smem_impl(const void* kernel, size_t bytes) {
     static int n_done = 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(g_mutex);
     for (int i = 0; i < n_done; ++i)
         if (done[i].fn == kernel && done[i].dev == dev) return true;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
@@ -50,14 +82,19 @@ int zero_fill(cudaStream_t stream, float* p, View v, int B, int C, int H, int W)
 }
 
 // Library-owned stream-ordered memory pool for scratch memory (FlowProjection's occupancy masks and
-// accumulator ring, the unfused fallback of the blend op).  A private pool with a high release
-// threshold keeps the blocks cached across calls; the device's default pool would hand them
-// back to the OS at every synchronisation (measured: 2 ms per call).  One pool per device,
-// created on first use.
+// accumulator ring, the unfused fallback of the blend op).  A private pool with a release threshold keeps the
+// blocks cached across calls; the device's default pool would hand them back to the OS at every
+// synchronisation (measured: 2 ms per call).  One pool per device, created on first use.  The pool keeps at most
+// kScratchKeepBytes cached between calls (a 4K batch can allocate more; the excess goes back to the driver at the
+// next synchronisation) and memc_b200_scratch_trim() releases everything.
+constexpr unsigned long long kScratchKeepBytes = 1ull << 30;
+static cudaMemPool_t g_pools[64] = {};
+
 static cudaMemPool_t scratch_pool() {
-    static cudaMemPool_t pools[64] = {};
+    cudaMemPool_t* pools = g_pools;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_mutex);
     if (!pools[dev]) {
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
@@ -69,7 +106,7 @@ static cudaMemPool_t scratch_pool() {
             cudaGetLastError();
             return nullptr;
         }
-        unsigned long long keep = ~0ull;
+        unsigned long long keep = kScratchKeepBytes;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         pools[dev] = pool;
     }
@@ -101,4 +138,15 @@ extern "C" const char* memc_b200_build_info(void) {
         __CUDACC_VER_BUILD__) " built " __DATE__;
 }
 
-extern "C" unsigned long long memc_b200_launch_count(void) { return memc::g_launches; }
+extern "C" unsigned long long memc_b200_launch_count(void) { return memc::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int memc_b200_scratch_trim(void) {
+    std::lock_guard<std::mutex> lock(memc::g_mutex);
+    int rc = 0;
+    for (int d = 0; d < 64; ++d)
+        if (memc::g_pools[d] && cudaMemPoolTrimTo(memc::g_pools[d], 0) != cudaSuccess) {
+            cudaGetLastError();
+            rc = -1;
+        }
+    return rc;
+}

@@ -233,6 +233,8 @@ static int sc_forward(cudaStream_t stream, const ScArgs& a, int flags) {
     if (a.fs <= 0) return -1;
     const int Ho = a.H - a.fs + 1, Wo = a.W - a.fs + 1;
     if (a.B <= 0 || a.C <= 0 || Ho <= 0 || Wo <= 0) return 0;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     dim3 block(BX, BY, 1), grid((Wo + BX - 1) / BX, (Ho + 2 * BY - 1) / (2 * BY), a.B);
     if (a.fs == 4) sc_fwd_kernel<4><<<grid, block, 0, stream>>>(a);
     else sc_fwd_kernel<0><<<grid, block, 0, stream>>>(a);
@@ -244,6 +246,8 @@ static int sc_backward(cudaStream_t stream, const ScArgs& a, int flags) {
     if (a.fs <= 0) return -1;
     const int Ho = a.H - a.fs + 1, Wo = a.W - a.fs + 1;
     if (a.B <= 0 || a.C <= 0 || Ho <= 0 || Wo <= 0) return 0;
+    DeviceGuard guard(a.in1p);
+    if (!guard.ok) return -1;
     const bool ow = (flags & MEMC_B200_OVERWRITE) != 0;
     dim3 block(BX, BY, 1);
     dim3 gout((Wo + BX - 1) / BX, (Ho + BY - 1) / BY, a.B), gin((a.W + BX - 1) / BX, (a.H + BY - 1) / BY, a.B);

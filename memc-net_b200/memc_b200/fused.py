@@ -49,7 +49,7 @@ def _fi_backward(in1, flow, filt, gout, fs):
     _lib.call("memc_b200_filter_interpolation_backward", _lib.stream_ptr(in1), B, C, H, W, fs, _lib.strides_of(in1),
               _lib.strides_of(flow), _lib.strides_of(filt), _lib.strides_of(gout), _lib.strides_of(g1), _lib.strides_of(g2),
               _lib.strides_of(g3), _lib.ptr(in1), _lib.ptr(flow), _lib.ptr(filt), _lib.ptr(gout), _lib.ptr(g1),
-              _lib.ptr(g2), _lib.ptr(g3), _lib.OVERWRITE)
+              _lib.ptr(g2), _lib.ptr(g3), _lib.fi_backward_flags())
     return g1, g2, g3
 
 
@@ -60,6 +60,7 @@ class _FilterInterpolateBlend(Function):
                                           ("ref0", "offset[0]", "filter[0]", "occlusion[0]", "ref2", "offset[1]",
                                            "filter[1]", "occlusion[1]"))]
         ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ts
+        _lib.check_same_device(*ts)
         B, C, H, W = ref0.shape
         ok = (ref1.shape == ref0.shape and flow0.shape == (B, 2, H, W) == flow1.shape and filt0.shape == filt1.shape and
               filt0.shape[0] == B and filt0.shape[2:] == (H, W) and occ0.shape == (B, 1, H, W) == occ1.shape)
@@ -99,7 +100,14 @@ def FlowProjectPair(flow_a, flow_b, requires_grad=None):
     from my_package.functions.FlowProjectionLayer import FlowProjectionLayer
     if flow_a.shape != flow_b.shape:
         raise _lib.MemcB200Error("FlowProjectPair: shapes differ %s %s" % (tuple(flow_a.shape), tuple(flow_b.shape)))
-    rg = (flow_a.requires_grad or flow_b.requires_grad) if requires_grad is None else requires_grad
+    _lib.check_same_device(flow_a, flow_b)
+    if requires_grad is None and flow_a.requires_grad != flow_b.requires_grad:
+        # the reference decides fill-hole PER DIRECTION (FlowProjectionModule(input.requires_grad)): one fused call
+        # cannot honour two different answers, so the pair is run as the two separate calls it stands for
+        return FlowProjectionLayer(flow_a.requires_grad)(flow_a), FlowProjectionLayer(flow_b.requires_grad)(flow_b)
+    rg = flow_a.requires_grad if requires_grad is None else requires_grad
+    # (the concatenation copies both inputs once: 16 B/px on top of the op's 20 B/px; pass one [2B,2,H,W] tensor to
+    # FlowProjectionLayer directly to avoid it)
     both = FlowProjectionLayer(rg)(torch.cat((_lib.check_tensor(flow_a, "flow_a"), _lib.check_tensor(flow_b, "flow_b")), dim=0))
     B = flow_a.size(0)
     return both[:B], both[B:]

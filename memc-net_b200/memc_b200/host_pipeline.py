@@ -13,9 +13,44 @@ stream, so the first upload of the next batch overlaps the last download of this
 frames otherwise costs B + 1 transfer slots: nothing to download during the first upload, nothing
 to upload during the last download); call `pipe.join()` before reading the host results.
 """
+import os
+
 import torch
 
 from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and so its first-touch page placement, incl. the pinned staging buffers allocated
+    afterwards) to the CPUs of the NUMA node the GPU hangs off.  One process per GPU is the deployment model
+    (torchrun); without this every rank's pinned buffers can land on one socket and all H2D / D2H traffic of an
+    8-GPU box crosses the inter-socket link (profiles/r02_scaling.md).  Returns a dict describing what was done;
+    never raises (a container may hide /sys or forbid sched_setaffinity)."""
+    info = {"device": int(device_index), "numa_node": None, "cpus": None, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        bdf = "%04x:%02x:%02x.0" % (dom, bus, dev)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        info["pci"] = bdf
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+            info["bound"] = True
+    except Exception as e:  # noqa: BLE001
+        info["error"] = repr(e)[:120]
+    return info
 
 
 class FilterInterpolationHostPipeline(object):

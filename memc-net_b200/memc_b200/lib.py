@@ -24,6 +24,30 @@ def variant(n):
 
 _lib = None
 
+# How FilterInterpolation backward accumulates gradinput1 inside a tile (include/memc_b200.h):
+#   "fixed"  per-tile int32 fixed point: every contribution rounded to <= 2^-22 x the tile's largest contribution
+#            (order independent, the speed path; absolute error of gradinput1 ~4e-6 on the benchmark workload)
+#   "float"  fp32 shared-memory atomics (MEMC_B200_FLOAT_ACCUM): keeps fp32 RELATIVE precision when gradient
+#            magnitudes inside one 32x8 tile differ by many orders (masked / occlusion-weighted losses); slower
+# Default from the environment variable MEMC_B200_FI_ACCUM, read once at import; set_fi_accumulation() at run time.
+_fi_accum = os.environ.get("MEMC_B200_FI_ACCUM", "fixed").strip().lower()
+
+
+def set_fi_accumulation(mode):
+    global _fi_accum
+    if mode not in ("fixed", "float"):
+        raise ValueError("accumulation mode must be 'fixed' or 'float', got %r" % (mode,))
+    _fi_accum = mode
+
+
+def get_fi_accumulation():
+    return "float" if _fi_accum == "float" else "fixed"
+
+
+def fi_backward_flags():
+    """Flags the autograd Functions pass to memc_b200_filter_interpolation_backward."""
+    return OVERWRITE | (FLOAT_ACCUM if _fi_accum == "float" else 0)
+
 
 class MemcB200Error(RuntimeError):
     pass
@@ -64,7 +88,7 @@ _NAMED = {
     "SeparableConvLayer_gpu_backward_kernel": [_P] + [_I] * 6 + [_I] * 16 + [_P] * 7,
 }
 EXPORTS = sorted(list(_EXTENDED) + list(_NAMED) +
-                 ["memc_b200_abi_version", "memc_b200_build_info", "memc_b200_launch_count"])
+                 ["memc_b200_abi_version", "memc_b200_build_info", "memc_b200_launch_count", "memc_b200_scratch_trim"])
 
 
 def load():
@@ -84,12 +108,18 @@ def load():
     lib.memc_b200_abi_version.restype = ctypes.c_int
     lib.memc_b200_build_info.restype = ctypes.c_char_p
     lib.memc_b200_launch_count.restype = ctypes.c_ulonglong
+    lib.memc_b200_scratch_trim.restype = ctypes.c_int
     _lib = lib
     return lib
 
 
 def launch_count():
     return int(load().memc_b200_launch_count())
+
+
+def scratch_trim():
+    """Release the library's cached scratch memory (stream-ordered pool) back to the driver."""
+    return int(load().memc_b200_scratch_trim())
 
 
 def build_info():
@@ -107,6 +137,13 @@ def check_tensor(t, name, ndim=4):
     if t.dim() != ndim:
         raise MemcB200Error("%s: must be %d-D (NCHW), got %d-D" % (name, ndim, t.dim()))
     return t
+
+
+def check_same_device(*tensors):
+    """Every operand of one call must live on ONE device (the library launches on the device that owns them)."""
+    devs = {t.device for t in tensors if isinstance(t, torch.Tensor)}
+    if len(devs) > 1:
+        raise MemcB200Error("operands are on different devices: %s" % sorted(str(d) for d in devs))
 
 
 def strides_of(t):

@@ -34,6 +34,7 @@ class _FlowProjectionFunction(Function):
     def backward(ctx, gradoutput, _gradcount):
         input1, count = ctx.saved_tensors
         gradoutput = prep(gradoutput, "gradoutput")
+        _lib.check_same_device(gradoutput, input1)
         B, _, H, W = input1.shape
         gi = torch.empty_like(input1)
         fast_call("memc_b200_flow_projection_backward", _lib.stream_ptr(input1), B, H, W,

@@ -14,6 +14,7 @@ class _InterpolationFunction(Function):
     @staticmethod
     def forward(ctx, input1, input2):
         input1, input2 = prep(input1, "input1"), prep(input2, "input2")
+        _lib.check_same_device(input1, input2)
         B, C, H, W = input1.shape
         if input2.shape != (B, 2, H, W):
             raise _lib.MemcB200Error("Interpolation: flow must be [B,2,H,W]")
@@ -28,6 +29,7 @@ class _InterpolationFunction(Function):
     def backward(ctx, gradoutput):
         input1, input2 = ctx.saved_tensors
         gradoutput = prep(gradoutput, "gradoutput")
+        _lib.check_same_device(gradoutput, *ctx.saved_tensors)
         B, C, H, W = input1.shape
         gi1, gi2 = torch.empty_like(input1), torch.empty_like(input2)
         fast_call("memc_b200_interpolation_backward", _lib.stream_ptr(input1), B, C, H, W,

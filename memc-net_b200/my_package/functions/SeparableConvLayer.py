@@ -16,6 +16,7 @@ class _SeparableConvFunction(Function):
     @staticmethod
     def forward(ctx, input1, input2, input3, filtersize):
         input1, input2, input3 = prep(input1, "input1"), prep(input2, "input2"), prep(input3, "input3")
+        _lib.check_same_device(input1, input2, input3)
         B, C, H, W = input1.shape
         fs = min(input2.size(1), input3.size(1))
         Ho, Wo = min(input2.size(2), input3.size(2)), min(input2.size(3), input3.size(3))
@@ -38,6 +39,7 @@ class _SeparableConvFunction(Function):
     def backward(ctx, gradoutput):
         input1, input2, input3 = ctx.saved_tensors
         gradoutput = prep(gradoutput, "gradoutput")
+        _lib.check_same_device(gradoutput, *ctx.saved_tensors)
         B, C, H, W = input1.shape
         gi1, gi2, gi3 = torch.empty_like(input1), torch.empty_like(input2), torch.empty_like(input3)
         fast_call("memc_b200_separable_conv_backward", _lib.stream_ptr(input1), B, C, H, W, ctx.fs,

@@ -669,3 +669,28 @@ def test_cuda_path_matches_golden_fixtures(L):
             out = torch.zeros(*z["out"].shape, device="cuda")
             assert my_lib.SeparableConvLayer_gpu_forward(t1, t2, t3, out) == 0
             close(out, z["out"], what=path)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_run_on_the_device_that_owns_the_tensors(L):
+    """tensors on cuda:1 while cuda:0 is current -- the library makes the owning device current for the
+    call (DeviceGuard in runtime.cu) and restores the caller's; results equal the same call made on cuda:0."""
+    from memc_b200 import synth
+    from my_package.modules.FilterInterpolationModule import FilterInterpolationModule
+    from my_package.modules.FlowProjectionModule import FlowProjectionModule
+    torch.cuda.set_device(0)
+    in1, flow, filt, gout = synth.filter_interpolation_case(2, 3, 96, 128, seed=3, device="cuda:0")
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        t1, t2, t3 = (t.to(d).requires_grad_() for t in (in1, flow, filt))
+        o = FilterInterpolationModule()(t1, t2, t3)
+        g = torch.autograd.grad(o, (t1, t2, t3), gout.to(d))
+        with torch.no_grad():
+            pr = FlowProjectionModule(False)(torch.cat([flow.to(d)] * 2, 0))   # B = 4: persistent pipeline
+        torch.cuda.synchronize(d)
+        assert torch.cuda.current_device() == 0
+        outs.append([x.cpu() for x in (o.detach(), *g, pr)])
+    for a, b in zip(*outs):
+        assert float((a - b).abs().max()) <= TOL
+    with pytest.raises(L.MemcB200Error):
+        FilterInterpolationModule()(in1, flow.to("cuda:1"), filt)

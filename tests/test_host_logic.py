@@ -104,3 +104,27 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
                 assert "liboracle" not in src and "libmemc_ref" not in src, os.path.join(dirpath, f)
+
+
+def test_fi_accumulation_mode_is_exposed(built_lib):
+    """training code can choose fp32 accumulation of gradinput1 (run time or MEMC_B200_FI_ACCUM)."""
+    from memc_b200 import lib
+    assert lib.get_fi_accumulation() in ("fixed", "float")
+    old = lib.get_fi_accumulation()
+    try:
+        lib.set_fi_accumulation("float")
+        assert lib.fi_backward_flags() == lib.OVERWRITE | lib.FLOAT_ACCUM
+        lib.set_fi_accumulation("fixed")
+        assert lib.fi_backward_flags() == lib.OVERWRITE
+        with pytest.raises(ValueError):
+            lib.set_fi_accumulation("double")
+    finally:
+        lib.set_fi_accumulation(old)
+
+
+def test_operands_must_share_a_device():
+    from memc_b200 import lib
+    a, b = torch.zeros(1, device="cpu"), torch.zeros(1, device="meta")
+    with pytest.raises(lib.MemcB200Error):
+        lib.check_same_device(a, b)
+    lib.check_same_device(a, a)
