@@ -201,7 +201,9 @@ MEMC_B200_API int memc_b200_filter_interpolation_backward(
  * `FilterInterpolate`):
  *     output = occlusion_0 * FilterInterpolation(input1_0, flow_0, filter_0)
  *            + occlusion_1 * FilterInterpolation(input1_1, flow_1, filter_1)
- * occlusion_k is [B,1,H,W] (broadcast over the channels); every element of `output` is written
+ * occlusion_k is [B,1,H,W] (broadcast over the channels); passing NULL for BOTH maps means the constant 0.5, i.e.
+ * the plain mean `warp0 / 2 + warp1 / 2` of networks/MEMC_Net_s.py:260-264 (exact: halving is exact in fp32);
+ * every element of `output` is written
  * (OVERWRITE semantics whatever `flags` says); bit-identical to the composition of
  * memc_b200_filter_interpolation_forward and the fp32 blend.  fs == 4, C == 3 take one fused
  * kernel; anything else is composed inside the library (two warps into stream-ordered scratch). */

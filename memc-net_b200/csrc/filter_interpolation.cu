@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(256) fi_blend_kernel(const float* __restrict__
                                                        View v1, float* __restrict__ out, View vo, int C, int H, int W) {
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
-    const float a0 = __ldg(occ0 + b * v0.b + (int64_t)y * v0.h + x), a1 = __ldg(occ1 + b * v1.b + (int64_t)y * v1.h + x);
+    const float a0 = occ0 ? __ldg(occ0 + b * v0.b + (int64_t)y * v0.h + x) : 0.5f;
+    const float a1 = occ1 ? __ldg(occ1 + b * v1.b + (int64_t)y * v1.h + x) : 0.5f;
     const int64_t plane = (int64_t)H * W;
     for (int c = 0; c < C; ++c) {
         const int64_t i = ((int64_t)b * C + c) * plane + (int64_t)y * W + x;  // the warps are dense scratch tensors
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) fi_blend_kernel(const float* __restrict__
 static int fi_blend_forward(cudaStream_t stream, const FiArgs& a0, const FiArgs& a1, const float* occ0, View v0,
                             const float* occ1, View v1, int flags) {
     if (a0.B <= 0 || a0.C <= 0 || a0.H <= 0 || a0.W <= 0) return 0;
-    if (a0.fs <= 0) return -1;
+    if (a0.fs <= 0 || (occ0 == nullptr) != (occ1 == nullptr)) return -1;  // both maps or neither (= the mean)
     DeviceGuard guard(a0.in1p);
     if (!guard.ok) return -1;
     if (!(flags & MEMC_B200_NO_FAST)) {

@@ -695,8 +695,8 @@ fi_blend_patch_kernel(const __grid_constant__ CUtensorMap m_flow0, const __grid_
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int x = x0 + SWD * warp + lxx, y = y0 + 4 * k + lyy;
-        o0[k] = o1[k] = 0.f;
-        if (x < p0.W && y < p0.H) {
+        o0[k] = o1[k] = 0.5f;  // no occlusion maps: the plain mean of MEMC_Net_s (networks/MEMC_Net_s.py:260-264)
+        if (bl.occ0p && x < p0.W && y < p0.H) {
             o0[k] = ldg_stream(bl.occ0p + b * bl.occ0.b + (int64_t)y * bl.occ0.h + x);
             o1[k] = ldg_stream(bl.occ1p + b * bl.occ1.b + (int64_t)y * bl.occ1.h + x);
         }
@@ -1146,6 +1146,7 @@ using BWD_DEFAULT = BwdF;
 }  // namespace
 
 int fi_backward_rows(cudaStream_t stream, const FiArgs& a, bool overwrite);  // filter_interpolation_bwd_rows.cu
+int fi_forward_cols(cudaStream_t stream, const FiArgs& a, int lanes_per_pixel);  // filter_interpolation_fwd_cols.cu
 
 // Kernel selection.  `variant` = MEMC_B200_VARIANT field of the call's flags: 0 is production, the others keep
 // earlier kernels reachable for A/B measurements (tools/kbench.py) and cross-checks in the tests.
@@ -1154,6 +1155,10 @@ int fi_forward_fast(cudaStream_t stream, const FiArgs& a) {
     if (a.fs != 4 || a.C < 1 || a.W % 4 || a.B > 65535) return 0;
     if (a.C > CB)  // e.g. the 64-channel context warps of MEMC_Net_star: channel-chunked kernel
         return variant == 1 ? 0 : launch_fwd_chunked<FwdK3>(stream, a);
+    if (variant == 3 || variant == 4) {  // (pixel, tap column) lanes: 2 / 4 lanes per pixel
+        const int r = fi_forward_cols(stream, a, variant == 3 ? 2 : 4);
+        if (r != 0) return r;
+    }
     switch (a.C) {
         case 1: return launch_fwd<1, FWD_DEFAULT>(stream, a);
         case 2: return launch_fwd<2, FWD_DEFAULT>(stream, a);

@@ -196,5 +196,28 @@ inline bool make_map_taps(CUtensorMap* map, const float* base, int B, int H, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The same [B,16,H,W] tap tensor for (pixel, tap COLUMN) lanes working on groups of gx x 2 pixels (forward):
+//     dims (W, y&1, i, 4 b + j, y>>1), strides (sh, sc, 4 sc, 2 sh), box (gx, 2, 4, 4, bh/2)
+// lands as [y>>1][j][i][y&1][x]: for one tap row j the words of (i, y&1, x) are 8 gx consecutive words.
+// Folding the batch into the j digit needs dense plane batches (sb == 16 sc) and an even H.
+inline bool make_map_taps_cols(CUtensorMap* map, const float* base, int B, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                               int gx, int bh, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+    if (H % 2 || bh % 2 || (B > 1 && sb != 16 * sc)) return false;
+    if (sh % 4 || sc % 4 || sh < W || sc <= 0) return false;
+    if (gx > 256 || bh > 512 || (gx * 4) % 16) return false;
+    const cuuint64_t gdim[5] = {(cuuint64_t)W, 2u, 4u, (cuuint64_t)4 * B, (cuuint64_t)(H / 2)};
+    const cuuint64_t gstr[4] = {(cuuint64_t)sh * 4, (cuuint64_t)sc * 4, (cuuint64_t)sc * 16, (cuuint64_t)sh * 8};
+    for (int i = 0; i < 4; ++i)
+        if (gstr[i] >= (1ull << 40)) return false;
+    const cuuint32_t box[5] = {(cuuint32_t)gx, 2u, 4u, 4u, (cuuint32_t)(bh / 2)};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace tma
 }  // namespace memc

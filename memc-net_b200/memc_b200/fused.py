@@ -12,6 +12,10 @@ paths NEXT TO the unchanged `my_package` API.
 networks/MEMC_Net_star.py:272-278 (their sixth argument `filter_size2` is unused there and optional
 here), so a network can rebind it:  `MEMC_Net.FilterInterpolate = staticmethod(fused.FilterInterpolate)`.
 
+`FilterInterpolateMean(ref0, ref2, offset, filter)` is the same call site in networks/MEMC_Net_s.py:258-264, where the two
+warps are averaged instead of occlusion-blended (`ref0_offset / 2.0 + ref2_offset / 2.0`): the same fused kernel with
+the constant weight 0.5 (no occlusion maps are read).
+
 `FlowProjectPair` runs both directions as ONE FlowProjection call on the concatenated batch (frames are
 independent, so each half equals the separate call; with 2 x B >= 3 frames the persistent pipeline has twice the
 frames to overlap), and returns the two halves as views.
@@ -56,31 +60,43 @@ def _fi_backward(in1, flow, filt, gout, fs):
 class _FilterInterpolateBlend(Function):
     @staticmethod
     def forward(ctx, ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1):
-        ts = [_prep(t, n) for t, n in zip((ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1),
-                                          ("ref0", "offset[0]", "filter[0]", "occlusion[0]", "ref2", "offset[1]",
-                                           "filter[1]", "occlusion[1]"))]
+        mean = occ0 is None  # FilterInterpolateMean: constant weights 0.5, no occlusion maps
+        ts = [None if t is None else _prep(t, n) for t, n in zip(
+            (ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1),
+            ("ref0", "offset[0]", "filter[0]", "occlusion[0]", "ref2", "offset[1]", "filter[1]", "occlusion[1]"))]
         ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ts
         _lib.check_same_device(*ts)
         B, C, H, W = ref0.shape
         ok = (ref1.shape == ref0.shape and flow0.shape == (B, 2, H, W) == flow1.shape and filt0.shape == filt1.shape and
-              filt0.shape[0] == B and filt0.shape[2:] == (H, W) and occ0.shape == (B, 1, H, W) == occ1.shape)
+              filt0.shape[0] == B and filt0.shape[2:] == (H, W) and
+              (mean or occ0.shape == (B, 1, H, W) == occ1.shape))
         if not ok:
-            raise _lib.MemcB200Error("FilterInterpolate: inconsistent shapes " + " ".join(str(tuple(t.shape)) for t in ts))
+            raise _lib.MemcB200Error("FilterInterpolate: inconsistent shapes " +
+                                     " ".join(str(tuple(t.shape)) for t in ts if t is not None))
         fs = int(math.sqrt(float(filt0.size(1))))  # my_lib_cuda.c:619-620
         out = torch.empty_like(ref0)
         S, P = _lib.strides_of, _lib.ptr
+        null, s0 = _lib.ctypes.c_void_p(None), _lib.Strides(0, 0, 0)
         _lib.call("memc_b200_filter_interpolation_blend_forward", _lib.stream_ptr(ref0), B, C, H, W, fs,
-                  S(ref0), S(flow0), S(filt0), S(ref1), S(flow1), S(filt1), S(occ0), S(occ1), S(out),
-                  P(ref0), P(flow0), P(filt0), P(ref1), P(flow1), P(filt1), P(occ0), P(occ1), P(out), _lib.OVERWRITE)
-        ctx.save_for_backward(*ts)
+                  S(ref0), S(flow0), S(filt0), S(ref1), S(flow1), S(filt1), s0 if mean else S(occ0), s0 if mean else S(occ1),
+                  S(out), P(ref0), P(flow0), P(filt0), P(ref1), P(flow1), P(filt1), null if mean else P(occ0),
+                  null if mean else P(occ1), P(out), _lib.OVERWRITE)
+        ctx.mean = mean
+        ctx.save_for_backward(*(t for t in ts if t is not None))
         ctx.fs = fs
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ctx.saved_tensors
         gout = _prep(gout, "gradoutput")
         grads = []
+        if ctx.mean:
+            ref0, flow0, filt0, ref1, flow1, filt1 = ctx.saved_tensors
+            half = (gout * 0.5).contiguous()
+            for ref, flow, filt in ((ref0, flow0, filt0), (ref1, flow1, filt1)):
+                grads += list(_fi_backward(ref, flow, filt, half, ctx.fs)) + [None]
+            return tuple(grads)
+        ref0, flow0, filt0, occ0, ref1, flow1, filt1, occ1 = ctx.saved_tensors
         for ref, flow, filt, occ in ((ref0, flow0, filt0, occ0), (ref1, flow1, filt1, occ1)):
             warp = _fi_forward(ref, flow, filt, ctx.fs)                      # recomputed, not stored
             g_occ = (gout * warp).sum(dim=1, keepdim=True)                   # d(occ * warp) / d occ
@@ -92,6 +108,11 @@ class _FilterInterpolateBlend(Function):
 def FilterInterpolate(ref0, ref2, offset, filter, occlusion, filter_size2=None):  # noqa: A002 (reference's names)
     """Drop-in for the networks' static method (networks/MEMC_Net.py:258-264)."""
     return _FilterInterpolateBlend.apply(ref0, offset[0], filter[0], occlusion[0], ref2, offset[1], filter[1], occlusion[1])
+
+
+def FilterInterpolateMean(ref0, ref2, offset, filter, filter_size2=None):  # noqa: A002 (reference's names)
+    """Drop-in for MEMC_Net_s.FilterInterpolate (networks/MEMC_Net_s.py:258-264): the mean of the two warps."""
+    return _FilterInterpolateBlend.apply(ref0, offset[0], filter[0], None, ref2, offset[1], filter[1], None)
 
 
 def FlowProjectPair(flow_a, flow_b, requires_grad=None):

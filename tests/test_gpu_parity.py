@@ -198,6 +198,15 @@ def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
     torch.cuda.synchronize()
     for o in outs[:-1]:
         assert torch.equal(o, outs[-1])
+    # (pixel, tap column) lanes, 2 and 4 lanes per pixel: the partial sums of a pixel meet in butterfly shuffles,
+    # so the result differs from the generic kernel by the summation order of 16 products only
+    for var in (3, 4):
+        o = torch.empty_like(t1)
+        L.call("memc_b200_filter_interpolation_forward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(o), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(o),
+               L.OVERWRITE | L.variant(var))
+        torch.cuda.synchronize()
+        assert float((o - outs[-1]).abs().max()) <= 2e-6, "variant %d" % var
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0),
@@ -401,6 +410,59 @@ def test_fused_filter_interpolate_equals_composition(L, shape):
     assert torch.equal(fused_out, comp), "fused forward must be bit-identical to the composition"
     for a, b, name in zip(fused_grads, comp_grads, ["ref0", "ref2", "off0", "off1", "filt0", "filt1", "occ0", "occ1"]):
         close(a, host(b), tol=2e-5, what="fused grad " + name)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 96, 128, 4, 4.0), (1, 3, 70, 132, 4, 10.0), (1, 5, 40, 100, 5, 3.0)])
+@pytest.mark.parametrize("mean", [False, True])
+def test_fused_call_sites_vs_oracle_composition(L, shape, mean):
+    """The fused call sites against the ORACLE's composition (not this repo's own Modules): the C oracle (pinned to
+    the reference's my_lib.c) warps both references, numpy blends them like networks/MEMC_Net.py:258-264
+    (occlusion weights) or networks/MEMC_Net_s.py:258-264 (plain mean); gradients of the references / flows / filters
+    against the oracle's backward fed with the blended gradient."""
+    from memc_b200 import fused
+    B, C, H, W, fs, sigma = shape
+    cases = [fi_case(B, C, H, W, fs, sigma, seed=80 + k) for k in range(2)]
+    rng = np.random.default_rng(5)
+    occs = [(0.5 + 0.3 * rng.standard_normal((B, 1, H, W))).astype(np.float32) for _ in range(2)]
+    gout = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    r = [dev(c[0]).requires_grad_() for c in cases]
+    o = [dev(c[1]).requires_grad_() for c in cases]
+    f = [dev(c[2]).requires_grad_() for c in cases]
+    if mean:
+        out = fused.FilterInterpolateMean(r[0], r[1], o, f, fs * fs)
+        wts = [np.float32(0.5), np.float32(0.5)]
+    else:
+        out = fused.FilterInterpolate(r[0], r[1], o, f, [dev(x) for x in occs], fs * fs)
+        wts = occs
+    warps = [cpu.filter_interpolation_forward(c[0], c[1], c[2], "f64") for c in cases]
+    close(out, wts[0] * warps[0] + wts[1] * warps[1], what="fused forward vs oracle composition")
+    grads = torch.autograd.grad(out, r + o + f, dev(gout))
+    for k in range(2):
+        e1, e2, e3 = cpu.filter_interpolation_backward(cases[k][0], cases[k][1], cases[k][2], (gout * wts[k]).astype(np.float32), "f64")
+        close(grads[k], e1, tol=2e-5, what="grad ref%d" % k)
+        close(grads[2 + k], e2, tol=2e-5, what="grad offset%d" % k)
+        close(grads[4 + k], e3, tol=2e-5, what="grad filter%d" % k)
+
+
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_fused_flow_project_pair_vs_oracle(L, fillhole):
+    """fused.FlowProjectPair against the oracle run on each direction separately (count exact, fill-hole incl.)."""
+    from memc_b200 import fused, synth
+    B, H, W = 2, 96, 160
+    fa, fb = synth.smooth_flow(B, H, W, 5.0, seed=1, device="cuda"), synth.tear_flow(B, H, W, 8.0, seed=2, device="cuda")
+    if fillhole:
+        with torch.no_grad():
+            pa, pb = fused.FlowProjectPair(fa, fb)
+    else:
+        pa, pb = fused.FlowProjectPair(fa.requires_grad_(), fb.requires_grad_())
+    for got, src in ((pa, fa), (pb, fb)):
+        eo, _ = cpu.flow_projection_forward(host(src), fillhole, "f64")
+        close(got, eo, what="FlowProjectPair vs oracle")
+    # mixed requires_grad: the reference decides fill-hole per direction (ADVICE r1)
+    fa2, fb2 = fa.detach().clone().requires_grad_(), fb.detach().clone()
+    qa, qb = fused.FlowProjectPair(fa2, fb2)
+    close(qa, cpu.flow_projection_forward(host(fa2), 0, "f64")[0], what="pair: direction with grad is not hole-filled")
+    close(qb, cpu.flow_projection_forward(host(fb2), 1, "f64")[0], what="pair: direction without grad is hole-filled")
 
 
 @pytest.mark.parametrize("B", [1, 3])

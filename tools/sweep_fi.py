@@ -41,8 +41,10 @@ for cfg in [int(c) for c in args.fwd.split(",") if c != ""]:
         fl = lib.OVERWRITE | lib.variant(cfg)
         o = run_fwd(fl); torch.cuda.synchronize()
         ok = bool(torch.equal(o, ref_o))
+        err = float((o - ref_o).abs().max())
         t = timeit(lambda: run_fwd(fl), args.iters)
-        r = {"op": "fwd", "cfg": cfg, "ms": t * 1e3, "frac": px * 96 / t / 1e9 / peak, "bitwise_equal_generic": ok}
+        r = {"op": "fwd", "cfg": cfg, "ms": t * 1e3, "frac": px * 96 / t / 1e9 / peak, "bitwise_equal_generic": ok,
+             "max_abs_vs_generic": err}
     except Exception as e:
         r = {"op": "fwd", "cfg": cfg, "error": str(e)[:200]}
     rows.append(r); print(json.dumps(r), flush=True)
