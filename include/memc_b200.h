@@ -63,9 +63,10 @@ typedef void *memc_stream_t; /* a cudaStream_t */
 #define MEMC_B200_NO_ZERO 4
 #define MEMC_B200_FLOAT_ACCUM 8
 /* bits 16..23: kernel variant, 0 = production.  Non-zero values keep earlier kernels reachable for A/B
- * measurements and for the tests' cross-checks (FilterInterpolation forward: 1 row segments, 2 patches with a
- * TMA-staged output; backward: 1 the round-1 one-pixel-per-lane kernel; FlowProjection forward: 1 frame-by-frame
- * launches instead of the persistent pipeline).  Nothing in the library reads environment variables. */
+ * measurements and for the tests' cross-checks (FilterInterpolation forward, C <= 4: 1 row segments, 2 patches with
+ * a TMA-staged output; C > 4: 1 generic kernel, 2 the round-1 patch kernel; backward: 1 the round-1
+ * one-pixel-per-lane kernel, 2-4 other tile shapes; FlowProjection forward: 1 frame-by-frame launches instead of the
+ * persistent pipeline).  Nothing in the library reads environment variables. */
 #define MEMC_B200_VARIANT(n) (((n) & 0xff) << 16)
 
 /* ---- library info ------------------------------------------------------------------ */

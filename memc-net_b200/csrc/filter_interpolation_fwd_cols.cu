@@ -1,24 +1,21 @@
-// filter_interpolation_fwd_cols.cu -- FilterInterpolation forward for sm_100a, fs = 4, C <= 4:
-// the "tap-column lanes" kernel (round 2; reference semantics my_lib_kernel.cu:1087-1218).
+// filter_interpolation_fwd_cols.cu -- FilterInterpolation forward for sm_100a, fs = 4, C > 4 (the 64-channel context
+// features MEMC_Net_star warps with the RGB frames' flow and filter, networks/MEMC_Net_star.py:280-285; reference
+// semantics my_lib_kernel.cu:1087-1218): "tap-column lanes", channel-chunked.
 //
-// The round-1 forward (one pixel per lane, 8x4 pixel patches) sits on the L1 / shared-memory data pipe: 130
-// wavefronts per 32 pixels, 46 of them bank-conflict replays of the 48 image-tap loads, because a warp's 32
-// windows spread over ~11 x 6 source cells that are not a permutation of the banks
-// (profiles/r01_ncu_bench_fi_fwd.txt).  Shared-memory LOADS broadcast: lanes that read the SAME word cost
-// nothing extra.  So the lanes of a warp are made to overlap on purpose:
+//   lane = (pixel of an 8 x 2 pixel group, tap column r in {0, 1}): the 2 lanes of a pixel own the columns r, r + 2 of
+//   its 4x4 window and walk the 4 tap rows together.  Shared-memory LOADS broadcast, and neighbouring pixels' windows
+//   overlap in 3 of 4 columns, so a warp instruction touches ~20 distinct words instead of 32: with a row pitch of
+//   72 words (= 8 mod 32) the measured conflict factor of the tap loads is 1.59 against 1.96 for one pixel per lane
+//   (profiles/r02_fi_lane_roles.md has the model and the measurements of the other lane maps that were built).
 //
-//   lane = (pixel of a GX x 2 pixel group, tap COLUMN r): the NL lanes of a pixel own the columns r, r + NL, ...
-//   of its 4x4 window and walk the 4 tap rows together.  Neighbouring pixels' windows overlap in 3 of 4 columns,
-//   so one warp instruction touches ~14-20 distinct words instead of 32, and with a row pitch of 72 words
-//   (= 8 mod 32) rows r, r + 1 of the box are 8 banks apart.  Modelled on the benchmark field
-//   (tools/bank_model.py --roles): 18.4 (NL = 4, 4x2 groups) / 25.0 (NL = 2, 8x2 groups) wavefronts per 32 pixels
-//   and channel against 31.4 for 8x4 patches; the partial sums of a pixel's lanes meet in 1-2 butterfly shuffles.
-//
-// The NL lanes of a pixel read NL different filter planes of the same pixel at once: the filter tile comes through
-// a rank-5 tensor map that splits the plane index into (tap row j, tap column i) and the image row into
-// (y >> 1, y & 1) (tma::make_map_taps_cols): a strip of GX pixels lands as [y>>1][j][i][y&1][x] and a warp's filter
-// read is 32 consecutive words.  Geometry is evaluated once per pixel and handed to the pixel's lanes with shuffles;
-// every tap of a lane is then a compile-time offset from one shared-memory base address.
+// The 2 lanes of a pixel read 2 different filter planes of the same pixel at once: the filter tile comes through a
+// rank-5 tensor map that splits the plane index into (tap row j, tap column i) and the image row into (y >> 1, y & 1)
+// (tma::make_map_taps_cols): a strip of 8 pixels lands as [y>>1][j][i][y&1][x] and a warp's filter read is 32
+// consecutive words.  Geometry is evaluated once per pixel and handed to the pixel's lanes with shuffles; the filter
+// taps are pre-multiplied with their quadrant's bilinear weight and stay in registers while the image streams through
+// a ring of 4-channel boxes; every tap is one LDS at a compile-time offset plus one FMA; the channel sums of a chunk
+// are reduced TRANSPOSED over the pixel's lanes (2 shuffles per 4 channels) and each lane stores 2 channels
+// (full 32-byte sectors).  The ring needs no block-wide barrier: the last warp to finish a box refills it.
 #include "filter_interpolation.cuh"
 #include "tma_utils.cuh"
 
@@ -26,25 +23,8 @@ namespace memc {
 
 namespace {
 
-constexpr int TW = 32, TH = 8, NT = 128;  // 4 warps; warp w owns tile rows 2w, 2w + 1
-constexpr int SW = 72, SH = 22;           // image box: pitch 72 words (= 8 mod 32), 22 rows, one TMA load
-
-template <int C, int NL_>
-struct Lay {
-    static constexpr int NL = NL_;            // lanes per pixel
-    static constexpr int GX = 16 / NL;        // group width (pixels); groups are GX x 2
-    static constexpr int PXS = 2 * GX;        // pixels per warp step
-    static constexpr int NSTEP = 64 / PXS;    // steps per warp (= strips per tile)
-    static constexpr int NK = 4 / NL;         // tap columns per lane: r, r + NL, ...
-    static constexpr int STRIP = TH * 16 * GX;  // floats per filter strip [y>>1][j][i][y&1][x]
-    static constexpr int JBLK = 8 * GX;       // floats per (y>>1, j) block: [i][y&1][x]
-    static constexpr int CH = SH * SW;        // channel stride inside the box (words)
-    static constexpr int OFF_FLOW = 16 * TH * TW * 4;
-    static constexpr int OFF_BAR = OFF_FLOW + 2 * TH * TW * 4;
-    static constexpr int OFF_IMG = OFF_BAR + 128;
-    static constexpr int TOTAL = OFF_IMG + C * CH * 4;
-    static_assert(NL == 2 || NL == 4, "2 or 4 lanes per pixel");
-};
+constexpr int TW = 32;  // tile width
+constexpr int SW = 72;  // image box pitch: 72 words (= 8 mod 32)
 
 // per-pixel geometry in the owner lane: code >= 0 fast ((ly << 8) | lx), -1 per-tap path, -2 invalid flow (copy the
 // input pixel, my_lib_kernel.cu:1209-1213), -3 outside the image
@@ -53,44 +33,67 @@ struct PxGeo {
     float alpha, beta;
 };
 
-template <int C, int NL>
-__global__ void __launch_bounds__(NT, 6)
-fi_fwd_cols_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                   const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
-    using Y = Lay<C, NL>;
-    constexpr int GX = Y::GX, PXS = Y::PXS, NSTEP = Y::NSTEP, NK = Y::NK;
+// ------------------------------------------------------------------------------------
+// C > 4 (the 64-channel context features MEMC_Net_star warps with the same flow / filter,
+// networks/MEMC_Net_star.py:280-285): same lanes, the image streams through a two-box ring of 4-channel boxes
+// while the lane's filter taps, bilinear coefficients and box offsets stay in registers.  Here the tap loads are
+// everything (16 per channel and pixel against 16 + 2 per pixel for filter and flow), so the conflict factor of
+// the lane map is the run time: 1.15 (4 lanes per pixel) / 1.56 (2) against 1.96 for the round-1 patches.
+// The partial sums of a chunk's 4 channels are reduced TRANSPOSED over the pixel's lanes (3 resp. 2 shuffles per
+// chunk instead of 8 / 4): each lane ends up with the total of the channel(s) it then stores.
+// ------------------------------------------------------------------------------------
+constexpr int KTH = 16, KSH = 32;  // tile rows (8 warps x 2 rows), box rows
+
+// NL lanes per pixel, CBK channels per streamed box, NBUF boxes in the ring
+template <int NL_, int CBK_, int NBUF_>
+struct LayK {
+    static constexpr int NL = NL_, CBK = CBK_, NBUF = NBUF_, GX = 16 / NL, PXS = 2 * GX, NSTEP = 64 / PXS, NK = 4 / NL;
+    static constexpr int STRIP = KTH * 16 * GX, JBLK = 8 * GX;
+    static constexpr int CH = KSH * SW, BOX = CBK * CH;  // words
+    static constexpr int OFF_FLOW = 16 * KTH * TW * 4;
+    static constexpr int OFF_BAR = OFF_FLOW + 2 * KTH * TW * 4;
+    static constexpr int OFF_IMG = OFF_BAR + 128;
+    static constexpr int TOTAL = OFF_IMG + NBUF * BOX * 4;
+    static_assert(CBK == 2 || CBK == 4, "2 or 4 channels per box");
+};
+
+template <class Y>
+__global__ void __launch_bounds__(256, 2)
+fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
+                           const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
+    constexpr int NL = Y::NL, CBK = Y::CBK, NBUF = Y::NBUF, GX = Y::GX, PXS = Y::PXS, NSTEP = Y::NSTEP, NK = Y::NK;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    const float* s_filt = reinterpret_cast<const float*>(sm);               // NSTEP strips
-    const float* s_flow = reinterpret_cast<const float*>(sm + Y::OFF_FLOW);  // [2][TH][TW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Y::OFF_BAR);           // 0 flow, 1 filter, 2 image
-    int* s_bb = reinterpret_cast<int*>(bars + 3);
-    const float* s_img = reinterpret_cast<const float*>(sm + Y::OFF_IMG);
+    const float* s_filt = reinterpret_cast<const float*>(sm);
+    const float* s_flow = reinterpret_cast<const float*>(sm + Y::OFF_FLOW);  // [2][KTH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Y::OFF_BAR);           // 0 flow, 1 filter, 2.. image ring
+    int* s_bb = reinterpret_cast<int*>(bars + 2 + NBUF);
+    int* s_done = s_bb + 4;  // [NBUF] warps that have finished with a ring buffer
+    unsigned char* const sm_img0 = sm + Y::OFF_IMG;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-    const int W = p.W, H = p.H;
-    const int px = lane % GX, py = (lane / GX) & 1, r = lane / PXS;  // this lane's role inside a step
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * KTH, b = blockIdx.z;
+    const int W = p.W, H = p.H, C = p.C;
+    const int nchunk = (C + CBK - 1) / CBK;
+    const int px = lane % GX, py = (lane / GX) & 1, r = lane / PXS;
 
     if (tid == 0) {
-        for (int k = 0; k < 3; ++k) tma::mbar_init(&bars[k], 1);
+        for (int k = 0; k < 2 + NBUF; ++k) tma::mbar_init(&bars[k], 1);
+        for (int k = 0; k < NBUF; ++k) s_done[k] = 0;
         s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
         tma::fence_barrier_init();
     }
     __syncthreads();
     if (tid == 0) {
-        tma::mbar_expect_tx(&bars[0], 2 * TH * TW * 4);
+        tma::mbar_expect_tx(&bars[0], 2 * KTH * TW * 4);
         tma::load_4d(sm + Y::OFF_FLOW, &m_flow, x0, y0, 0, b, &bars[0]);
-        tma::mbar_expect_tx(&bars[1], 16 * TH * TW * 4);
+        tma::mbar_expect_tx(&bars[1], 16 * KTH * TW * 4);
 #pragma unroll
         for (int s = 0; s < NSTEP; ++s)
             tma::load_5d(sm + s * Y::STRIP * 4, &m_filt, x0 + GX * s, 0, 0, 4 * b, y0 >> 1, &bars[1]);
     }
-
-    // ---- geometry once per pixel.  The warp's 64 pixels (2 rows) are spread over the lanes so that the PXS pixels
-    // of step s sit in PXS different lanes under the same register index: lane l owns, for k = 0, 1, the pixel
-    // (px, py) of step 2 (l / PXS) + k.
-    tma::mbar_wait(&bars[0], 0, 31);
+    // ---- geometry once per pixel (lane l owns, for k = 0, 1, the pixel (px, py) of step 2 (l / PXS) + k)
+    tma::mbar_wait(&bars[0], 0, 41);
     PxGeo me[2];
     bool me_valid[2];
     {
@@ -99,7 +102,7 @@ fi_fwd_cols_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
         for (int k = 0; k < 2; ++k) {
             const int s = 2 * (lane / PXS) + k;
             const int xl = GX * s + px, yl = 2 * warp + py;
-            const FiGeom geo = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * TW + xl], s_flow[(TH + yl) * TW + xl]);
+            const FiGeom geo = fi_geometry(x0 + xl, y0 + yl, W, H, s_flow[yl * TW + xl], s_flow[(KTH + yl) * TW + xl]);
             const bool inside = x0 + xl < W && y0 + yl < H;
             me_valid[k] = geo.valid && inside;
             me[k].ix = geo.ix; me[k].iy = geo.iy; me[k].alpha = geo.alpha; me[k].beta = geo.beta;
@@ -117,158 +120,187 @@ fi_fwd_cols_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
         }
     }
     __syncthreads();
-    const bool any_valid = s_bb[0] <= s_bb[1];
     int bx = 0, by = 0;
-    if (any_valid) {
-        // windows span [min ix - 1, max ix + 2] x [min iy - 1, max iy + 2]; a span larger than the box centres it (what
-        // it misses takes the per-tap path); x origin rounded down to 4 pixels (TMA: 16-byte coordinates); the box is
-        // kept inside the image, so a window inside the box needs no clamping
+    if (s_bb[0] <= s_bb[1]) {
         const int need_w = s_bb[1] - s_bb[0] + 4 + 3, need_h = s_bb[3] - s_bb[2] + 4;
         bx = s_bb[0] - 1;
         by = s_bb[2] - 1;
         if (need_w > SW) bx += (need_w - SW) / 2;
-        if (need_h > SH) by += (need_h - SH) / 2;
-        bx = max(0, min(bx, W - SW)) & ~3;  // W >= SW, H >= SH and W % 4 == 0 are launch preconditions
-        by = max(0, min(by, H - SH));
+        if (need_h > KSH) by += (need_h - KSH) / 2;
+        bx = max(0, min(bx, W - SW)) & ~3;  // W >= SW, H >= KSH and W % 4 == 0 are launch preconditions
+        by = max(0, min(by, H - KSH));
     }
-    if (tid == 0 && any_valid) {
-        tma::mbar_expect_tx(&bars[2], C * Y::CH * 4);
-        tma::load_4d(sm + Y::OFF_IMG, &m_img, bx, by, 0, b, &bars[2]);
+    if (tid == 0) {
+        for (int ch = 0; ch < NBUF && ch < nchunk; ++ch) {
+            tma::mbar_expect_tx(&bars[2 + ch], Y::BOX * 4);
+            tma::load_4d(sm_img0 + ch * Y::BOX * 4, &m_img, bx, by, ch * CBK, b, &bars[2 + ch]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (!me_valid[k]) continue;
         const int lx = me[k].ix - 1 - bx, ly = me[k].iy - 1 - by;
-        const bool fast = (unsigned)lx <= (unsigned)(SW - 4) && (unsigned)ly <= (unsigned)(SH - 4);
+        const bool fast = (unsigned)lx <= (unsigned)(SW - 4) && (unsigned)ly <= (unsigned)(KSH - 4);
         me[k].code = fast ? ((ly << 8) | lx) : -1;
     }
-    tma::mbar_wait(&bars[1], 0, 32);
-    if (any_valid) tma::mbar_wait(&bars[2], 0, 33);
+    tma::mbar_wait(&bars[1], 0, 42);
 
-    const float* in1b = p.in1p + b * p.in1.b;
-    const int y = y0 + 2 * warp + py;
-    float* const out_lane = p.outp + b * p.out.b + (int64_t)y * p.out.h + x0 + px;  // + GX s: this lane's pixel of step s
-    const float* const f_lane = s_filt + warp * 4 * Y::JBLK + lane;                 // + s STRIP + j JBLK + k 32: tap (j, r + NL k)
-    const float* const img_lane = s_img + r;                                        // + box offset of tap (0, 0) + NL k
+    // ---- per-step state of this lane, kept across the channel chunks: the box offset of its first tap and its
+    // filter taps PRE-MULTIPLIED with the bilinear weight of their quadrant, (1-a | a) x (1-b | b):
+    //     out = sum_taps v * (w * quadrant weight)        (one FMA per tap and channel, nothing else)
+    // st[s] >= 0: fast (box offset); -1: per-tap path; -2: invalid flow (copy the input pixel); -3: outside the image
+    int st[NSTEP];
+    float wv[NSTEP][NK][4];
+    bool any_slow = false;
 #pragma unroll
     for (int s = 0; s < NSTEP; ++s) {
         const int src = (s >> 1) * PXS + (lane & (PXS - 1));
         const int code = __shfl_sync(0xffffffffu, me[s & 1].code, src);
         const float a = __shfl_sync(0xffffffffu, me[s & 1].alpha, src), bt = __shfl_sync(0xffffffffu, me[s & 1].beta, src);
-        int Lc = 0, T = 0;
-        if (__builtin_expect(__any_sync(0xffffffffu, code == -1), 0)) {  // rare: someone needs full coordinates
-            Lc = __shfl_sync(0xffffffffu, me[s & 1].ix, src) - 1;
-            T = __shfl_sync(0xffffffffu, me[s & 1].iy, src) - 1;
-        }
-        const float* f = f_lane + s * Y::STRIP;
-        float sum[C];
+        st[s] = code >= 0 ? (code >> 8) * SW + (code & 255) + r : code;
+        any_slow |= code == -1;
+        const float* f = s_filt + s * Y::STRIP + warp * 4 * Y::JBLK + lane;
 #pragma unroll
-        for (int c = 0; c < C; ++c) sum[c] = 0.f;
-        if (__builtin_expect(code >= 0, 1)) {
-            // every tap of the lane is a compile-time offset from one base: no per-tap integer arithmetic
-            const float* base = img_lane + (code >> 8) * SW + (code & 255);
+        for (int k = 0; k < NK; ++k) {
+            const float cw = (NL == 2 ? k == 0 : r < 2) ? (1.0f - a) : a;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                float top[C], bot[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) top[c] = bot[c] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float w = f[j * Y::JBLK + k * 32];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float v = base[c * Y::CH + j * SW + NL * k];
-                        if (j < 2) top[c] = fmaf(v, w, top[c]);
-                        else bot[c] = fmaf(v, w, bot[c]);
-                    }
-                }
-                // column r + NL k belongs to the left (< 2) or right quadrants: (1 - alpha) / alpha; rows 0, 1: (1 - beta)
-                const float cw = (NL == 2 ? k == 0 : r < 2) ? (1.0f - a) : a;
-                const float wt_ = cw * (1.0f - bt), wb_ = cw * bt;
-#pragma unroll
-                for (int c = 0; c < C; ++c) sum[c] = fmaf(wt_, top[c], fmaf(wb_, bot[c], sum[c]));
+            for (int j = 0; j < 4; ++j) {
+                // a pixel that is not on the fast path reads box word 0 with weight 0 (the main loop is branch free);
+                // the rare per-tap path below fetches its taps again
+                const float w = f[j * Y::JBLK + k * 32] * (cw * (j < 2 ? 1.0f - bt : bt));
+                wv[s][k][j] = code >= 0 ? w : 0.f;
             }
-        } else if (code == -1) {
-            // window touches the image border or leaves the staged box: per-tap clamping, box or global source
+        }
+    }
+    any_slow = __any_sync(0xffffffffu, any_slow);
+
+    const float* in1b = p.in1p + b * p.in1.b;
+    const int y = y0 + 2 * warp + py;
+    // channel(s) of a chunk this lane ends up with after the transposed reduction
+    const int my_c = CBK == 2 ? (r & 1) : NL == 4 ? (((r & 1) << 1) | (r >> 1)) : 2 * r;
+    for (int ch = 0, buf = 0, par = 0; ch < nchunk; ++ch) {
+        const float* s_img = reinterpret_cast<const float*>(sm_img0 + buf * Y::BOX * 4);
+        tma::mbar_wait(&bars[2 + buf], par, 43);
+        const int c0 = ch * CBK;
+#pragma unroll
+        for (int s = 0; s < NSTEP; ++s) {
+            float sum[CBK];
+#pragma unroll
+            for (int c = 0; c < CBK; ++c) sum[c] = 0.f;
+            {
+                // branch free: straight-line loads + FMAs of all steps can be interleaved by the compiler
+                const float* base = s_img + max(st[s], 0);
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int c = 0; c < CBK; ++c) sum[c] = fmaf(base[c * Y::CH + j * SW + NL * k], wv[s][k][j], sum[c]);
+            }
+            if (__builtin_expect(any_slow, 0)) {  // warp-uniform: someone in this warp has a pixel on the per-tap path
+                const int src = (s >> 1) * PXS + (lane & (PXS - 1));
+                const int Lc = __shfl_sync(0xffffffffu, me[s & 1].ix, src) - 1, T = __shfl_sync(0xffffffffu, me[s & 1].iy, src) - 1;
+                const float a = __shfl_sync(0xffffffffu, me[s & 1].alpha, src), bt = __shfl_sync(0xffffffffu, me[s & 1].beta, src);
+                if (st[s] == -1) {
+                    const float* f = s_filt + s * Y::STRIP + warp * 4 * Y::JBLK + lane;
 #pragma unroll 1
-            for (int k = 0; k < NK; ++k) {
-                const int i = r + NL * k;
-                const int cx = clampi(Lc + i, 0, W - 1);
-                const int ux = cx - bx;
-                float top[C], bot[C];
+                    for (int k = 0; k < NK; ++k) {
+                        const int cx = clampi(Lc + r + NL * k, 0, W - 1);
+                        const int ux = cx - bx;
+                        const float cw = (NL == 2 ? k == 0 : r < 2) ? (1.0f - a) : a;
 #pragma unroll
-                for (int c = 0; c < C; ++c) top[c] = bot[c] = 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            const int cy = clampi(T + j, 0, H - 1);
+                            const int uy = cy - by;
+                            const bool in_box = (unsigned)uy < (unsigned)KSH && (unsigned)ux < (unsigned)SW;
+                            const float w = f[j * Y::JBLK + k * 32] * (cw * (j < 2 ? 1.0f - bt : bt));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float w = f[j * Y::JBLK + k * 32];
-                    const int cy = clampi(T + j, 0, H - 1);
-                    const int uy = cy - by;
-                    const bool in_box = (unsigned)uy < (unsigned)SH && (unsigned)ux < (unsigned)SW;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float v = in_box ? s_img[c * Y::CH + uy * SW + ux] : __ldg(in1b + c * p.in1.c + (int64_t)cy * p.in1.h + cx);
-                        if (j < 2) top[c] = fmaf(v, w, top[c]);
-                        else bot[c] = fmaf(v, w, bot[c]);
+                            for (int c = 0; c < CBK; ++c) {
+                                float v = 0.f;
+                                if (in_box) v = s_img[c * Y::CH + uy * SW + ux];
+                                else if (c0 + c < C) v = __ldg(in1b + (int64_t)(c0 + c) * p.in1.c + (int64_t)cy * p.in1.h + cx);
+                                sum[c] = fmaf(v, w, sum[c]);
+                            }
+                        }
                     }
                 }
-                const float cw = i < 2 ? (1.0f - a) : a;
-                const float wt_ = cw * (1.0f - bt), wb_ = cw * bt;
+            }
+            // transposed reduction over the NL lanes of the pixel (lanes PXS apart)
+            float mine0, mine1 = 0.f;
+            if (CBK == 4) {
+                const bool hi = NL == 4 ? (r & 1) : (r != 0);  // keeps channels 2, 3 of the chunk; sends 0, 1
+                const float k0 = hi ? sum[2 % CBK] : sum[0], k1 = hi ? sum[3 % CBK] : sum[1];
+                const float g0 = __shfl_xor_sync(0xffffffffu, hi ? sum[0] : sum[2 % CBK], NL == 4 ? 8 : 16);
+                const float g1 = __shfl_xor_sync(0xffffffffu, hi ? sum[1] : sum[3 % CBK], NL == 4 ? 8 : 16);
+                mine0 = k0 + g0;
+                mine1 = k1 + g1;
+                if (NL == 4) {
+                    const bool hi2 = (r & 2) != 0;  // keeps the second of its two channels
+                    const float g = __shfl_xor_sync(0xffffffffu, hi2 ? mine0 : mine1, 16);
+                    mine0 = (hi2 ? mine1 : mine0) + g;
+                }
+            } else {  // 2 channels per box: lane keeps channel r & 1
+                const bool hi = (r & 1) != 0;
+                mine0 = (hi ? sum[1] : sum[0]) + __shfl_xor_sync(0xffffffffu, hi ? sum[0] : sum[1], NL == 4 ? 8 : 16);
+                if (NL == 4) mine0 += __shfl_xor_sync(0xffffffffu, mine0, 16);
+            }
+            if (st[s] == -3) continue;  // outside the image
+            const int x = x0 + GX * s + px;
+            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
+            const float* inp = in1b + (int64_t)y * p.in1.h + x;
 #pragma unroll
-                for (int c = 0; c < C; ++c) sum[c] = fmaf(wt_, top[c], fmaf(wb_, bot[c], sum[c]));
+            for (int q = 0; q < (CBK == 4 && NL == 2 ? 2 : 1); ++q) {
+                const int c = c0 + my_c + q;
+                if (c >= C || (CBK == 2 && NL == 4 && r >= 2)) break;  // (2 channels over 4 lanes: lanes r, r ^ 2 hold the same total)
+                float v = q ? mine1 : mine0;
+                if (st[s] == -2) v = __ldg(inp + (int64_t)c * p.in1.c);  // my_lib_kernel.cu:1209-1213
+                stg_stream(outp + (int64_t)c * p.out.c, v);
             }
         }
-        // the NL lanes of a pixel are PXS lanes apart: butterfly over r
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], 16);
-            if (NL == 4) sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], 8);
+        // no block-wide barrier: the LAST warp to finish with this buffer refills it, nobody waits for anybody
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();  // this warp's reads of the buffer are ordered before the count
+            if (atomicAdd(&s_done[buf], 1) == 7) {
+                s_done[buf] = 0;
+                __threadfence_block();
+                if (ch + NBUF < nchunk) {
+                    tma::fence_proxy_async();
+                    tma::mbar_expect_tx(&bars[2 + buf], Y::BOX * 4);
+                    tma::load_4d(sm_img0 + buf * Y::BOX * 4, &m_img, bx, by, (ch + NBUF) * CBK, b, &bars[2 + buf]);
+                }
+            }
         }
-        float* outp = out_lane + GX * s;
-        if (__builtin_expect(code >= -1, 1)) {
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                if ((c % NL) == r) stg_stream(outp + c * p.out.c, sum[c]);  // lane r of the pixel writes channels r, r + NL, ...
-        } else if (code == -2) {  // my_lib_kernel.cu:1209-1213: an invalid flow copies the input pixel
-            const float* inp = in1b + (int64_t)y * p.in1.h + x0 + GX * s + px;
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                if ((c % NL) == r) stg_stream(outp + c * p.out.c, __ldg(inp + c * p.in1.c));
-        }
+        if (++buf == NBUF) { buf = 0; par ^= 1; }
     }
 }
 
-template <int C, int NL>
-int launch_cols(cudaStream_t stream, const FiArgs& a) {
-    using Y = Lay<C, NL>;
+template <class Y>
+int launch_cols_chunked(cudaStream_t stream, const FiArgs& a) {
+    constexpr int CBK = Y::CBK;
     CUtensorMap m[3];
-    if (!tma::make_map_nchw(&m[0], a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, TH, 2,
+    if (!tma::make_map_nchw(&m[0], a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, KTH, 2,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B) ||
-        !tma::make_map_taps_cols(&m[1], a.filtp, a.B, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, Y::GX, TH,
+        !tma::make_map_taps_cols(&m[1], a.filtp, a.B, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, Y::GX, KTH,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, SW, SH, a.C,
+        !tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, SW, KSH, CBK,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return 0;
     constexpr size_t smem = (size_t)Y::TOTAL + 128;
-    if (!ensure_dynamic_smem(fi_fwd_cols_kernel<C, NL>, smem)) return 0;
-    dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
-    fi_fwd_cols_kernel<C, NL><<<grid, NT, smem, stream>>>(m[0], m[1], m[2], a);
+    if (!ensure_dynamic_smem(fi_fwd_cols_chunked_kernel<Y>, smem)) return 0;
+    dim3 grid((a.W + TW - 1) / TW, (a.H + KTH - 1) / KTH, a.B);
+    fi_fwd_cols_chunked_kernel<Y><<<grid, 256, smem, stream>>>(m[0], m[1], m[2], a);
     count_launch();
-    return check_launch("FilterInterpolation forward (TMA, tap-column lanes)") == 0 ? 1 : -1;
+    return check_launch("FilterInterpolation forward (TMA, tap-column lanes, channel-chunked)") == 0 ? 1 : -1;
 }
 
 }  // namespace
 
-// 1 = handled, 0 = layout preconditions not met (caller falls back), -1 = launch error.  nl = lanes per pixel (2 / 4)
-int fi_forward_cols(cudaStream_t stream, const FiArgs& a, int nl) {
-    if (a.fs != 4 || a.C < 1 || a.C > 4 || a.W % 4 || a.H % 2 || a.B > 65535 || a.W < SW || a.H < SH) return 0;
+// C > 4 only.  1 = handled, 0 = layout preconditions not met (caller falls back), -1 = launch error
+int fi_forward_cols(cudaStream_t stream, const FiArgs& a) {
+    if (a.fs != 4 || a.C <= 4 || a.W % 4 || a.H % 2 || a.B > 65535 || a.W < SW || a.H < KSH) return 0;
     if (a.B > 1 && a.filt.b != 16 * a.filt.c) return 0;  // the tap map folds the batch into the plane index
-    switch (a.C) {
-        case 1: return nl == 4 ? launch_cols<1, 4>(stream, a) : launch_cols<1, 2>(stream, a);
-        case 2: return nl == 4 ? launch_cols<2, 4>(stream, a) : launch_cols<2, 2>(stream, a);
-        case 3: return nl == 4 ? launch_cols<3, 4>(stream, a) : launch_cols<3, 2>(stream, a);
-        case 4: return nl == 4 ? launch_cols<4, 4>(stream, a) : launch_cols<4, 2>(stream, a);
-    }
-    return 0;
+    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a);  // 2 lanes / pixel, 4 channels / box, 2 boxes: 110 KB, 2 CTAs / SM
 }
 
 }  // namespace memc

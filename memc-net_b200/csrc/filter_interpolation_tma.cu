@@ -1146,18 +1146,20 @@ using BWD_DEFAULT = BwdF;
 }  // namespace
 
 int fi_backward_rows(cudaStream_t stream, const FiArgs& a, bool overwrite);  // filter_interpolation_bwd_rows.cu
-int fi_forward_cols(cudaStream_t stream, const FiArgs& a, int lanes_per_pixel);  // filter_interpolation_fwd_cols.cu
+int fi_forward_cols(cudaStream_t stream, const FiArgs& a);  // filter_interpolation_fwd_cols.cu (C > 4)
 
 // Kernel selection.  `variant` = MEMC_B200_VARIANT field of the call's flags: 0 is production, the others keep
 // earlier kernels reachable for A/B measurements (tools/kbench.py) and cross-checks in the tests.
 int fi_forward_fast(cudaStream_t stream, const FiArgs& a) {
     const int variant = (a.flags >> 16) & 0xff;
     if (a.fs != 4 || a.C < 1 || a.W % 4 || a.B > 65535) return 0;
-    if (a.C > CB)  // e.g. the 64-channel context warps of MEMC_Net_star: channel-chunked kernel
-        return variant == 1 ? 0 : launch_fwd_chunked<FwdK3>(stream, a);
-    if (variant == 3 || variant == 4) {  // (pixel, tap column) lanes: 2 / 4 lanes per pixel
-        const int r = fi_forward_cols(stream, a, variant == 3 ? 2 : 4);
-        if (r != 0) return r;
+    if (a.C > CB) {  // e.g. the 64-channel context warps of MEMC_Net_star: channel-chunked kernels
+        if (variant == 1) return 0;   // generic kernel
+        if (variant != 2) {           // production: (pixel, tap column) lanes
+            const int r = fi_forward_cols(stream, a);
+            if (r != 0) return r;
+        }
+        return launch_fwd_chunked<FwdK3>(stream, a);  // round-1 kernel (8x4 patches); also the fallback
     }
     switch (a.C) {
         case 1: return launch_fwd<1, FWD_DEFAULT>(stream, a);

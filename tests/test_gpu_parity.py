@@ -196,17 +196,12 @@ def test_filter_interpolation_fast_path_equals_generic_bitwise(L, shape):
                L.strides_of(t2), L.strides_of(t3), L.strides_of(o), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(o), flags)
         outs.append(o)
     torch.cuda.synchronize()
-    for o in outs[:-1]:
+    for o in (outs[1:-1] if C > 4 else outs[:-1]):
         assert torch.equal(o, outs[-1])
-    # (pixel, tap column) lanes, 2 and 4 lanes per pixel: the partial sums of a pixel meet in butterfly shuffles,
-    # so the result differs from the generic kernel by the summation order of 16 products only
-    for var in (3, 4):
-        o = torch.empty_like(t1)
-        L.call("memc_b200_filter_interpolation_forward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
-               L.strides_of(t2), L.strides_of(t3), L.strides_of(o), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(o),
-               L.OVERWRITE | L.variant(var))
-        torch.cuda.synchronize()
-        assert float((o - outs[-1]).abs().max()) <= 2e-6, "variant %d" % var
+    # C > 4 production = (pixel, tap column) lanes: the partial sums of a pixel meet in shuffles and the taps are
+    # pre-multiplied with the bilinear weights, so it differs from the generic kernel by rounding order only
+    if C > 4:
+        assert float((outs[0] - outs[-1]).abs().max()) <= 2e-6
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 96, 128, 3.0), (1, 3, 270, 480, 6.0), (1, 3, 200, 324, 30.0), (2, 4, 64, 96, 1.0),

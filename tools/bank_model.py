@@ -13,6 +13,7 @@ pixels spaced `xstep` apart in x (xstep == 1: adjacent), optionally staggered by
 at one instruction the lane rows work on different sub-pixels.
 
   python tools/bank_model.py            # table for the candidate mappings / pitches
+  python tools/bank_model.py --roles    # round 2: lanes = (pixel, tap row / tap column) maps
 No GPU needed.  Results are summarised in profiles/r01_bank_conflict_model.md.
 """
 import argparse
@@ -77,8 +78,66 @@ def model(ix, iy, valid, lw, lh, ppt, xstep, stagger, pitch, sample_taps=(0, 5, 
     return tot_l / cnt, tot_a / cnt
 
 
+def role_model(ix, iy, valid, pix, colsets, rowsets, pitch):
+    """Lanes = (pixel of a small group, tap subset).  pix: list of (dx, dy) of the group's pixels; the 32 / len(pix)
+    lanes of a pixel are indexed by role r; role r handles the taps (j, i) for j in rowsets[r], i in colsets[r], one
+    warp instruction per (j-index, i-index) pair.  Returns (load, atomic) wavefronts per 32 pixels and channel
+    (ideal: 16)."""
+    H, W = ix.shape
+    pix = np.array(pix)
+    npx = len(pix)
+    lane = np.arange(32)
+    p, r = lane % npx, lane // npx
+    gw, gh = int(pix[:, 0].max()) + 1, int(pix[:, 1].max()) + 1
+    ys = np.arange(0, H - gh, gh)[::3]
+    xs = np.arange(0, W - gw, gw)
+    X = np.broadcast_to(xs[None, :, None] + pix[p, 0][None, None, :], (len(ys), len(xs), 32)).reshape(-1, 32)
+    Y = np.broadcast_to(ys[:, None, None] + pix[p, 1][None, None, :], (len(ys), len(xs), 32)).reshape(-1, 32)
+    sx, sy, v = ix[Y, X], iy[Y, X], valid[Y, X]
+    tl = ta = 0.0
+    n = steps = 0
+    for a in range(len(rowsets[0])):
+        for b in range(len(colsets[0])):
+            jj = np.array([rowsets[rr][a] for rr in r])
+            ii = np.array([colsets[rr][b] for rr in r])
+            addr = (sy + jj[None, :]).astype(np.int64) * pitch + sx + ii[None, :]
+            wl, wa = wavefronts(addr, v)
+            tl += wl.sum(); ta += wa.sum(); n += len(wl); steps += 1
+    per32 = (32.0 / npx) * steps
+    return tl / n * per32, ta / n * per32
+
+
+def roles_table(ix, iy, valid):
+    row8 = [(i, 0) for i in range(8)]
+    g42 = [(i % 4, i // 4) for i in range(8)]
+    g82 = [(i % 8, i // 8) for i in range(16)]
+    px84 = [(i % 8, i // 8) for i in range(32)]
+    px321 = [(i, 0) for i in range(32)]
+    all4 = [[0, 1, 2, 3]]
+    cases = [
+        ("one pixel per lane, 32x1 row segments (round-1 backward)", px321, all4, all4),
+        ("one pixel per lane, 8x4 patches (forward C <= 4)", px84, all4, all4),
+        ("(pixel, tap ROW) lanes, 8x1 groups (backward C <= 4)", row8, [[0, 1, 2, 3]] * 4, [[0], [1], [2], [3]]),
+        ("(pixel, tap ROW) lanes, 4x2 groups", g42, [[0, 1, 2, 3]] * 4, [[0], [1], [2], [3]]),
+        ("(pixel, tap COLUMN) lanes, 4 per pixel, 8x1 groups", row8, [[0], [1], [2], [3]], [[0, 1, 2, 3]] * 4),
+        ("(pixel, tap COLUMN) lanes, 4 per pixel, 4x2 groups", g42, [[0], [1], [2], [3]], [[0, 1, 2, 3]] * 4),
+        ("(pixel, tap COLUMNS r, r+2) lanes, 2 per pixel, 8x2 groups (forward C > 4)", g82, [[0, 2], [1, 3]], [[0, 1, 2, 3]] * 2),
+    ]
+    pitches = [64, 72, 80]
+    print("wavefronts per 32 pixels and channel (ideal 16), load / atomic")
+    print("| lane map | " + " | ".join("pitch %d" % p for p in pitches) + " |")
+    print("|---|" + "---|" * len(pitches))
+    for name, pix, cols, rows in cases:
+        cells = []
+        for pitch in pitches:
+            l, a = role_model(ix, iy, valid, pix, cols, rows, pitch)
+            cells.append("%.1f / %.1f" % (l, a))
+        print("| %s | " % name + " | ".join(cells) + " |", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--roles", action="store_true", help="lanes = (pixel, tap subset) maps of round 2")
     ap.add_argument("--grid", type=int, default=16)
     ap.add_argument("--sigma", type=float, default=6.0)
     ap.add_argument("--height", type=int, default=1080)
@@ -91,6 +150,9 @@ def main():
     valid = (x2 >= 0) & (y2 >= 0) & (x2 <= W - 1) & (y2 <= H - 1)
     ix = np.where(valid, x2, 0).astype(np.int32)
     iy = np.where(valid, y2, 0).astype(np.int32)
+    if args.roles:
+        roles_table(ix, iy, valid)
+        return
 
     maps = [
         ("32x1 (production)", 32, 1, 1, 1, False),

@@ -18,9 +18,9 @@ def run(flags):
     torch.cuda.synchronize()
     return o
 ref_o = run(lib.OVERWRITE | lib.NO_FAST)
-for cfg in [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "0,1").split(",")]:
+for cfg in [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "0,1,2").split(",")]:
     try:
-        fl = lib.OVERWRITE | lib.variant(cfg)  # MEMC_B200_VARIANT: 0 production, 1 generic kernel
+        fl = lib.OVERWRITE | lib.variant(cfg)  # MEMC_B200_VARIANT: 0 production (tap-column lanes), 1 generic kernel, 2 round-1 patches
         ok = bool(torch.equal(run(fl), ref_o))
         t = timeit(lambda: run(fl), 10)
         print(json.dumps({"cfg": cfg, "ms": t * 1e3, "frac": px * (2 * C + 18) * 4 / t / 1e9 / peak, "bitwise_equal_generic": ok}), flush=True)
