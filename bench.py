@@ -398,15 +398,19 @@ def networks_leg(torch, dist, dev, rank, world):
         res, times = {}, {}
         for impl in ("ours", "ref"):
             run(impl)                                   # warm-up (cuDNN autotune, allocator)
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            res[impl] = run(impl)
-            e1.record()
-            torch.cuda.synchronize()
-            times[impl] = e0.elapsed_time(e1) * 1e-3
+            best = None
+            for _ in range(3):                          # the convolutions dominate and jitter: best of 3
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res[impl] = run(impl)
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1) * 1e-3
+                best = t if best is None else min(best, t)
+            times[impl] = best
         cmp_ = refnet.compare(res["ours"], res["ref"])
         tt = torch.tensor([times["ours"], times["ref"], cmp_["max_abs"], -cmp_["psnr_db"]], device=dev, dtype=torch.float64)
         if dist is not None:
@@ -435,8 +439,8 @@ def run_ours(args, rank, world, local_rank):
     numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: NUMA-local staging buffers per rank
     lib.load()
     distributed = world > 1
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if distributed and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
 
