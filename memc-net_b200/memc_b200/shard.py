@@ -54,3 +54,66 @@ def run_sharded(fn, tensors, gather=True, group=None):
     local = shard_frames(tensors, rank, world)
     out = fn(*local)
     return gather_frames(out, batch, group) if gather else out
+
+
+class PeerGather(object):
+    """The optional output exchange over NVLink peer memory instead of a NCCL collective.
+
+    Every rank owns one SYMMETRIC buffer [world, B, ...] (torch.distributed._symmetric_memory: the same allocation on every
+    rank, each mapped into every other rank's address space over NVLink / NVSwitch).  `push(frame, index)` orders a side
+    stream after the caller's current stream and copies the frame into slot [rank, index] of EVERY rank's buffer with
+    device-to-device copies -- copy engines, no SMs, so the exchange of frame i runs under the compute of frame i + 1 without
+    taking SMs from it the way a NCCL kernel does (measured on 8 x B200: profiles/r02_scaling.md).  `finish()` adds a
+    device-side barrier over all ranks (signal pads in the same symmetric memory) behind the pushes and makes the caller's
+    stream wait for it: after that the local buffer holds every rank's frames.
+
+    One process per GPU, NCCL process group initialised (the rendezvous exchanges the memory handles through it).  Raises
+    RuntimeError where symmetric memory is not available (callers fall back to `gather_frames`)."""
+
+    def __init__(self, frames_per_rank_shape, dtype=torch.float32, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001  (newer torch enables it on rendezvous)
+            pass
+        shape = (self.world,) + tuple(frames_per_rank_shape)
+        self.buf = symm.empty(*shape, dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.peers = [self.hdl.get_buffer(r, shape, dtype) for r in range(self.world)]
+        self.stream = torch.cuda.Stream(device=device)
+        self._read_done = {}
+        self.hdl.barrier()
+
+    def push(self, frame, index):
+        """frame: this rank's frame `index` ([...] = frames_per_rank_shape[1:]), produced on the current stream.  The source
+        may be overwritten again once `wait_reusable(index)` has been ordered before the overwrite."""
+        cur = torch.cuda.current_stream(self.buf.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for k in range(self.world):  # start with the own slot, then the peers in ring order (spreads the switch ports)
+                r = (self.rank + k) % self.world
+                self.peers[r][self.rank, index].copy_(frame, non_blocking=True)
+            ev = self._read_done.get(index)
+            if ev is None:
+                ev = self._read_done[index] = torch.cuda.Event()
+            ev.record(self.stream)
+
+    def wait_reusable(self, index):
+        """Order the current stream after the last push of frame `index` has finished READING its source."""
+        ev = self._read_done.get(index)
+        if ev is not None:
+            torch.cuda.current_stream(self.buf.device).wait_event(ev)
+
+    def barrier_async(self):
+        """Device-side barrier over all ranks behind the pushes issued so far, on the side stream (nobody waits here)."""
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier()
+
+    def finish(self):
+        """barrier_async() + make the caller's current stream wait: afterwards the local buffer holds everybody's frames."""
+        self.barrier_async()
+        torch.cuda.current_stream(self.buf.device).wait_stream(self.stream)
+        return self.buf
