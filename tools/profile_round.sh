@@ -3,22 +3,18 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
+timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
+# launch list of the bench step (per-launch times are cold-cache and serialised: only the SHARES are comparable)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/bench_under_ncu.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fi_bwd_tma -s 3 -c 1 -o $O/bench_fi_bwd -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ncu_bwd.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-networks > $O/bench_under_ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fi_bwd_rows -s 3 -c 1 -o $O/bench_fi_bwd -f \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-networks > $O/ncu_bwd.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fi_fwd_patch -s 3 -c 1 -o $O/bench_fi_fwd -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ncu_fwd.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-networks > $O/ncu_fwd.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fp_pipeline -s 1 -c 1 -o $O/fp_pipeline -f \
     python tools/run_one.py fp_fwd 16 > $O/ncu_fp.log 2>&1
-FLOW=contention timeout 300 ncu --set full --clock-control none -k regex:fp_pipeline -s 1 -c 1 -o $O/fp_pipeline_contention -f \
-    python tools/run_one.py fp_fwd 16 > $O/ncu_fp2.log 2>&1
-C=64 timeout 300 ncu --set full --clock-control none -k regex:fi_fwd_tma_chunked -s 2 -c 1 -o $O/fi_fwd_c64 -f \
+C=64 timeout 300 ncu --set full --clock-control none -k regex:fi_fwd_cols_chunked -s 2 -c 1 -o $O/fi_fwd_c64 -f \
     python tools/run_one.py fi_fwd 1 > $O/ncu_c64.log 2>&1
-timeout 400 python tools/kbench.py --iters 20 --out $O/kbench.json > $O/kbench.log 2>&1
-timeout 200 python tools/kbench.py --iters 20 --only fismooth --out $O/kbench_smooth.json > $O/kbench_smooth.log 2>&1
-timeout 400 python tests/legacy_bench.py --iters 10 --out $O/legacy_bench.json > $O/legacy_bench.log 2>&1
 timeout 200 python tools/sweep_fi.py --iters 20 --out $O/sweep_fi.json > $O/sweep_fi.log 2>&1
-timeout 100 python tools/fp_small.py > $O/fp_small.log 2>&1
+timeout 200 python tools/sweep_c64.py > $O/sweep_c64.log 2>&1
 cat $O/bench_n1.json
