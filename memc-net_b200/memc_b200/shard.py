@@ -70,7 +70,7 @@ class PeerGather(object):
     One process per GPU, NCCL process group initialised (the rendezvous exchanges the memory handles through it).  Raises
     RuntimeError where symmetric memory is not available (callers fall back to `gather_frames`)."""
 
-    def __init__(self, frames_per_rank_shape, dtype=torch.float32, device=None, group=None):
+    def __init__(self, frames_per_rank_shape, dtype=torch.float32, device=None, group=None, streams=None):
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -83,7 +83,11 @@ class PeerGather(object):
         self.buf = symm.empty(*shape, dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, group)
         self.peers = [self.hdl.get_buffer(r, shape, dtype) for r in range(self.world)]
-        self.stream = torch.cuda.Stream(device=device)
+        # one copy stream per peer (capped): a single stream of peer copies keeps ONE copy engine busy (~380 GB/s
+        # measured on 8 x B200); several streams drive several engines and NVLink ports at once
+        n = max(1, min(self.world - 1, 7) if streams is None else int(streams))
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+        self.stream = self.streams[0]
         self._read_done = {}
         self.hdl.barrier()
 
@@ -91,24 +95,26 @@ class PeerGather(object):
         """frame: this rank's frame `index` ([...] = frames_per_rank_shape[1:]), produced on the current stream.  The source
         may be overwritten again once `wait_reusable(index)` has been ordered before the overwrite."""
         cur = torch.cuda.current_stream(self.buf.device)
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            for k in range(self.world):  # start with the own slot, then the peers in ring order (spreads the switch ports)
-                r = (self.rank + k) % self.world
+        evs = self._read_done.setdefault(index, [torch.cuda.Event() for _ in self.streams])
+        for s in self.streams:
+            s.wait_stream(cur)
+        for k in range(self.world):  # the own slot first, then the peers in ring order, round robin over the copy streams
+            r = (self.rank + k) % self.world
+            with torch.cuda.stream(self.streams[k % len(self.streams)]):
                 self.peers[r][self.rank, index].copy_(frame, non_blocking=True)
-            ev = self._read_done.get(index)
-            if ev is None:
-                ev = self._read_done[index] = torch.cuda.Event()
-            ev.record(self.stream)
+        for s, ev in zip(self.streams, evs):
+            ev.record(s)
 
     def wait_reusable(self, index):
         """Order the current stream after the last push of frame `index` has finished READING its source."""
-        ev = self._read_done.get(index)
-        if ev is not None:
-            torch.cuda.current_stream(self.buf.device).wait_event(ev)
+        cur = torch.cuda.current_stream(self.buf.device)
+        for ev in self._read_done.get(index, ()):
+            cur.wait_event(ev)
 
     def barrier_async(self):
-        """Device-side barrier over all ranks behind the pushes issued so far, on the side stream (nobody waits here)."""
+        """Device-side barrier over all ranks behind the pushes issued so far, on the first copy stream (nobody waits here)."""
+        for s in self.streams[1:]:
+            self.stream.wait_stream(s)
         with torch.cuda.stream(self.stream):
             self.hdl.barrier()
 
