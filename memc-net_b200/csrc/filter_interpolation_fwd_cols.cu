@@ -50,23 +50,27 @@ struct LayK {
     static constexpr int NL = NL_, CBK = CBK_, NBUF = NBUF_, GX = 16 / NL, PXS = 2 * GX, NSTEP = 64 / PXS, NK = 4 / NL;
     static constexpr int STRIP = KTH * 16 * GX, JBLK = 8 * GX;
     static constexpr int CH = KSH * SW, BOX = CBK * CH;  // words
-    static constexpr int OFF_FLOW = 16 * KTH * TW * 4;
-    static constexpr int OFF_BAR = OFF_FLOW + 2 * KTH * TW * 4;
-    static constexpr int OFF_IMG = OFF_BAR + 128;
+    // shared memory: [barriers | ring box 0 | ring box 1 ...]; the flow + filter STAGING area (36 KB) aliases the LAST ring
+    // box: it is dead once every lane holds its taps in registers, and the ring only reaches that box with the second chunk
+    static constexpr int OFF_BAR = 0;
+    static constexpr int OFF_IMG = 128;
+    static constexpr int OFF_STAGE = OFF_IMG + (NBUF - 1) * BOX * 4;  // filter strips, then the flow tile
+    static constexpr int OFF_FLOW = OFF_STAGE + 16 * KTH * TW * 4;
     static constexpr int TOTAL = OFF_IMG + NBUF * BOX * 4;
+    static_assert((16 + 2) * KTH * TW * 4 <= BOX * 4, "the staging area must fit one ring box");
     static_assert(CBK == 2 || CBK == 4, "2 or 4 channels per box");
 };
 
 template <class Y>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
                            const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
     constexpr int NL = Y::NL, CBK = Y::CBK, NBUF = Y::NBUF, GX = Y::GX, PXS = Y::PXS, NSTEP = Y::NSTEP, NK = Y::NK;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
-    const float* s_filt = reinterpret_cast<const float*>(sm);
-    const float* s_flow = reinterpret_cast<const float*>(sm + Y::OFF_FLOW);  // [2][KTH][TW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Y::OFF_BAR);           // 0 flow, 1 filter, 2.. image ring
+    const float* s_filt = reinterpret_cast<const float*>(sm + Y::OFF_STAGE);  // NSTEP strips (aliases the last ring box)
+    const float* s_flow = reinterpret_cast<const float*>(sm + Y::OFF_FLOW);   // [2][KTH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Y::OFF_BAR);            // 0 flow, 1 filter, 2.. image ring
     int* s_bb = reinterpret_cast<int*>(bars + 2 + NBUF);
     int* s_done = s_bb + 4;  // [NBUF] warps that have finished with a ring buffer
     unsigned char* const sm_img0 = sm + Y::OFF_IMG;
@@ -90,7 +94,7 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
         tma::mbar_expect_tx(&bars[1], 16 * KTH * TW * 4);
 #pragma unroll
         for (int s = 0; s < NSTEP; ++s)
-            tma::load_5d(sm + s * Y::STRIP * 4, &m_filt, x0 + GX * s, 0, 0, 4 * b, y0 >> 1, &bars[1]);
+            tma::load_5d(sm + Y::OFF_STAGE + s * Y::STRIP * 4, &m_filt, x0 + GX * s, 0, 0, 4 * b, y0 >> 1, &bars[1]);
     }
     // ---- geometry once per pixel (lane l owns, for k = 0, 1, the pixel (px, py) of step 2 (l / PXS) + k)
     tma::mbar_wait(&bars[0], 0, 41);
@@ -131,7 +135,7 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
         by = max(0, min(by, H - KSH));
     }
     if (tid == 0) {
-        for (int ch = 0; ch < NBUF && ch < nchunk; ++ch) {
+        for (int ch = 0; ch < NBUF - 1 && ch < nchunk; ++ch) {  // (the last box still holds the staged flow / filter)
             tma::mbar_expect_tx(&bars[2 + ch], Y::BOX * 4);
             tma::load_4d(sm_img0 + ch * Y::BOX * 4, &m_img, bx, by, ch * CBK, b, &bars[2 + ch]);
         }
@@ -165,14 +169,21 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
             const float cw = (NL == 2 ? k == 0 : r < 2) ? (1.0f - a) : a;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                // a pixel that is not on the fast path reads box word 0 with weight 0 (the main loop is branch free);
-                // the rare per-tap path below fetches its taps again
+                // the main loop is branch free: an invalid pixel reads box word 0 with weight 0; a pixel on the per-tap
+                // path keeps its taps (its main-loop sum is garbage and is discarded by the per-tap loop)
                 const float w = f[j * Y::JBLK + k * 32] * (cw * (j < 2 ? 1.0f - bt : bt));
-                wv[s][k][j] = code >= 0 ? w : 0.f;
+                wv[s][k][j] = code >= -1 ? w : 0.f;
             }
         }
     }
     any_slow = __any_sync(0xffffffffu, any_slow);
+    // geometry and taps live in registers now: the staging area becomes the last ring box
+    __syncthreads();
+    if (tid == 0 && NBUF - 1 < nchunk) {
+        tma::fence_proxy_async();
+        tma::mbar_expect_tx(&bars[2 + NBUF - 1], Y::BOX * 4);
+        tma::load_4d(sm_img0 + (NBUF - 1) * Y::BOX * 4, &m_img, bx, by, (NBUF - 1) * CBK, b, &bars[2 + NBUF - 1]);
+    }
 
     const float* in1b = p.in1p + b * p.in1.b;
     const int y = y0 + 2 * warp + py;
@@ -200,26 +211,24 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
             if (__builtin_expect(any_slow, 0)) {  // warp-uniform: someone in this warp has a pixel on the per-tap path
                 const int src = (s >> 1) * PXS + (lane & (PXS - 1));
                 const int Lc = __shfl_sync(0xffffffffu, me[s & 1].ix, src) - 1, T = __shfl_sync(0xffffffffu, me[s & 1].iy, src) - 1;
-                const float a = __shfl_sync(0xffffffffu, me[s & 1].alpha, src), bt = __shfl_sync(0xffffffffu, me[s & 1].beta, src);
                 if (st[s] == -1) {
-                    const float* f = s_filt + s * Y::STRIP + warp * 4 * Y::JBLK + lane;
-#pragma unroll 1
+#pragma unroll
+                    for (int c = 0; c < CBK; ++c) sum[c] = 0.f;  // discard what the branch-free loop made of box word 0
+#pragma unroll  // (k must stay a compile-time index: wv lives in registers)
                     for (int k = 0; k < NK; ++k) {
                         const int cx = clampi(Lc + r + NL * k, 0, W - 1);
                         const int ux = cx - bx;
-                        const float cw = (NL == 2 ? k == 0 : r < 2) ? (1.0f - a) : a;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int cy = clampi(T + j, 0, H - 1);
                             const int uy = cy - by;
                             const bool in_box = (unsigned)uy < (unsigned)KSH && (unsigned)ux < (unsigned)SW;
-                            const float w = f[j * Y::JBLK + k * 32] * (cw * (j < 2 ? 1.0f - bt : bt));
 #pragma unroll
                             for (int c = 0; c < CBK; ++c) {
                                 float v = 0.f;
                                 if (in_box) v = s_img[c * Y::CH + uy * SW + ux];
                                 else if (c0 + c < C) v = __ldg(in1b + (int64_t)(c0 + c) * p.in1.c + (int64_t)cy * p.in1.h + cx);
-                                sum[c] = fmaf(v, w, sum[c]);
+                                sum[c] = fmaf(v, wv[s][k][j], sum[c]);
                             }
                         }
                     }
@@ -300,7 +309,7 @@ int launch_cols_chunked(cudaStream_t stream, const FiArgs& a) {
 int fi_forward_cols(cudaStream_t stream, const FiArgs& a) {
     if (a.fs != 4 || a.C <= 4 || a.W % 4 || a.H % 2 || a.B > 65535 || a.W < SW || a.H < KSH) return 0;
     if (a.B > 1 && a.filt.b != 16 * a.filt.c) return 0;  // the tap map folds the batch into the plane index
-    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a);  // 2 lanes / pixel, 4 channels / box, 2 boxes: 110 KB, 2 CTAs / SM
+    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a);  // 2 lanes / pixel, 4 channels / box, 2 boxes: 74 KB, 3 CTAs / SM
 }
 
 }  // namespace memc
