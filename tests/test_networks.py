@@ -133,7 +133,11 @@ def test_memc_net_ve_on_vimeo_fixtures(built_lib):
     c["off_fraction"], s["off_fraction"] = _off_fraction(ours, r1, thr), _off_fraction(r2, r1, thr)
     print("MEMC_Net_VE vimeo 00001/0266: ours-vs-ref", c, "| ref-vs-ref", s)
     _save("MEMC_Net_VE vimeo", {"rectified": {"ours_vs_ref": c, "ref_vs_ref": s}})
-    assert c["finite"] and c["psnr_db"] >= 70.0 and c["psnr_db"] >= s["psnr_db"] - 12.0
+    # (no FlowProjection in this network: the reference arm is deterministic; ours differs by the fp32 rounding ORDER of
+    # the 64-channel context warp, ~1e-7 relative, amplified by the random-init EDSR whose output range is ~1e4)
+    d = (ours - r1).abs().flatten().float()
+    assert c["finite"] and c["psnr_db"] >= 70.0
+    assert float(d.kthvalue(max(1, int(d.numel() * (1.0 - 1e-4)))).values) <= 2e-3 * c["range"]
     # the Interpolate call site: occlusion-weighted pair of plain bilinear warps
     from networks import MEMC_Net_VE as VE   # (networks/__init__.py rebinds the submodule name to the class)
     g = torch.Generator(device="cuda").manual_seed(3)
