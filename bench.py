@@ -305,6 +305,34 @@ def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
     del c_in, c_flow, c_filt, c_go, c_out, cg
     torch.cuda.empty_cache()
 
+    # --- RGB frame + its 64-channel context features warped with one flow / filter (MEMC_Net_star.py:272-285): one pass
+    r_in, r_flow, r_filt, _ = synth.filter_interpolation_case(1, 3, H, W, FS, seed=5, device=dev)
+    x_in = torch.randn(1, 64, H, W, device=dev)
+    r_out, x_out = torch.empty_like(r_in), torch.empty_like(x_in)
+
+    def o_pair():
+        lib.call("memc_b200_filter_interpolation_forward_pair", st, 1, 3, 64, H, W, FS, S(r_in), S(x_in), S(r_flow), S(r_filt),
+                 S(r_out), S(x_out), P(r_in), P(x_in), P(r_flow), P(r_filt), P(r_out), P(x_out), lib.OVERWRITE)
+
+    def o_two():
+        lib.call("memc_b200_filter_interpolation_forward", st, 1, 3, H, W, FS, S(r_in), S(r_flow), S(r_filt), S(r_out),
+                 P(r_in), P(r_flow), P(r_filt), P(r_out), lib.OVERWRITE)
+        lib.call("memc_b200_filter_interpolation_forward", st, 1, 64, H, W, FS, S(x_in), S(r_flow), S(r_filt), S(x_out),
+                 P(x_in), P(r_flow), P(r_filt), P(x_out), lib.OVERWRITE)
+
+    t, t2 = _timed(torch, o_pair), _timed(torch, o_two)
+    tl = None
+    if have_ref:
+        def l_pair():
+            r_out.zero_(); x_out.zero_()
+            ref.gpu_filter_interpolation_forward(r_in, r_flow, r_filt, r_out)
+            ref.gpu_filter_interpolation_forward(x_in, r_flow, r_filt, x_out)
+        tl = _timed(torch, l_pair, 3)
+    entry("fused RGB + 64 context channels with one flow / filter 1920x1080, batch 1 (two plain calls: %.3f ms)" % (t2 * 1e3),
+          H * W, (2 * 67 + 18) * 4, t, tl)
+    del r_in, r_flow, r_filt, x_in, r_out, x_out
+    torch.cuda.empty_cache()
+
     # --- fused call site: two warps + occlusion blend (networks/MEMC_Net.py:258-264)
     in1b, flowb, filtb, _ = synth.filter_interpolation_case(B, C, H, W, FS, seed=7, device=dev)
     occ = [torch.rand(B, 1, H, W, device=dev) for _ in range(2)]

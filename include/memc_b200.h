@@ -217,6 +217,19 @@ MEMC_B200_API int memc_b200_filter_interpolation_blend_forward(
     const float *input1_1, const float *flow_1, const float *filter_1,
     const float *occlusion_0, const float *occlusion_1, float *output, int flags);
 
+/* Two images warped with ONE flow and ONE filter in one pass:
+ *     output_a = FilterInterpolation(input_a, flow, filter),   output_b = FilterInterpolation(input_b, flow, filter)
+ * -- the RGB frame and its context features in networks/MEMC_Net_star.py:272-285, which call the op twice per reference
+ * with identical offset / filter.  flow, filter, geometry and bounding box are fetched / computed once (fs == 4, even H,
+ * dense filter batch stride; otherwise, and with MEMC_B200_NO_FAST, the two plain calls are made inside the library).
+ * Every element of both outputs is written. */
+MEMC_B200_API int memc_b200_filter_interpolation_forward_pair(
+    memc_stream_t stream, int batch, int channel_a, int channel_b, int h, int w, int filter_size,
+    memc_strides s_in_a, memc_strides s_in_b, memc_strides s_flow, memc_strides s_filter,
+    memc_strides s_out_a, memc_strides s_out_b,
+    const float *input_a, const float *input_b, const float *flow, const float *filter,
+    float *output_a, float *output_b, int flags);
+
 MEMC_B200_API int memc_b200_flow_projection_forward(
     memc_stream_t stream, int batch, int h, int w, int fillhole,
     memc_strides s_flow, memc_strides s_count, memc_strides s_out,

@@ -334,6 +334,30 @@ extern "C" int memc_b200_filter_interpolation_blend_forward(
     return fi_blend_forward(stream, a0, a1, occlusion_0, mk_view(s_occ_0), occlusion_1, mk_view(s_occ_1), flags);
 }
 
+extern "C" int memc_b200_filter_interpolation_forward_pair(
+    memc_stream_t stream, int batch, int channel_a, int channel_b, int h, int w, int filter_size,
+    memc_strides s_in_a, memc_strides s_in_b, memc_strides s_flow, memc_strides s_filter,
+    memc_strides s_out_a, memc_strides s_out_b,
+    const float* input_a, const float* input_b, const float* flow, const float* filter,
+    float* output_a, float* output_b, int flags) {
+    FiArgs a{};
+    a.B = batch; a.C = channel_a; a.H = h; a.W = w; a.fs = filter_size;
+    a.in1 = mk_view(s_in_a); a.flow = mk_view(s_flow); a.filt = mk_view(s_filter); a.out = mk_view(s_out_a);
+    a.in1p = input_a; a.flowp = flow; a.filtp = filter; a.outp = output_a;
+    a.flags = flags;
+    if (batch > 0 && h > 0 && w > 0 && channel_a > 0 && channel_b > 0 && filter_size > 0 && !(flags & MEMC_B200_NO_FAST)) {
+        DeviceGuard guard(a.in1p);
+        if (!guard.ok) return -1;
+        const int r = fi_forward_cols_pair(stream, a, input_b, mk_view(s_in_b), output_b, mk_view(s_out_b), channel_b);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
+    // composition of the plain op: the flow / filter tiles are read twice
+    if (fi_forward(stream, a, flags) != 0) return -1;
+    FiArgs b2 = a;
+    b2.C = channel_b; b2.in1 = mk_view(s_in_b); b2.out = mk_view(s_out_b); b2.in1p = input_b; b2.outp = output_b;
+    return fi_forward(stream, b2, flags);
+}
+
 extern "C" int memc_b200_filter_interpolation_forward(
     memc_stream_t stream, int batch, int channel, int h, int w, int filter_size,
     memc_strides s_in1, memc_strides s_flow, memc_strides s_filter, memc_strides s_out,

@@ -61,10 +61,22 @@ struct LayK {
     static_assert(CBK == 2 || CBK == 4, "2 or 4 channels per box");
 };
 
+// An optional SECOND image warped with the same flow and filter in the same pass (the RGB frame next to its 64-channel
+// context features: networks/MEMC_Net_star.py:272-285 call FilterInterpolation twice per reference with identical
+// offset / filter).  Its channels are simply further chunks of the ring: flow tile, filter tile, geometry, bounding box and
+// the lane's taps are shared.  C2 == 0: no second source.
+struct Src2 {
+    const float* in1p;
+    float* outp;
+    View in1, out;
+    int C;
+};
+
 template <class Y>
 __global__ void __launch_bounds__(256, 3)
 fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_constant__ CUtensorMap m_filt,
-                           const __grid_constant__ CUtensorMap m_img, const __grid_constant__ FiArgs p) {
+                           const __grid_constant__ CUtensorMap m_img, const __grid_constant__ CUtensorMap m_img2,
+                           const __grid_constant__ FiArgs p, const __grid_constant__ Src2 q) {
     constexpr int NL = Y::NL, CBK = Y::CBK, NBUF = Y::NBUF, GX = Y::GX, PXS = Y::PXS, NSTEP = Y::NSTEP, NK = Y::NK;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
@@ -77,8 +89,16 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * KTH, b = blockIdx.z;
-    const int W = p.W, H = p.H, C = p.C;
-    const int nchunk = (C + CBK - 1) / CBK;
+    const int W = p.W, H = p.H;
+    int bx_ = 0, by_ = 0;  // box origin (set after the bounding box is known; the lambda below reads them by reference)
+    const int nchunk1 = (p.C + CBK - 1) / CBK;            // chunks [0, nchunk1): first source; the rest: second source
+    const int nchunk = nchunk1 + (q.C + CBK - 1) / CBK;
+    // ring slot `buf` <- chunk `ch`
+    auto issue_chunk = [&](int ch, int buf) {
+        tma::mbar_expect_tx(&bars[2 + buf], Y::BOX * 4);
+        if (ch < nchunk1) tma::load_4d(sm_img0 + buf * Y::BOX * 4, &m_img, bx_, by_, ch * CBK, b, &bars[2 + buf]);
+        else tma::load_4d(sm_img0 + buf * Y::BOX * 4, &m_img2, bx_, by_, (ch - nchunk1) * CBK, b, &bars[2 + buf]);
+    };
     const int px = lane % GX, py = (lane / GX) & 1, r = lane / PXS;
 
     if (tid == 0) {
@@ -134,11 +154,10 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
         bx = max(0, min(bx, W - SW)) & ~3;  // W >= SW, H >= KSH and W % 4 == 0 are launch preconditions
         by = max(0, min(by, H - KSH));
     }
+    bx_ = bx;
+    by_ = by;
     if (tid == 0) {
-        for (int ch = 0; ch < NBUF - 1 && ch < nchunk; ++ch) {  // (the last box still holds the staged flow / filter)
-            tma::mbar_expect_tx(&bars[2 + ch], Y::BOX * 4);
-            tma::load_4d(sm_img0 + ch * Y::BOX * 4, &m_img, bx, by, ch * CBK, b, &bars[2 + ch]);
-        }
+        for (int ch = 0; ch < NBUF - 1 && ch < nchunk; ++ch) issue_chunk(ch, ch);  // (the last box still holds the staging)
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -181,18 +200,22 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
     __syncthreads();
     if (tid == 0 && NBUF - 1 < nchunk) {
         tma::fence_proxy_async();
-        tma::mbar_expect_tx(&bars[2 + NBUF - 1], Y::BOX * 4);
-        tma::load_4d(sm_img0 + (NBUF - 1) * Y::BOX * 4, &m_img, bx, by, (NBUF - 1) * CBK, b, &bars[2 + NBUF - 1]);
+        issue_chunk(NBUF - 1, NBUF - 1);
     }
 
-    const float* in1b = p.in1p + b * p.in1.b;
     const int y = y0 + 2 * warp + py;
     // channel(s) of a chunk this lane ends up with after the transposed reduction
     const int my_c = CBK == 2 ? (r & 1) : NL == 4 ? (((r & 1) << 1) | (r >> 1)) : 2 * r;
     for (int ch = 0, buf = 0, par = 0; ch < nchunk; ++ch) {
         const float* s_img = reinterpret_cast<const float*>(sm_img0 + buf * Y::BOX * 4);
         tma::mbar_wait(&bars[2 + buf], par, 43);
-        const int c0 = ch * CBK;
+        // this chunk's source: channels [c0, c0 + CBK) of the first or of the second image
+        const bool second = ch >= nchunk1;
+        const int c0 = (second ? ch - nchunk1 : ch) * CBK, C = second ? q.C : p.C;
+        const float* in1b = second ? q.in1p + b * q.in1.b : p.in1p + b * p.in1.b;
+        float* outb = second ? q.outp + b * q.out.b : p.outp + b * p.out.b;
+        const int64_t in_c = second ? q.in1.c : p.in1.c, in_h = second ? q.in1.h : p.in1.h;
+        const int64_t out_c = second ? q.out.c : p.out.c, out_h = second ? q.out.h : p.out.h;
 #pragma unroll
         for (int s = 0; s < NSTEP; ++s) {
             float sum[CBK];
@@ -227,7 +250,7 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
                             for (int c = 0; c < CBK; ++c) {
                                 float v = 0.f;
                                 if (in_box) v = s_img[c * Y::CH + uy * SW + ux];
-                                else if (c0 + c < C) v = __ldg(in1b + (int64_t)(c0 + c) * p.in1.c + (int64_t)cy * p.in1.h + cx);
+                                else if (c0 + c < C) v = __ldg(in1b + (int64_t)(c0 + c) * in_c + (int64_t)cy * in_h + cx);
                                 sum[c] = fmaf(v, wv[s][k][j], sum[c]);
                             }
                         }
@@ -255,15 +278,15 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
             }
             if (st[s] == -3) continue;  // outside the image
             const int x = x0 + GX * s + px;
-            float* outp = p.outp + b * p.out.b + (int64_t)y * p.out.h + x;
-            const float* inp = in1b + (int64_t)y * p.in1.h + x;
+            float* outp = outb + (int64_t)y * out_h + x;
+            const float* inp = in1b + (int64_t)y * in_h + x;
 #pragma unroll
-            for (int q = 0; q < (CBK == 4 && NL == 2 ? 2 : 1); ++q) {
-                const int c = c0 + my_c + q;
+            for (int qq = 0; qq < (CBK == 4 && NL == 2 ? 2 : 1); ++qq) {
+                const int c = c0 + my_c + qq;
                 if (c >= C || (CBK == 2 && NL == 4 && r >= 2)) break;  // (2 channels over 4 lanes: lanes r, r ^ 2 hold the same total)
-                float v = q ? mine1 : mine0;
-                if (st[s] == -2) v = __ldg(inp + (int64_t)c * p.in1.c);  // my_lib_kernel.cu:1209-1213
-                stg_stream(outp + (int64_t)c * p.out.c, v);
+                float v = qq ? mine1 : mine0;
+                if (st[s] == -2) v = __ldg(inp + (int64_t)c * in_c);  // my_lib_kernel.cu:1209-1213
+                stg_stream(outp + (int64_t)c * out_c, v);
             }
         }
         // no block-wide barrier: the LAST warp to finish with this buffer refills it, nobody waits for anybody
@@ -275,8 +298,7 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
                 __threadfence_block();
                 if (ch + NBUF < nchunk) {
                     tma::fence_proxy_async();
-                    tma::mbar_expect_tx(&bars[2 + buf], Y::BOX * 4);
-                    tma::load_4d(sm_img0 + buf * Y::BOX * 4, &m_img, bx, by, (ch + NBUF) * CBK, b, &bars[2 + buf]);
+                    issue_chunk(ch + NBUF, buf);
                 }
             }
         }
@@ -285,9 +307,9 @@ fi_fwd_cols_chunked_kernel(const __grid_constant__ CUtensorMap m_flow, const __g
 }
 
 template <class Y>
-int launch_cols_chunked(cudaStream_t stream, const FiArgs& a) {
+int launch_cols_chunked(cudaStream_t stream, const FiArgs& a, const Src2& q) {
     constexpr int CBK = Y::CBK;
-    CUtensorMap m[3];
+    CUtensorMap m[4];
     if (!tma::make_map_nchw(&m[0], a.flowp, a.B, 2, a.H, a.W, a.flow.b, a.flow.c, a.flow.h, TW, KTH, 2,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B) ||
         !tma::make_map_taps_cols(&m[1], a.filtp, a.B, a.H, a.W, a.filt.b, a.filt.c, a.filt.h, Y::GX, KTH,
@@ -295,21 +317,37 @@ int launch_cols_chunked(cudaStream_t stream, const FiArgs& a) {
         !tma::make_map_nchw(&m[2], a.in1p, a.B, a.C, a.H, a.W, a.in1.b, a.in1.c, a.in1.h, SW, KSH, CBK,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return 0;
+    m[3] = m[2];
+    if (q.C > 0 && !tma::make_map_nchw(&m[3], q.in1p, a.B, q.C, a.H, a.W, q.in1.b, q.in1.c, q.in1.h, SW, KSH, CBK,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return 0;
     constexpr size_t smem = (size_t)Y::TOTAL + 128;
     if (!ensure_dynamic_smem(fi_fwd_cols_chunked_kernel<Y>, smem)) return 0;
     dim3 grid((a.W + TW - 1) / TW, (a.H + KTH - 1) / KTH, a.B);
-    fi_fwd_cols_chunked_kernel<Y><<<grid, 256, smem, stream>>>(m[0], m[1], m[2], a);
+    fi_fwd_cols_chunked_kernel<Y><<<grid, 256, smem, stream>>>(m[0], m[1], m[2], m[3], a, q);
     count_launch();
     return check_launch("FilterInterpolation forward (TMA, tap-column lanes, channel-chunked)") == 0 ? 1 : -1;
 }
 
 }  // namespace
 
-// C > 4 only.  1 = handled, 0 = layout preconditions not met (caller falls back), -1 = launch error
-int fi_forward_cols(cudaStream_t stream, const FiArgs& a) {
-    if (a.fs != 4 || a.C <= 4 || a.W % 4 || a.H % 2 || a.B > 65535 || a.W < SW || a.H < KSH) return 0;
+// 1 = handled, 0 = layout preconditions not met (caller falls back), -1 = launch error
+static int cols_preconditions(const FiArgs& a) {
+    if (a.fs != 4 || a.W % 4 || a.H % 2 || a.B > 65535 || a.W < SW || a.H < KSH) return 0;
     if (a.B > 1 && a.filt.b != 16 * a.filt.c) return 0;  // the tap map folds the batch into the plane index
-    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a);  // 2 lanes / pixel, 4 channels / box, 2 boxes: 74 KB, 3 CTAs / SM
+    return 1;
+}
+
+// C > 4 only
+int fi_forward_cols(cudaStream_t stream, const FiArgs& a) {
+    if (a.C <= 4 || !cols_preconditions(a)) return 0;
+    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a, Src2{});  // 2 lanes / pixel, 4 channels / box, 2 boxes: 74 KB, 3 CTAs / SM
+}
+
+// two images, one flow / filter: out = FI(in1, flow, filter), out2 = FI(in2, flow, filter); any channel counts
+int fi_forward_cols_pair(cudaStream_t stream, const FiArgs& a, const float* in2, View v_in2, float* out2, View v_out2, int C2) {
+    if (a.C < 1 || C2 < 1 || !cols_preconditions(a)) return 0;
+    return launch_cols_chunked<LayK<2, 4, 2>>(stream, a, Src2{in2, out2, v_in2, v_out2, C2});
 }
 
 }  // namespace memc

@@ -16,6 +16,10 @@ here), so a network can rebind it:  `MEMC_Net.FilterInterpolate = staticmethod(f
 warps are averaged instead of occlusion-blended (`ref0_offset / 2.0 + ref2_offset / 2.0`): the same fused kernel with
 the constant weight 0.5 (no occlusion maps are read).
 
+`FilterInterpolateShared(input_a, input_b, offset, filter)` warps two images that share flow and filter -- the RGB frame and
+its 64-channel context features in networks/MEMC_Net_star.py:272-285 -- in one kernel: flow, filter, geometry and bounding box
+are fetched / computed once.
+
 `FlowProjectPair` runs both directions as ONE FlowProjection call on the concatenated batch (frames are
 independent, so each half equals the separate call; with 2 x B >= 3 frames the persistent pipeline has twice the
 frames to overlap), and returns the two halves as views.
@@ -113,6 +117,39 @@ def FilterInterpolate(ref0, ref2, offset, filter, occlusion, filter_size2=None):
 def FilterInterpolateMean(ref0, ref2, offset, filter, filter_size2=None):  # noqa: A002 (reference's names)
     """Drop-in for MEMC_Net_s.FilterInterpolate (networks/MEMC_Net_s.py:258-264): the mean of the two warps."""
     return _FilterInterpolateBlend.apply(ref0, offset[0], filter[0], None, ref2, offset[1], filter[1], None)
+
+
+class _FilterInterpolateShared(Function):
+    @staticmethod
+    def forward(ctx, in_a, in_b, flow, filt):
+        in_a, in_b, flow, filt = (_prep(t, n) for t, n in zip((in_a, in_b, flow, filt), ("input_a", "input_b", "offset", "filter")))
+        _lib.check_same_device(in_a, in_b, flow, filt)
+        B, Ca, H, W = in_a.shape
+        Cb = in_b.size(1)
+        if in_b.shape != (B, Cb, H, W) or flow.shape != (B, 2, H, W) or filt.shape[0] != B or filt.shape[2:] != (H, W):
+            raise _lib.MemcB200Error("FilterInterpolateShared: inconsistent shapes")
+        fs = int(math.sqrt(float(filt.size(1))))
+        out_a, out_b = torch.empty_like(in_a), torch.empty_like(in_b)
+        S, P = _lib.strides_of, _lib.ptr
+        _lib.call("memc_b200_filter_interpolation_forward_pair", _lib.stream_ptr(in_a), B, Ca, Cb, H, W, fs,
+                  S(in_a), S(in_b), S(flow), S(filt), S(out_a), S(out_b), P(in_a), P(in_b), P(flow), P(filt),
+                  P(out_a), P(out_b), _lib.OVERWRITE)
+        ctx.save_for_backward(in_a, in_b, flow, filt)
+        ctx.fs = fs
+        return out_a, out_b
+
+    @staticmethod
+    def backward(ctx, g_a, g_b):
+        in_a, in_b, flow, filt = ctx.saved_tensors
+        ga1, ga2, ga3 = _fi_backward(in_a, flow, filt, _prep(g_a, "gradoutput_a"), ctx.fs)
+        gb1, gb2, gb3 = _fi_backward(in_b, flow, filt, _prep(g_b, "gradoutput_b"), ctx.fs)
+        return ga1, gb1, ga2 + gb2, ga3 + gb3
+
+
+def FilterInterpolateShared(input_a, input_b, offset, filter):  # noqa: A002 (reference's names)
+    """(FilterInterpolationModule()(input_a, offset, filter), FilterInterpolationModule()(input_b, offset, filter)) in one
+    pass over the flow / filter planes: the RGB frame and its context features of networks/MEMC_Net_star.py:272-285."""
+    return _FilterInterpolateShared.apply(input_a, input_b, offset, filter)
 
 
 def FlowProjectPair(flow_a, flow_b, requires_grad=None):

@@ -66,6 +66,7 @@ _EXTENDED = {
     "memc_b200_filter_interpolation_backward": [_P, _I, _I, _I, _I, _I, _S, _S, _S, _S, _S, _S, _S,
                                                 _P, _P, _P, _P, _P, _P, _P, _I],
     "memc_b200_filter_interpolation_blend_forward": [_P, _I, _I, _I, _I, _I] + [_S] * 9 + [_P] * 9 + [_I],
+    "memc_b200_filter_interpolation_forward_pair": [_P, _I, _I, _I, _I, _I, _I] + [_S] * 6 + [_P] * 6 + [_I],
     "memc_b200_flow_projection_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],
     "memc_b200_flow_projection_backward": [_P, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
     "memc_b200_interpolation_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],

@@ -439,6 +439,28 @@ def test_fused_call_sites_vs_oracle_composition(L, shape, mean):
         close(grads[4 + k], e3, tol=2e-5, what="grad filter%d" % k)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64, 128, 3.0), (1, 3, 16, 96, 160, 8.0), (1, 3, 5, 70, 132, 2.0), (1, 3, 64, 37, 100, 2.0)])
+def test_fused_shared_flow_pair_vs_oracle(L, shape):
+    """fused.FilterInterpolateShared (the RGB frame and its context features warped with ONE flow / filter in one kernel,
+    networks/MEMC_Net_star.py:272-285) against the oracle's two separate warps, forward and backward; the last shape has
+    an odd H: the library composes the two plain calls itself."""
+    from memc_b200 import fused
+    B, Ca, Cb, H, W, sigma = shape
+    in_a, flow, filt, gout_a = fi_case(B, Ca, H, W, 4, sigma, seed=90)
+    rng = np.random.default_rng(6)
+    in_b = rng.standard_normal((B, Cb, H, W)).astype(np.float32)
+    gout_b = rng.standard_normal((B, Cb, H, W)).astype(np.float32)
+    ta, tb, tf, tk = (dev(x).requires_grad_() for x in (in_a, in_b, flow, filt))
+    oa, ob = fused.FilterInterpolateShared(ta, tb, tf, tk)
+    close(oa, cpu.filter_interpolation_forward(in_a, flow, filt, "f64"), what="shared pair: first image")
+    close(ob, cpu.filter_interpolation_forward(in_b, flow, filt, "f64"), what="shared pair: second image")
+    ga, gb, gf, gk = torch.autograd.grad((oa, ob), (ta, tb, tf, tk), (dev(gout_a), dev(gout_b)))
+    a1, a2, a3 = cpu.filter_interpolation_backward(in_a, flow, filt, gout_a, "f64")
+    b1, b2, b3 = cpu.filter_interpolation_backward(in_b, flow, filt, gout_b, "f64")
+    close(ga, a1, tol=2e-5, what="grad first image"), close(gb, b1, tol=2e-5, what="grad second image")
+    close(gf, a2 + b2, tol=2e-5, what="grad flow"), close(gk, a3 + b3, tol=2e-5, what="grad filter")
+
+
 @pytest.mark.parametrize("fillhole", [0, 1])
 def test_fused_flow_project_pair_vs_oracle(L, fillhole):
     """fused.FlowProjectPair against the oracle run on each direction separately (count exact, fill-hole incl.)."""
