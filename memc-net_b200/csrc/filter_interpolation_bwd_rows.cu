@@ -46,10 +46,13 @@ constexpr int GW = 8;       // pixels per group: lane = (p = lane & 7, j = lane 
 constexpr int SW = 72;      // box pitch (words)
 constexpr int SLAB_H = 4;   // the box is made of slabs of 4 rows
 
-// C channels, TH tile rows (= warps), NSLAB slabs at most, MINB resident CTAs per SM
-template <int C, int TH_, int NSLAB_, int MINB_>
+// C channels, TH tile rows (= warps), NSLAB slabs at most, MINB resident CTAs per SM; CACHE: the lane's filter taps and
+// gradoutput values of all 4 groups stay in registers between the bound pass and the scatter (28 registers), else they are
+// read from shared memory a second time (fewer registers: one more CTA per SM)
+template <int C, int TH_, int NSLAB_, int MINB_, bool CACHE_ = true>
 struct Lay {
     static constexpr int TH = TH_, NSLAB = NSLAB_, MINB = MINB_, NT = 32 * TH_;
+    static constexpr bool CACHE = CACHE_;
     static constexpr int STRIP = TH * 16 * GW;  // floats per filter strip [y][i][j][x]
     static constexpr int CH = SLAB_H * SW;      // channel stride inside a slab (words) = 288 = 0 mod 32
     static constexpr int SLAB = C * CH;         // words per slab [c][4][72]
@@ -77,8 +80,8 @@ struct PxGeo {
 };
 
 template <class Y, int C, bool OVERWRITE, bool INT_ACC>
-__device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, float* s_flow, const float* s_img, float* s_acc,
-                                             const PxGeo& me, const float (&wt)[4][4], const float (&go)[4][C], float scale,
+__device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, const float* s_gout, float* s_flow, const float* s_img,
+                                             float* s_acc, const PxGeo& me, const float (&wt_c)[4][4], const float (&go_c)[4][C], float scale,
                                              int x0, int y0, int b, int bx, int by, int box_rows, int lane, int warp) {
     constexpr int TH = Y::TH, STRIP = Y::STRIP;
     const int W = p.W, H = p.H;
@@ -91,6 +94,19 @@ __device__ __forceinline__ void compute_rows(const FiArgs& p, float* s_filt, flo
 #pragma unroll  // wt[g][] / go[g][] live in registers: g must be a compile-time index
     for (int g = 0; g < 4; ++g) {
         const int src = GW * g + pl, xl = src, x = x0 + xl;
+        float wt[4][4], go[4][C];  // only [g] is used: the cached copy, or this group's words read again
+        if (Y::CACHE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wt[g][i] = wt_c[g][i];
+#pragma unroll
+            for (int c = 0; c < C; ++c) go[g][c] = go_c[g][c];
+        } else {
+            const float* f = s_filt + g * STRIP + (warp * 16 + j) * GW + pl;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wt[g][i] = f[i * 4 * GW];
+#pragma unroll
+            for (int c = 0; c < C; ++c) go[g][c] = s_gout[(c * TH + warp) * TW + GW * g + pl];
+        }
         const int code = __shfl_sync(0xffffffffu, me.code, src);
         const float a = __shfl_sync(0xffffffffu, me.alpha, src), bt = __shfl_sync(0xffffffffu, me.beta, src);
         int Lc = 0, T = 0;
@@ -350,12 +366,24 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
     if (any_valid) tma::mbar_wait(&bars[3], 0, 24);
 
     if (scale > 0.f)
-        compute_rows<Y, C, OVERWRITE, true>(p, s_filt, s_flow, s_img, s_acc, me, wt, go, scale, x0, y0, b, bx, by, box_rows, lane, warp);
+        compute_rows<Y, C, OVERWRITE, true>(p, s_filt, s_gout, s_flow, s_img, s_acc, me, wt, go, scale, x0, y0, b, bx, by, box_rows, lane, warp);
     else
-        compute_rows<Y, C, OVERWRITE, false>(p, s_filt, s_flow, s_img, s_acc, me, wt, go, 1.0f, x0, y0, b, bx, by, box_rows, lane, warp);
+        compute_rows<Y, C, OVERWRITE, false>(p, s_filt, s_gout, s_flow, s_img, s_acc, me, wt, go, 1.0f, x0, y0, b, bx, by, box_rows, lane, warp);
 
-    // ---- flush: slabs of gradinput1 by TMA reduce-add, gradinput3 strips and the gradinput2 tile by TMA store
+    // ---- flush: gradinput3 strips and the gradinput2 tile by TMA store -- issued first, they run while the threads convert
+    // the accumulation slabs -- then the slabs of gradinput1 by TMA reduce-add
+    tma::fence_proxy_async();  // this thread's staged gradinput3 / gradinput2 words -> visible to the async proxy
     __syncthreads();
+    if (tid == 0) {
+        // stores / reductions that hang over the right or bottom image edge are clipped by the TMA (tma_probe tests 9-11)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (OVERWRITE) tma::store_5d(&m_gi3, x0 + GW * g, 0, 0, y0, b, s_filt + g * STRIP);
+            else tma::reduce_add_5d(&m_gi3, x0 + GW * g, 0, 0, y0, b, s_filt + g * STRIP);
+        }
+        if (OVERWRITE) tma::store_4d(&m_gi2, x0, y0, 0, b, s_flow);
+        tma::bulk_commit();
+    }
     if (scale > 0.f) {  // fixed point -> fp32 in place
         int4* ai = reinterpret_cast<int4*>(s_acc);
         float4* af = reinterpret_cast<float4*>(s_acc);
@@ -364,17 +392,10 @@ fi_bwd_rows_kernel(const __grid_constant__ CUtensorMap m_flow, const __grid_cons
             af[i] = make_float4((float)q.x * inv_scale, (float)q.y * inv_scale, (float)q.z * inv_scale, (float)q.w * inv_scale);
         }
     }
-    tma::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+    tma::fence_proxy_async();  // converted slabs -> visible to the async proxy
     __syncthreads();
     if (tid == 0) {
-        // stores / reductions that hang over the right or bottom image edge are clipped by the TMA (tma_probe tests 9-11)
         for (int s = 0; s < nslab; ++s) tma::reduce_add_4d(&m_gi1, bx, by + SLAB_H * s, 0, b, s_acc + s * Y::SLAB);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (OVERWRITE) tma::store_5d(&m_gi3, x0 + GW * g, 0, 0, y0, b, s_filt + g * STRIP);
-            else tma::reduce_add_5d(&m_gi3, x0 + GW * g, 0, 0, y0, b, s_filt + g * STRIP);
-        }
-        if (OVERWRITE) tma::store_4d(&m_gi2, x0, y0, 0, b, s_flow);
         tma::bulk_commit();
         tma::bulk_wait_read_all();  // shared memory must stay alive until the TMA has read it
     }
@@ -409,6 +430,8 @@ int launch_rows_c(cudaStream_t stream, const FiArgs& a, bool ow, int variant) {
     using Y6 = Lay<C, 6, 5, 4>;  // 32x6 tile, 192 threads, 50 KB: 4 CTAs / SM
     using Y4 = Lay<C, 4, 4, 5>;  // 32x4 tile, 128 threads, 38 KB: 5 CTAs / SM
     using Y12 = Lay<C, 12, 7, 2>;  // 32x12 tile, 384 threads, 80 KB: 2 CTAs / SM
+    // (Lay<C, 8, 5, 4, false> -- taps re-read instead of cached, 56 KB, 64 registers, 4 CTAs / SM -- measured 0.562 ms
+    // against 0.519 ms: the extra shared-memory reads cost more than the fourth CTA brings; not instantiated)
     if (variant == 4) return ow ? launch_rows<Y12, C, true>(stream, a) : launch_rows<Y12, C, false>(stream, a);
     if (variant == 2) return ow ? launch_rows<Y6, C, true>(stream, a) : launch_rows<Y6, C, false>(stream, a);
     if (variant == 3) return ow ? launch_rows<Y4, C, true>(stream, a) : launch_rows<Y4, C, false>(stream, a);
