@@ -1,8 +1,10 @@
 // runtime.cu -- library info, launch accounting and the strided zero-fill used by the
 // MEMC_B200_OVERWRITE entry points.
 #include "memc_common.cuh"
+#include "tma_utils.cuh"
 #include <atomic>
 #include <mutex>
+#include <string.h>
 
 namespace memc {
 
@@ -13,6 +15,31 @@ static std::atomic<unsigned long long> g_launches{0};
 static std::mutex g_mutex;  // guards the smem-attribute table and the lazy creation of the scratch pools
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- tensor-map cache: 256 direct-mapped entries per process, keyed by (device, everything the encoding depends on)
+namespace tma {
+bool encode_cached(CUtensorMap* map, const MapKey& key) {
+    struct Entry { bool used; int dev; MapKey key; CUtensorMap map; };
+    static Entry table[256];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over the key bytes
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+    for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ kb[i]) * 1099511628211ull;
+    Entry& e = table[(h ^ (uint64_t)dev) & 255u];
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if (e.used && e.dev == dev && memcmp(&e.key, &key, sizeof(MapKey)) == 0) {
+            *map = e.map;
+            return true;
+        }
+    }
+    if (!encode_direct(map, key)) return false;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    e.used = true; e.dev = dev; e.key = key; e.map = *map;
+    return true;
+}
+}  // namespace tma
 
 DeviceGuard::DeviceGuard(const void* ptr) {
     if (!ptr) return;  // empty tensors: nothing will be launched

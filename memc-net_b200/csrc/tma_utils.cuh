@@ -144,12 +144,46 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// Encoded maps are cached (runtime.cu): cuTensorMapEncodeTiled costs 1-2 us and a launch needs 3-7 maps, which is a
+// fifth of a small-frame call; a network calls the ops with the same buffers (the caching allocator hands the same
+// blocks back) and shapes frame after frame.  The key is everything the encoding depends on.
+struct MapKey {
+    const void* base;
+    uint32_t rank, promo, swizzle;
+    uint64_t gdim[5], gstr[4];
+    uint32_t box[5];
+};
+inline bool encode_direct(CUtensorMap* map, const MapKey& key) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5];
+    for (int i = 0; i < 5; ++i) { gdim[i] = key.gdim[i]; box[i] = key.box[i]; }
+    for (int i = 0; i < 4; ++i) gstr[i] = key.gstr[i];
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, key.rank, const_cast<void*>(key.base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)key.swizzle, (CUtensorMapL2promotion)key.promo,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#ifdef MEMC_TMA_NO_CACHE  // standalone tools (tools/tma_probe.cu) do not link runtime.cu
+inline bool encode_cached(CUtensorMap* map, const MapKey& key) { return encode_direct(map, key); }
+#else
+bool encode_cached(CUtensorMap* map, const MapKey& key);
+#endif
+
+inline bool encode_f32(CUtensorMap* map, uint32_t rank, const float* base, const cuuint64_t* gdim, const cuuint64_t* gstr,
+                       const cuuint32_t* box, CUtensorMapL2promotion promo, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
+    MapKey k{};
+    k.base = base; k.rank = rank; k.promo = (uint32_t)promo; k.swizzle = (uint32_t)swz;
+    for (uint32_t i = 0; i < rank; ++i) { k.gdim[i] = gdim[i]; k.box[i] = box[i]; }
+    for (uint32_t i = 0; i + 1 < rank; ++i) k.gstr[i] = gstr[i];
+    return encode_cached(map, k);
+}
+
 // fp32 NCHW tensor [B,C,H,W] with element strides (b,c,h,1) -> rank-4 tiled map, box (bw,bh,bc,1).
 // Returns false when the layout cannot be described (alignment / size limits).
 inline bool make_map_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int W, int64_t sb, int64_t sc,
                           int64_t sh, int bw, int bh, int bc, CUtensorMapL2promotion promo) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
     // a size-1 dimension's stride is irrelevant: substitute a legal one
     if (H == 1) sh = W;
@@ -163,10 +197,7 @@ inline bool make_map_nchw(CUtensorMap* map, const float* base, int B, int C, int
     for (int i = 0; i < 3; ++i)
         if (gstr[i] >= (1ull << 40)) return false;
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return encode_f32(map, 4, base, gdim, gstr, box, promo);
 }
 
 // A [B,16,H,W] tensor of 4x4 tap planes (plane t = 4 j + i: tap row j, tap column i) as a rank-5 map with the
@@ -177,8 +208,6 @@ inline bool make_map_nchw(CUtensorMap* map, const float* base, int B, int C, int
 // a warp whose lanes are (pixel, tap row) pairs.  (The strides are not monotonic; the TMA does not care.)
 inline bool make_map_taps(CUtensorMap* map, const float* base, int B, int H, int W, int64_t sb, int64_t sc, int64_t sh,
                           int bw, int bh, CUtensorMapL2promotion promo) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
     if (H == 1) sh = W;
     if (B == 1) sb = 16 * sc;
@@ -190,10 +219,7 @@ inline bool make_map_taps(CUtensorMap* map, const float* base, int B, int H, int
     for (int i = 0; i < 4; ++i)
         if (gstr[i] >= (1ull << 40)) return false;
     const cuuint32_t box[5] = {(cuuint32_t)bw, 4u, 4u, (cuuint32_t)bh, 1u};
-    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return encode_f32(map, 5, base, gdim, gstr, box, promo);
 }
 
 // The same [B,16,H,W] tap tensor for (pixel, tap COLUMN) lanes working on groups of gx x 2 pixels (forward):
@@ -202,8 +228,6 @@ inline bool make_map_taps(CUtensorMap* map, const float* base, int B, int H, int
 // Folding the batch into the j digit needs dense plane batches (sb == 16 sc) and an even H.
 inline bool make_map_taps_cols(CUtensorMap* map, const float* base, int B, int H, int W, int64_t sb, int64_t sc, int64_t sh,
                                int gx, int bh, CUtensorMapL2promotion promo) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
     if (H % 2 || bh % 2 || (B > 1 && sb != 16 * sc)) return false;
     if (sh % 4 || sc % 4 || sh < W || sc <= 0) return false;
@@ -213,10 +237,7 @@ inline bool make_map_taps_cols(CUtensorMap* map, const float* base, int B, int H
     for (int i = 0; i < 4; ++i)
         if (gstr[i] >= (1ull << 40)) return false;
     const cuuint32_t box[5] = {(cuuint32_t)gx, 2u, 4u, 4u, (cuuint32_t)(bh / 2)};
-    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return encode_f32(map, 5, base, gdim, gstr, box, promo);
 }
 
 }  // namespace tma

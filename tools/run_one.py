@@ -30,6 +30,23 @@ elif op == "fp_fwd":
         lib.call("memc_b200_flow_projection_forward", lib.stream_ptr(flow), B, H, W, 1, S(flow), S(count), S(out),
                  P(flow), P(count), P(out), flags)
 torch.cuda.synchronize()
+if op in ("ip_fwd", "fp_bwd"):
+    H, W = 1080, 1920
+    in1, flow, _, gout = synth.filter_interpolation_case(4, 3, H, W, seed=0, device="cuda")
+    st = lib.stream_ptr(in1)
+    if op == "ip_fwd":
+        out = torch.empty_like(in1)
+        for _ in range(3):
+            lib.call("memc_b200_interpolation_forward", st, 4, 3, H, W, S(in1), S(flow), S(out), P(in1), P(flow), P(out), flags)
+    else:
+        fl = synth.smooth_flow(16, H, W, 6.0, seed=1, device="cuda")
+        cnt, prj = torch.empty(16, 1, H, W, device="cuda"), torch.empty_like(fl)
+        lib.call("memc_b200_flow_projection_forward", st, 16, H, W, 0, S(fl), S(cnt), S(prj), P(fl), P(cnt), P(prj), flags)
+        go, gi = torch.randn_like(fl), torch.empty_like(fl)
+        for _ in range(3):
+            lib.call("memc_b200_flow_projection_backward", st, 16, H, W, S(fl), S(cnt), S(go), S(gi), P(fl), P(cnt), P(go),
+                     P(gi), flags)
+    torch.cuda.synchronize()
 if op in ("ip_bwd", "sc_bwd", "sc_fwd"):
     H, W = 1080, 1920
     B = 4

@@ -1,6 +1,7 @@
 // tma_probe.cu -- which TMA forms does this driver / GPU accept?  (development probe, run on the B200 box)
 //   nvcc -gencode arch=compute_100a,code=sm_100a -I memc-net_b200/csrc -o /tmp/tma_probe tools/tma_probe.cu && for t in 0 1 2 3 4 5 6 7; do /tmp/tma_probe $t; done
 // Each test runs in its own process (an illegal instruction kills the context).
+#define MEMC_TMA_NO_CACHE
 #include "tma_utils.cuh"
 #include <cstdio>
 #include <cstdlib>
