@@ -31,11 +31,21 @@ constexpr int TW = 64, TH = 16, NT = 256, PPT = TW * TH / NT;  // source tile, 4
 constexpr int SW = 96, SH = 32;                                // target box (pitch 96 = 3*32 words)
 constexpr int BOX = SW * SH;
 
-struct __align__(128) Smem {
-    int box[3][SH][SW];  // x, y (fixed point) and count: 36 KB
+// per-tile control words; two sets, used alternately by consecutive splat tiles of a CTA: a tile resets the set of the
+// NEXT tile, so that a tile's atomics need no barrier between "control words initialised" and "first atomic"
+struct Ctl {
     int bb[4];
     unsigned maxbits;
     int kmax;  // largest number of sources of this tile that share one corner cell
+    __device__ __forceinline__ void reset() {
+        bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;
+        maxbits = 0u;
+        kmax = 0;
+    }
+};
+struct __align__(128) Smem {
+    int box[3][SH][SW];  // x, y (fixed point) and count: 36 KB
+    Ctl ctl[2];
 };
 
 __device__ __forceinline__ bool fp_valid(float x2, float y2, int W, int H) {
@@ -77,13 +87,17 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View 
 // to global memory, as do sources whose corner cell misses the staged box.
 //
 // Precondition: a __syncthreads() separates this call from the CTA's previous use of `s`.
-__device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], const float (&fy)[PPT], int x0, int y0,
+// PRE: the control set s.ctl[par] was reset before that barrier (by the previous tile): no barrier is needed before this
+// tile's first atomics on it (one barrier less per tile in the persistent pipeline).
+template <bool PRE>
+__device__ __forceinline__ void splat_tile(Smem& s_, int par, const float (&fx)[PPT], const float (&fy)[PPT], int x0, int y0,
                                            float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H) {
     const int tid = threadIdx.x, lane = tid & 31;
+    struct View_ { int (&box)[3][SH][SW]; int (&bb)[4]; unsigned& maxbits; int& kmax; };
+    View_ s{s_.box, s_.ctl[par].bb, s_.ctl[par].maxbits, s_.ctl[par].kmax};
     if (tid == 0) {
-        s.bb[0] = INT_MAX; s.bb[1] = INT_MIN; s.bb[2] = INT_MAX; s.bb[3] = INT_MIN;
-        s.maxbits = 0u;
-        s.kmax = 0;
+        s_.ctl[par ^ 1].reset();  // for the next tile (nobody touches that set until the barrier at the end of this tile)
+        if (!PRE) s_.ctl[par].reset();
     }
     {   // zero the box
         int4* z = reinterpret_cast<int4*>(&s.box[0][0][0]);
@@ -112,13 +126,13 @@ __device__ __forceinline__ void splat_tile(Smem& s, const float (&fx)[PPT], cons
     mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);  // REDUX
     mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mloc));
-    __syncthreads();  // bounding-box cells initialised, box zeroed
+    if (!PRE) __syncthreads();  // control words initialised
     if (lane == 0 && mnx <= mxx) {
         atomicMin(&s.bb[0], mnx); atomicMax(&s.bb[1], mxx);
         atomicMin(&s.bb[2], mny); atomicMax(&s.bb[3], mxy);
         if (mb) atomicMax(&s.maxbits, mb);
     }
-    __syncthreads();
+    __syncthreads();  // bounding box and maximum complete; box zeroed
     if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (uniform across the CTA)
 
     // corner cells span [min L, max L] x [min T, max T]; box x origin multiple of 4 (vector flush)
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(NT, 4) fp_splat_kernel(const FpArgs p, const i
     float fx[PPT], fy[PPT];
     load_flow(p.flowp, p.flow, x0, y0, b, p.W, p.H, fx, fy);
     float* ox = p.outp + (int64_t)b * p.out.b;
-    splat_tile(s, fx, fy, x0, y0, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b, p.out.h, p.count.h, p.W, p.H);
+    splat_tile<false>(s, 0, fx, fy, x0, y0, ox, ox + p.out.c, p.countp + (int64_t)b * p.count.b, p.out.h, p.count.h, p.W, p.H);
 }
 
 // average + occupancy bit masks.  One CTA = one 128 x 32 pixel block:
@@ -628,7 +642,10 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
     if (tid == 0) {
         s_q[0] = decode_item(p, nS, nA, total, (int)atomicAdd(p.ctrl, 1u));
         s_q[1] = decode_item(p, nS, nA, total, (int)atomicAdd(p.ctrl, 1u));
+        s.ctl[0].reset();
+        s.ctl[1].reset();
     }
+    int splat_par = 0;  // control set of the next splat tile (uniform across the CTA)
     __syncthreads();
     Item it = s_q[0], in = s_q[1];
     int slot = 2;
@@ -654,7 +671,9 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
         if (it.type == 0) {
             {
                 float* acc = p.scratch + (int64_t)(it.frame % 3) * 3 * plane;
-                splat_tile(s, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W, p.H);
+                splat_tile<true>(s, splat_par, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W,
+                                 p.H);
+                splat_par ^= 1;
             }
         } else if (it.type == 1) {
             pipe_average_tile(p, rw, it.tile, it.frame);
