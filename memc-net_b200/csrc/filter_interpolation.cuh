@@ -23,6 +23,8 @@ struct FiArgs {
 // preconditions do not hold (the caller then runs the generic kernels), -1 on error
 int fi_forward_fast(cudaStream_t stream, const FiArgs& a);
 int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool overwrite);
+// C > 4, C % 4 == 0 (filter_interpolation_bwd_chunked.cu): 1 / 0 / -1 as above
+int fi_backward_chunked(cudaStream_t stream, const FiArgs& a, bool overwrite);
 // two images warped with ONE flow / filter in one pass (filter_interpolation_fwd_cols.cu): 1 / 0 / -1 as above
 int fi_forward_cols_pair(cudaStream_t stream, const FiArgs& a, const float* in2, View v_in2, float* out2, View v_out2, int C2);
 // fused FilterInterpolation pair + occlusion blend (forward, fs == 4, C == 3); a0.outp = blended output

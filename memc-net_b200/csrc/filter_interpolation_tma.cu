@@ -1183,7 +1183,8 @@ int fi_blend_forward_fast(cudaStream_t stream, const FiArgs& a0, const FiArgs& a
 
 int fi_backward_fast(cudaStream_t stream, const FiArgs& a, bool ow) {
     const int variant = (a.flags >> 16) & 0xff;
-    if (a.fs != 4 || a.C < 1 || a.C > CB || a.W % 4 || a.B > 65535) return 0;
+    if (a.C > CB) return variant == 1 ? 0 : fi_backward_chunked(stream, a, ow);  // channel chunks (variant 1: generic kernel)
+    if (a.fs != 4 || a.C < 1 || a.W % 4 || a.B > 65535) return 0;
     if (variant != 1) {  // production: (pixel, tap row) lanes
         const int r = fi_backward_rows(stream, a, ow);
         if (r != 0) return r;

@@ -235,6 +235,63 @@ def test_filter_interpolation_backward_kernels_agree(L, shape, overwrite):
             assert err <= TOL * scale, "%s %s: %.3e vs generic (scale %.3g)" % (which, name, err, scale)
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 96, 128, 3.0), (2, 16, 64, 160, 6.0), (1, 64, 130, 200, 4.0), (1, 12, 200, 324, 30.0),
+                                   (1, 8, 33, 96, 1.5), (1, 32, 8, 72, 1.0), (1, 8, 270, 480, 60.0)])
+@pytest.mark.parametrize("overwrite", [True, False])
+def test_filter_interpolation_backward_channel_chunks(L, shape, overwrite):
+    """C > 4 (C % 4 == 0): the channel-chunked tap-row backward (filter_interpolation_bwd_chunked.cu) against the
+    generic kernel and the fp64 oracle, OVERWRITE and the reference's += contract; large sigma = windows that leave
+    the staged box (per-tap path), tiny frames = box clamped into the image."""
+    from memc_b200 import synth
+    B, C, H, W, sigma = shape
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, sigma=sigma, seed=29, device="cuda")
+    base = L.OVERWRITE if overwrite else 0
+    res = []
+    n0 = L.launch_count()
+    for flags in (base, base | L.NO_FAST):
+        fill = 7.0 if overwrite else 0.5
+        g1, g2, g3 = torch.full_like(t1, fill), torch.full_like(t2, fill), torch.full_like(t3, fill)
+        L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(tg), L.strides_of(g1), L.strides_of(g2),
+               L.strides_of(g3), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(tg), L.ptr(g1), L.ptr(g2), L.ptr(g3), flags)
+        res.append((g1, g2, g3))
+    torch.cuda.synchronize()
+    for k, name in enumerate(("gradinput1", "gradinput2", "gradinput3")):
+        gen = res[1][k]
+        scale = max(1.0, float(gen.abs().max()))
+        err = float((res[0][k] - gen).abs().max())
+        assert err <= TOL * scale, "chunked %s: %.3e vs generic (scale %.3g)" % (name, err, scale)
+    if overwrite and H * W <= 130 * 200:
+        e = cpu.filter_interpolation_backward(host(t1), host(t2), host(t3), host(tg), "f64")
+        for got, exp, name in zip(res[0], e, ("gi1", "gi2", "gi3")):
+            close(got, exp, what="chunked %s vs fp64 oracle" % name)
+
+
+def test_filter_interpolation_backward_channel_chunks_nonfinite_and_float_accum(L):
+    """A chunk with NaN / Inf gradients takes the fp32 path for that chunk only (same NaN / Inf masks as the generic
+    kernel, which mirrors the reference arithmetic); MEMC_B200_FLOAT_ACCUM takes it for every chunk."""
+    from memc_b200 import synth
+    B, C, H, W = 1, 16, 96, 160
+    t1, t2, t3, tg = synth.filter_interpolation_case(B, C, H, W, sigma=2.0, seed=31, device="cuda")
+    tg[0, 5, 40, 70] = float("nan")
+    tg[0, 9, 10, 20] = float("inf")
+    res = []
+    for flags in (L.OVERWRITE, L.OVERWRITE | L.FLOAT_ACCUM, L.OVERWRITE | L.NO_FAST):
+        g1, g2, g3 = torch.empty_like(t1), torch.empty_like(t2), torch.empty_like(t3)
+        L.call("memc_b200_filter_interpolation_backward", L.stream_ptr(t1), B, C, H, W, 4, L.strides_of(t1),
+               L.strides_of(t2), L.strides_of(t3), L.strides_of(tg), L.strides_of(g1), L.strides_of(g2),
+               L.strides_of(g3), L.ptr(t1), L.ptr(t2), L.ptr(t3), L.ptr(tg), L.ptr(g1), L.ptr(g2), L.ptr(g3), flags)
+        res.append((g1, g2, g3))
+    torch.cuda.synchronize()
+    for r in res[:2]:
+        for fast, gen in zip(r, res[2]):
+            assert torch.equal(torch.isnan(fast), torch.isnan(gen))
+            assert torch.equal(torch.isinf(fast), torch.isinf(gen))
+            ok = torch.isfinite(gen)
+            assert float((fast[ok] - gen[ok]).abs().max()) <= 1e-5 * max(1.0, float(gen[ok].abs().max()))
+    assert bool(torch.isnan(res[0][0]).any()) and bool(torch.isinf(res[0][0]).any())
+
+
 def test_filter_interpolation_backward_propagates_nonfinite_gradients(L):
     """The fast backward accumulates gradinput1 in per-tile fixed point; a tile whose gradients
     are not finite must fall back to float accumulation so NaN/Inf land where the reference

@@ -26,3 +26,8 @@ for cfg in [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "0,1,2").spli
         print(json.dumps({"cfg": cfg, "ms": t * 1e3, "frac": px * (2 * C + 18) * 4 / t / 1e9 / peak, "bitwise_equal_generic": ok}), flush=True)
     except Exception as e:
         print(json.dumps({"cfg": cfg, "error": str(e)[:200]}), flush=True)
+# backward, C = 64: production (channel-chunked tap-row lanes) vs the generic kernel (MEMC_B200_VARIANT(1))
+for name, fl in (("bwd chunked", lib.OVERWRITE), ("bwd generic", lib.OVERWRITE | lib.variant(1))):
+    _, _, b = fi_calls(B, C, H, W, fl)
+    t = timeit(b, 10)
+    print(json.dumps({"cfg": name, "ms": t * 1e3, "frac": px * (3 * C + 36) * 4 / t / 1e9 / peak}), flush=True)
