@@ -59,9 +59,44 @@ __device__ __forceinline__ void tile_pixel(int k, int& xl, int& yl) {
     xl = (threadIdx.x & 31) + 32 * (seg % (TW / 32));
 }
 
+// L2 eviction policies (createpolicy): the persistent pipeline marks what it streams (flow in) evict-first and what it
+// keeps coming back to (the accumulator ring) evict-last, so that the 75 MB ring is what stays in the 126 MB L2.
+// kind: 0 normal, 1 evict-first, 2 evict-last
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    uint64_t pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ldg_stream_pol(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_add4_pol(float* p, float4 v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ldcg4_pol(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void stcg4_pol(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
+
 // flow of this thread's pixels of tile (x0, y0) of frame b: coalesced read-only loads
+template <bool POL = false>
 __device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View fv, int x0, int y0, int b, int W, int H,
-                                          float (&fx)[PPT], float (&fy)[PPT]) {
+                                          float (&fx)[PPT], float (&fy)[PPT], uint64_t pol = 0) {
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         int xl, yl;
@@ -70,8 +105,8 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View 
         fx[k] = fy[k] = 0.f;
         if (x < W && y < H) {
             const float* f = flowp + (int64_t)b * fv.b + (int64_t)y * fv.h + x;
-            fx[k] = ldg_stream(f);
-            fy[k] = ldg_stream(f + fv.c);
+            fx[k] = POL ? ldg_stream_pol(f, pol) : ldg_stream(f);
+            fy[k] = POL ? ldg_stream_pol(f + fv.c, pol) : ldg_stream(f + fv.c);
         }
     }
 }
@@ -91,7 +126,8 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flowp, View 
 // tile's first atomics on it (one barrier less per tile in the persistent pipeline).
 template <bool PRE>
 __device__ __forceinline__ void splat_tile(Smem& s_, int par, const float (&fx)[PPT], const float (&fy)[PPT], int x0, int y0,
-                                           float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H) {
+                                           float* ox, float* oy, float* cn, int64_t out_h, int64_t cnt_h, int W, int H,
+                                           uint64_t pol = 0) {
     const int tid = threadIdx.x, lane = tid & 31;
     struct View_ { int (&box)[3][SH][SW]; int (&bb)[4]; unsigned& maxbits; int& kmax; };
     View_ s{s_.box, s_.ctl[par].bb, s_.ctl[par].maxbits, s_.ctl[par].kmax};
@@ -230,7 +266,8 @@ __device__ __forceinline__ void splat_tile(Smem& s_, int par, const float (&fx)[
                         const float sc = pl == 2 ? 1.0f : inv_scale;
                         const float4 val = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
                         float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) + (int64_t)(by + uy) * (pl == 2 ? cnt_h : out_h) + bx + ux;
-                        atomicAdd(reinterpret_cast<float4*>(dst), val);
+                        if (PRE) red_add4_pol(dst, val, pol);  // pipeline: the accumulator ring, L2 evict-last
+                        else atomicAdd(reinterpret_cast<float4*>(dst), val);
                     }
                 }
         }
@@ -406,6 +443,7 @@ __global__ void __launch_bounds__(256) fp_fillhole_mask_kernel(float* __restrict
 // ------------------------------------------------------------------------------------
 struct FpPipe {
     int B, H, W, fillhole;
+    int l2_hints;       // 1: flow loads evict-first, accumulator ring evict-last (createpolicy); 0: no hints
     const float* flowp;
     View flow;
     float* outp;
@@ -437,7 +475,7 @@ __device__ __forceinline__ void wait_count(const unsigned* counter, unsigned tar
 
 // average + masks of one 128 x 32 block of frame f (layout of fp_average_mask_kernel); the
 // accumulator cells it consumed are handed back zeroed
-__device__ __forceinline__ void pipe_average_tile(const FpPipe& p, unsigned (*rw)[4], int idx, int f) {
+__device__ __forceinline__ void pipe_average_tile(const FpPipe& p, unsigned (*rw)[4], int idx, int f, uint64_t pol) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bxx = idx % p.nA_x, byy = idx / p.nA_x;
     const int W = p.W, H = p.H;
@@ -463,9 +501,9 @@ __device__ __forceinline__ void pipe_average_tile(const FpPipe& p, unsigned (*rw
             c[h] = sx[h] = sy[h] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (in[h]) {
                 const int64_t o = (int64_t)y * W + x;
-                c[h] = __ldcg(reinterpret_cast<const float4*>(acc + 2 * plane + o));
-                sx[h] = __ldcg(reinterpret_cast<const float4*>(acc + o));
-                sy[h] = __ldcg(reinterpret_cast<const float4*>(acc + plane + o));
+                c[h] = ldcg4_pol(acc + 2 * plane + o, pol);
+                sx[h] = ldcg4_pol(acc + o, pol);
+                sy[h] = ldcg4_pol(acc + plane + o, pol);
             }
         }
 #pragma unroll
@@ -482,9 +520,9 @@ __device__ __forceinline__ void pipe_average_tile(const FpPipe& p, unsigned (*rw
                     if (cc.z > 0.f) { vx.z = sx[h].z / cc.z; vy.z = sy[h].z / cc.z; }
                     if (cc.w > 0.f) { vx.w = sx[h].w / cc.w; vy.w = sy[h].w / cc.w; }
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    __stcg(reinterpret_cast<float4*>(acc + o), z);
-                    __stcg(reinterpret_cast<float4*>(acc + plane + o), z);
-                    __stcg(reinterpret_cast<float4*>(acc + 2 * plane + o), z);
+                    stcg4_pol(acc + o, z, pol);
+                    stcg4_pol(acc + plane + o, z, pol);
+                    stcg4_pol(acc + 2 * plane + o, z, pol);
                 }
                 __stcg(reinterpret_cast<float4*>(ox + o), vx);  // fill-hole reads neighbours back from L2
                 __stcg(reinterpret_cast<float4*>(oy + o), vy);
@@ -652,11 +690,12 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
     float cfx[PPT], cfy[PPT], nfx[PPT], nfy[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) cfx[k] = cfy[k] = nfx[k] = nfy[k] = 0.f;
-    if (it.type == 0) load_flow(p.flowp, p.flow, it.tx * TW, it.tile * TH, it.frame, p.W, p.H, cfx, cfy);
+    const uint64_t pol_flow = l2_policy(p.l2_hints ? 1 : 0), pol_ring = l2_policy(p.l2_hints ? 2 : 0);
+    if (it.type == 0) load_flow<true>(p.flowp, p.flow, it.tx * TW, it.tile * TH, it.frame, p.W, p.H, cfx, cfy, pol_flow);
     while (it.type != -2) {
         int fetched = 0;
         if (tid == 0) fetched = (int)atomicAdd(p.ctrl, 1u);  // the position after next; consumed at the end of this item
-        if (in.type == 0) load_flow(p.flowp, p.flow, in.tx * TW, in.tile * TH, in.frame, p.W, p.H, nfx, nfy);
+        if (in.type == 0) load_flow<true>(p.flowp, p.flow, in.tx * TW, in.tile * TH, in.frame, p.W, p.H, nfx, nfy, pol_flow);
         {   // dependency of this item: normally long satisfied and already known
             const unsigned* dep = nullptr;
             unsigned need = 0;
@@ -672,11 +711,11 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
             {
                 float* acc = p.scratch + (int64_t)(it.frame % 3) * 3 * plane;
                 splat_tile<true>(s, splat_par, cfx, cfy, it.tx * TW, it.tile * TH, acc, acc + plane, acc + 2 * plane, p.W, p.W, p.W,
-                                 p.H);
+                                 p.H, pol_ring);
                 splat_par ^= 1;
             }
         } else if (it.type == 1) {
-            pipe_average_tile(p, rw, it.tile, it.frame);
+            pipe_average_tile(p, rw, it.tile, it.frame, pol_ring);
         } else if (it.type == 2) {
             pipe_fill_tile(p, rw, it.tile, it.frame);
         }
@@ -702,7 +741,7 @@ __global__ void __launch_bounds__(NT, 4) fp_pipeline_kernel(const FpPipe p) {
 size_t pad32(size_t n) { return (n + 31) & ~(size_t)31; }
 
 // OVERWRITE calls: the persistent pipeline.  1 = handled, 0 = not applicable, -1 = error
-int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
+int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a, int l2_hints) {
     const size_t smem = sizeof(Smem);
     if (!ensure_dynamic_smem(fp_pipeline_kernel, smem)) return 0;
     // device properties and occupancy are looked up once per device (this sits on the launch-bound small-frame path)
@@ -732,7 +771,7 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a) {
     if (n_sm <= 0) return 0;
     const int64_t plane = (int64_t)a.H * a.W;
     FpPipe p;
-    p.B = a.B; p.H = a.H; p.W = a.W; p.fillhole = a.fillhole;
+    p.B = a.B; p.H = a.H; p.W = a.W; p.fillhole = a.fillhole; p.l2_hints = l2_hints;
     p.flowp = a.flowp; p.flow = a.flow;
     p.outp = a.outp; p.countp = a.countp;
     p.out_b = a.out.b; p.out_c = a.out.c; p.cnt_b = a.count.b;
@@ -788,7 +827,7 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
     // the library produces every element: persistent pipeline (from 3 frames on; below that its phases
     // cannot overlap across frames and the per-frame launches are quicker: 43 vs 58 us at B = 1, 720p)
     if (overwrite && a.B >= 3 && variant != 1) {
-        const int r = fp_forward_pipeline(stream, a);
+        const int r = fp_forward_pipeline(stream, a, variant == 2 ? 0 : 1);  // variant 2: without the L2 eviction hints
         if (r != 0) return r;
     }
     const size_t smem = sizeof(Smem);

@@ -8,5 +8,7 @@ for kind, fl in (("smooth", synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda
                  ("convergent", synth.radial_flow(B, H, W, 0.9, device="cuda")), ("divergent", synth.radial_flow(B, H, W, -0.5, device="cuda"))):
     cnt, prj = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(fl)
     st = lib.stream_ptr(fl)
-    f = lambda: lib.call("memc_b200_flow_projection_forward", st, B, H, W, 1, S(fl), S(cnt), S(prj), P(fl), P(cnt), P(prj), lib.OVERWRITE)
-    print(kind, "%.3f ms" % (timeit(f, 15, flush=False) * 1e3), flush=True)
+    for v in (0, 2, 0, 2):  # MEMC_B200_VARIANT(2): the pipeline without its L2 eviction hints
+        f = lambda: lib.call("memc_b200_flow_projection_forward", st, B, H, W, 1, S(fl), S(cnt), S(prj), P(fl), P(cnt), P(prj),
+                             lib.OVERWRITE | lib.variant(v))
+        print(kind, "variant", v, "%.3f ms" % (timeit(f, 15, flush=False) * 1e3), flush=True)
