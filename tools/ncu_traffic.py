@@ -3,7 +3,7 @@ write profiles/traffic.json (read by bench.py for roofline.traffic).
     python tools/ncu_traffic.py gpurun_out/bench_fi_bwd.ncu-rep gpurun_out/bench_fi_fwd.ncu-rep"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-out = {"source": "ncu --set full --clock-control none -k regex:fi_(fwd|bwd)_tma python bench.py --steps 2 --warmup 3 --no-cpu",
+out = {"source": "ncu --set full --clock-control none -k regex:fi_bwd_rows | fi_fwd_patch  -s 3 -c 1  python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-networks (tools/profile_round.sh)",
        "workload": "B=4 x 1920x1080, C=3, fs=4 (bench.py)"}
 for rep in sys.argv[1:]:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
