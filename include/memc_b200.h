@@ -120,6 +120,27 @@ MEMC_B200_API int FlowProjection_gpu_backward_kernel(
     const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
     const float *input1, const float *count, const float *gradoutput, float *gradinput1);
 
+/* replaces my_lib_kernel.h:189-200 (called from my_lib_cuda.c:898): FlowProjection with a per-source weight
+ * (input2 [B,1,H,W], e.g. an inverse depth): scatter -w*flow and w -> divide where the accumulated weight > 0 ->
+ * (fillhole ? fill-hole : nothing).  SURVEY section 8(f) rank 4; the reference ships this C side but no Python class. */
+MEMC_B200_API int DepthFlowProjection_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int fillhole,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const float *input1, const float *input2, float *count, float *output);
+
+/* replaces my_lib_kernel.h:202-220 (called from my_lib_cuda.c:963); `output` is the forward's result */
+MEMC_B200_API int DepthFlowProjection_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const float *input1, const float *input2, const float *count, const float *output, const float *gradoutput,
+    float *gradinput1, float *gradinput2);
+
 /* replaces my_lib_kernel.h:67-81 (called from my_lib_cuda.c:402 and, for the Ch variant,
  * :519) */
 MEMC_B200_API int InterpolationLayer_gpu_forward_kernel(
@@ -239,6 +260,18 @@ MEMC_B200_API int memc_b200_flow_projection_backward(
     memc_stream_t stream, int batch, int h, int w,
     memc_strides s_flow, memc_strides s_count, memc_strides s_gout, memc_strides s_gi,
     const float *flow, const float *count, const float *gradoutput, float *gradinput, int flags);
+
+MEMC_B200_API int memc_b200_depth_flow_projection_forward(
+    memc_stream_t stream, int batch, int h, int w, int fillhole,
+    memc_strides s_flow, memc_strides s_depth, memc_strides s_count, memc_strides s_out,
+    const float *flow, const float *depth, float *count, float *output, int flags);
+
+MEMC_B200_API int memc_b200_depth_flow_projection_backward(
+    memc_stream_t stream, int batch, int h, int w,
+    memc_strides s_flow, memc_strides s_depth, memc_strides s_count, memc_strides s_out, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2,
+    const float *flow, const float *depth, const float *count, const float *output, const float *gradoutput,
+    float *gradinput1, float *gradinput2, int flags);
 
 MEMC_B200_API int memc_b200_interpolation_forward(
     memc_stream_t stream, int batch, int channel, int h, int w,

@@ -1,0 +1,432 @@
+// depth_flow_projection.cu -- DepthFlowProjection (the depth-aware variant of the
+// FlowProjection splat): every source pixel splats -w * flow and w (w = input2, e.g. an inverse depth) into the four
+// cells around its target, the sums are divided where the accumulated weight is positive, holes are filled as in
+// FlowProjection; the backward is a gather over the same four cells.
+//
+// Semantics: reference my_package/src/my_lib_kernel.cu:2053-2121 (scatter), :2123-2166 (average), :2169-2263
+// (fill-hole, same walks and the same never-executed downward search as FlowProjection's), :2265-2362 (backward),
+// launchers :2364-2497; CPU twin my_lib.c:1637-1877 (no fill-hole there).  The reference ships the C side and the FFI
+// entry (my_lib_cuda.c:857-985) but no Python Function for it; my_package/functions/DepthFlowProjectionLayer.py here
+// follows FlowProjectionLayer.py's conventions.
+//
+// Average and fill-hole are FlowProjection's own kernels (flow_projection.cu: they only look at count and output, and
+// treat a non-positive accumulated weight exactly like the reference: the walk stops at the first count != 0, only
+// count > 0 contributes).  Forward fast path: dfp_splat_kernel below (weighted corner histogram in shared memory).
+#include "flow_projection.cuh"
+#include <limits.h>
+
+namespace memc {
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+
+struct DfpArgs {
+    FpArgs f;              // flow / count / out (fwd: output, bwd: gradoutput) / gi (= gradinput1)
+    View depth;            // input2 [B,1,H,W]
+    const float* depthp;
+    View fout;             // bwd: the forward's output
+    const float* foutp;
+    View gi2;              // bwd: gradinput2 [B,1,H,W]
+    float* gi2p;
+};
+
+__device__ __forceinline__ bool dfp_valid(float x2, float y2, int W, int H) {
+    return x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1);
+}
+
+// ------------------------------------------------------------------------------ scatter (generic)
+// one source pixel per thread: 4 cells x (out.x, out.y, count); a clamped R / Bm hits the same cell twice, as in the
+// reference (my_lib_kernel.cu:2103-2117)
+__global__ void __launch_bounds__(BX* BY) dfp_scatter_kernel(const DfpArgs p) {
+    const int w = blockIdx.x * BX + threadIdx.x;
+    const int h = blockIdx.y * BY + threadIdx.y;
+    const int b = blockIdx.z;
+    const FpArgs& f = p.f;
+    if (w >= f.W || h >= f.H) return;
+    const float* fl = f.flowp + b * f.flow.b + (int64_t)h * f.flow.h + w;
+    const float fx = ldg_stream(fl);
+    const float fy = ldg_stream(fl + f.flow.c);
+    const float x2 = (float)w + fx, y2 = (float)h + fy;
+    if (!dfp_valid(x2, y2, f.W, f.H)) return;
+    const float wt = ldg_stream(p.depthp + b * p.depth.b + (int64_t)h * p.depth.h + w);
+    const int L = (int)x2, T = (int)y2;
+    const int R = min(L + 1, f.W - 1), Bm = min(T + 1, f.H - 1);
+    float* ox = f.outp + b * f.out.b;
+    float* oy = ox + f.out.c;
+    float* cn = f.countp + b * f.count.b;
+    const int64_t oT = (int64_t)T * f.out.h, oB = (int64_t)Bm * f.out.h;
+    const int64_t cT = (int64_t)T * f.count.h, cB = (int64_t)Bm * f.count.h;
+    const float vx = -wt * fx, vy = -wt * fy;  // my_lib_kernel.cu:2103: "- temp * fx"
+    red_add(ox + oT + L, vx); red_add(ox + oT + R, vx);
+    red_add(ox + oB + L, vx); red_add(ox + oB + R, vx);
+    red_add(oy + oT + L, vy); red_add(oy + oT + R, vy);
+    red_add(oy + oB + L, vy); red_add(oy + oB + R, vy);
+    red_add(cn + cT + L, wt); red_add(cn + cT + R, wt);
+    red_add(cn + cB + L, wt); red_add(cn + cB + R, wt);
+}
+
+// ------------------------------------------------------------------------------ scatter (shared-memory fast path)
+// FlowProjection's corner-histogram recipe (flow_projection_fast.cu) with weights: the SAME three values (-w fx, -w fy,
+// w) go to the four cells (L..L+1) x (T..T+1), so the splat is a 2x2 box filter of the histogram A[T][L] += value.
+// A 64x16 source tile accumulates A in a 96x32 shared-memory box with native int32 atomics: three fixed-point planes
+// (scales 2^e from the tile's max |w f| resp. max |w|) plus an integer multiplicity plane whose atomics return how many
+// sources share a corner cell (K bounds every filtered cell by 4 K M: the scale spends the bits a worst-case bound
+// would waste).  The flush applies the box filter in exact integer arithmetic and leaves through 128-bit vector
+// reductions.  Clamped repeats at the last column / row and sources whose corner misses the box go direct.
+// Tiles the fixed point cannot hold -- a non-finite weight, or weights spanning more than 2^18 (the smallest would be
+// rounded away and a cell could lose its "accumulated weight > 0") -- send every source direct.
+constexpr int TW = 64, TH = 16, NT = 256, PPT = TW * TH / NT;
+constexpr int SW = 96, SH = 32, BOX = SW * SH;
+
+struct __align__(128) DSmem {
+    int box[4][SH][SW];  // -w fx, -w fy, w (fixed point), multiplicity: 48 KB
+    int bb[4];
+    unsigned max_v, max_w, min_w;  // float bit patterns of max |w f|, max |w|, min |w| over w != 0
+    int kmax;
+};
+
+__device__ __forceinline__ void dfp_tile_pixel(int k, int& xl, int& yl) {
+    const int seg = (threadIdx.x >> 5) + k * (NT / 32);
+    yl = seg / (TW / 32);
+    xl = (threadIdx.x & 31) + 32 * (seg % (TW / 32));
+}
+
+__global__ void __launch_bounds__(NT, 4) dfp_splat_kernel(const DfpArgs p, const int b0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DSmem& s = *reinterpret_cast<DSmem*>(smem_raw);
+    const FpArgs& f = p.f;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = f.W, H = f.H, b = b0 + blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    float* ox = f.outp + b * f.out.b;
+    float* oy = ox + f.out.c;
+    float* cn = f.countp + b * f.count.b;
+    const int64_t out_h = f.out.h, cnt_h = f.count.h;
+
+    if (tid == 0) {
+        s.bb[0] = INT_MAX; s.bb[1] = INT_MIN; s.bb[2] = INT_MAX; s.bb[3] = INT_MIN;
+        s.max_v = 0u; s.max_w = 0u; s.min_w = 0x7f800000u;
+        s.kmax = 0;
+    }
+    {
+        int4* z = reinterpret_cast<int4*>(&s.box[0][0][0]);
+        for (int i = tid; i < 4 * BOX / 4; i += NT) z[i] = make_int4(0, 0, 0, 0);
+    }
+    float fx[PPT], fy[PPT], fw[PPT];
+    int L[PPT], T[PPT];
+    bool ok[PPT];
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+    float mv = 0.f, mw = 0.f;
+    unsigned mnw = 0x7f800000u;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        int xl, yl;
+        dfp_tile_pixel(k, xl, yl);
+        const int x = x0 + xl, y = y0 + yl;
+        fx[k] = fy[k] = fw[k] = 0.f;
+        if (x < W && y < H) {
+            const float* fl = f.flowp + (int64_t)b * f.flow.b + (int64_t)y * f.flow.h + x;
+            fx[k] = ldg_stream(fl);
+            fy[k] = ldg_stream(fl + f.flow.c);
+            fw[k] = ldg_stream(p.depthp + (int64_t)b * p.depth.b + (int64_t)y * p.depth.h + x);
+        }
+        const float x2 = (float)x + fx[k], y2 = (float)y + fy[k];
+        ok[k] = x < W && y < H && dfp_valid(x2, y2, W, H);
+        L[k] = ok[k] ? (int)x2 : 0;
+        T[k] = ok[k] ? (int)y2 : 0;
+        if (ok[k]) {
+            mnx = min(mnx, L[k]); mxx = max(mxx, L[k]);
+            mny = min(mny, T[k]); mxy = max(mxy, T[k]);
+            const float aw = fabsf(fw[k]);
+            mv = fmaxf_nan(mv, fmaxf_nan(fabsf(fw[k] * fx[k]), fabsf(fw[k] * fy[k])));
+            mw = fmaxf_nan(mw, aw);
+            if (aw > 0.f) mnw = min(mnw, __float_as_uint(aw));
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    // |x| of a float orders like its bit pattern; NaN patterns sort above +Inf: integer maxima, NaN propagates
+    const unsigned bv = __reduce_max_sync(0xffffffffu, __float_as_uint(mv));
+    const unsigned bw = __reduce_max_sync(0xffffffffu, __float_as_uint(mw));
+    mnw = __reduce_min_sync(0xffffffffu, mnw);
+    __syncthreads();  // control words initialised
+    if (lane == 0 && mnx <= mxx) {
+        atomicMin(&s.bb[0], mnx); atomicMax(&s.bb[1], mxx);
+        atomicMin(&s.bb[2], mny); atomicMax(&s.bb[3], mxy);
+        if (bv) atomicMax(&s.max_v, bv);
+        if (bw) atomicMax(&s.max_w, bw);
+        atomicMin(&s.min_w, mnw);
+    }
+    __syncthreads();  // bounding box and extrema complete; box zeroed
+    if (s.bb[0] > s.bb[1]) return;  // no valid source pixel in this tile (uniform across the CTA)
+
+    int bx = s.bb[0], by = s.bb[2];
+    {
+        const int need_w = s.bb[1] - s.bb[0] + 1 + 3, need_h = s.bb[3] - s.bb[2] + 1;
+        if (need_w > SW) bx += (need_w - SW) / 2;
+        if (need_h > SH) by += (need_h - SH) / 2;
+        bx = max(0, min(bx, W - SW)) & ~3;
+        by = max(0, min(by, H - SH));
+    }
+    // can the fixed point hold this tile?  finite extrema, and the smallest non-zero |w| at least 2^-18 of the largest
+    const float Mv = __uint_as_float(s.max_v), Mw = __uint_as_float(s.max_w), mnW = __uint_as_float(s.min_w);
+    const bool fixed_ok = s.max_v < 0x7f800000u && s.max_w < 0x7f800000u && (Mw == 0.f || mnW * 262144.0f >= Mw);
+
+    bool in_box[PPT];
+    int kloc = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int ux = L[k] - bx, uy = T[k] - by;
+        in_box[k] = fixed_ok && ok[k] && (unsigned)ux < (unsigned)SW && (unsigned)uy < (unsigned)SH;
+        if (in_box[k]) kloc = max(kloc, atomicAdd(&s.box[3][uy][ux], 1) + 1);
+    }
+    kloc = __reduce_max_sync(0xffffffffu, kloc);
+    if (lane == 0 && kloc) atomicMax(&s.kmax, kloc);
+    __syncthreads();
+    float sc_v = 1.0f, inv_v = 1.0f, sc_w = 1.0f, inv_w = 1.0f;
+    {
+        constexpr int LOG2_PX = 31 - __builtin_clz(TW * TH - 1) + 1;  // every source is in exactly one corner cell
+        const int log2_4k = 32 - __clz(4 * max(s.kmax, 1) - 1);       // ceil(log2(4 K))
+        const int head = min(LOG2_PX, log2_4k);
+        int ex;
+        if (fixed_ok && Mv > 0.f) {
+            frexpf(Mv, &ex);
+            const int e = max(-120, min(31 - ex - head, 120));
+            sc_v = ldexpf(1.0f, e); inv_v = ldexpf(1.0f, -e);
+        }
+        if (fixed_ok && Mw > 0.f) {
+            frexpf(Mw, &ex);
+            const int e = max(-120, min(31 - ex - head, 120));
+            sc_w = ldexpf(1.0f, e); inv_w = ldexpf(1.0f, -e);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        if (!ok[k]) continue;
+        const int ux = L[k] - bx, uy = T[k] - by;
+        const float vx = -fw[k] * fx[k], vy = -fw[k] * fy[k];
+        if (in_box[k]) {
+            atomicAdd(&s.box[0][uy][ux], __float2int_rn(vx * sc_v));
+            atomicAdd(&s.box[1][uy][ux], __float2int_rn(vy * sc_v));
+            atomicAdd(&s.box[2][uy][ux], __float2int_rn(fw[k] * sc_w));
+        }
+        const bool last_col = L[k] == W - 1, last_row = T[k] == H - 1;
+        if (__builtin_expect(!in_box[k] || last_col || last_row, 0)) {
+            const int R = min(L[k] + 1, W - 1), Bm = min(T[k] + 1, H - 1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    // in the box: only the clamped repeats are missing from the 2x2 pattern
+                    if (in_box[k] && !((i == 1 && last_col) || (j == 1 && last_row))) continue;
+                    const int cx = i ? R : L[k], cy = j ? Bm : T[k];
+                    red_add(ox + (int64_t)cy * out_h + cx, vx);
+                    red_add(oy + (int64_t)cy * out_h + cx, vy);
+                    red_add(cn + (int64_t)cy * cnt_h + cx, fw[k]);
+                }
+        }
+    }
+    __syncthreads();
+    if (!fixed_ok) return;
+    // ---- flush: 2x2 box filter of the corner histogram, four cells per 128-bit vector reduction, zero vectors skipped
+    const int ax0 = max(s.bb[0], bx) - bx, ax1 = min(s.bb[1], bx + SW - 1) - bx;
+    const int ay0 = max(s.bb[2], by) - by, ay1 = min(s.bb[3], by + SH - 1) - by;
+    if (ax0 > ax1 || ay0 > ay1) return;
+    const int cx1 = min(ax1 + 1, W - 1 - bx), cy1 = min(ay1 + 1, H - 1 - by);
+    const int v0 = ax0 >> 2, v1 = cx1 >> 2;
+    for (int uy = ay0 + (tid >> 5); uy <= cy1; uy += NT / 32)
+        for (int v = v0 + lane; v <= v1; v += 32) {
+            const int ux = v << 2;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                int q[4], a[2][5];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int yy = uy - 1 + rr;
+                    const bool row_ok = (unsigned)yy < (unsigned)SH;
+                    a[rr][0] = (row_ok && ux > 0) ? s.box[pl][yy][ux - 1] : 0;
+                    int4 t = make_int4(0, 0, 0, 0);
+                    if (row_ok && ux < SW) t = *reinterpret_cast<const int4*>(&s.box[pl][yy][ux]);
+                    a[rr][1] = t.x; a[rr][2] = t.y; a[rr][3] = t.z; a[rr][4] = t.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = a[0][k] + a[0][k + 1] + a[1][k] + a[1][k + 1];
+                if ((q[0] | q[1] | q[2] | q[3]) == 0) continue;
+                const float sc = pl == 2 ? inv_w : inv_v;
+                const float4 val = make_float4((float)q[0] * sc, (float)q[1] * sc, (float)q[2] * sc, (float)q[3] * sc);
+                float* dst = (pl == 0 ? ox : pl == 1 ? oy : cn) + (int64_t)(by + uy) * (pl == 2 ? cnt_h : out_h) + bx + ux;
+                atomicAdd(reinterpret_cast<float4*>(dst), val);
+            }
+        }
+}
+
+// ----------------------------------------------------------------------------- backward
+// gradinput1[ch] = - sum over the 4 cells of gradoutput[ch] * w / count;  gradinput2 = - sum over cells and both
+// channels of gradoutput / count * (flow - output)  -- my_lib_kernel.cu:2312-2357, in its order of operations
+// (products and quotients as written; the reference accumulates into the caller's zero-filled buffers with +=).
+template <bool OVERWRITE>
+__global__ void __launch_bounds__(BX* BY, 6) dfp_bwd_kernel(const DfpArgs p) {
+    const int w = blockIdx.x * BX + threadIdx.x;
+    const int h = blockIdx.y * BY + threadIdx.y;
+    const int b = blockIdx.z;
+    const FpArgs& f = p.f;
+    if (w >= f.W || h >= f.H) return;
+    const float* fl = f.flowp + b * f.flow.b + (int64_t)h * f.flow.h + w;
+    const float fx = ldg_stream(fl), fy = ldg_stream(fl + f.flow.c);
+    float* gx = f.gip + b * f.gi.b + (int64_t)h * f.gi.h + w;
+    float* gy = gx + f.gi.c;
+    float* gw = p.gi2p + b * p.gi2.b + (int64_t)h * p.gi2.h + w;
+    const float x2 = (float)w + fx, y2 = (float)h + fy;
+    if (!dfp_valid(x2, y2, f.W, f.H)) {
+        if (OVERWRITE) { stg_stream(gx, 0.f); stg_stream(gy, 0.f); stg_stream(gw, 0.f); }
+        return;
+    }
+    const float wt = ldg_stream(p.depthp + b * p.depth.b + (int64_t)h * p.depth.h + w);
+    const int L = (int)x2, T = (int)y2;
+    const int R = min(L + 1, f.W - 1), Bm = min(T + 1, f.H - 1);
+    const float* cn = f.countp + b * f.count.b;
+    const float* gox = f.goutp + b * f.out.b;
+    const float* goy = gox + f.out.c;
+    const float* fox = p.foutp + b * p.fout.b;
+    const float* foy = fox + p.fout.c;
+    const int cx[4] = {L, R, L, R}, cy[4] = {T, T, Bm, Bm};
+    float c[4], ax[4], ay[4], px[4], py[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // all 20 gathers in flight together
+        c[k] = __ldg(cn + (int64_t)cy[k] * f.count.h + cx[k]);
+        ax[k] = __ldg(gox + (int64_t)cy[k] * f.out.h + cx[k]);
+        ay[k] = __ldg(goy + (int64_t)cy[k] * f.out.h + cx[k]);
+        px[k] = __ldg(fox + (int64_t)cy[k] * p.fout.h + cx[k]);
+        py[k] = __ldg(foy + (int64_t)cy[k] * p.fout.h + cx[k]);
+    }
+    float sx = OVERWRITE ? 0.f : *gx, sy = OVERWRITE ? 0.f : *gy, sw = OVERWRITE ? 0.f : *gw;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sx += -ax[k] * wt / c[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sy += -ay[k] * wt / c[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sw += -ax[k] / c[k] * (fx - px[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sw += -ay[k] / c[k] * (fy - py[k]);
+    *gx = sx;
+    *gy = sy;
+    *gw = sw;
+}
+
+int dfp_forward(cudaStream_t stream, const DfpArgs& a, int flags) {
+    const FpArgs& f = a.f;
+    if (f.B <= 0 || f.H <= 0 || f.W <= 0) return 0;
+    DeviceGuard guard(f.flowp);
+    if (!guard.ok) return -1;
+    if ((flags & MEMC_B200_OVERWRITE) && !(flags & MEMC_B200_NO_ZERO)) {
+        if (zero_fill(stream, f.countp, f.count, f.B, 1, f.H, f.W) != 0) return -1;
+        if (zero_fill(stream, f.outp, f.out, f.B, 2, f.H, f.W) != 0) return -1;
+    }
+    bool done = false;
+    // fast path: 128-bit vector reductions want 16-byte aligned rows; a frame at least one box large
+    if (!(flags & MEMC_B200_NO_FAST) && f.W >= SW && f.H >= SH && f.W % 4 == 0 && f.out.h % 4 == 0 && f.out.c % 4 == 0 &&
+        f.out.b % 4 == 0 && f.count.h % 4 == 0 && f.count.b % 4 == 0 && !(reinterpret_cast<uintptr_t>(f.outp) & 15u) &&
+        !(reinterpret_cast<uintptr_t>(f.countp) & 15u) && ensure_dynamic_smem(dfp_splat_kernel, sizeof(DSmem))) {
+        const dim3 grid((f.W + TW - 1) / TW, (f.H + TH - 1) / TH, 1);
+        for (int b0 = 0; b0 < f.B; b0 += 65535) {
+            dim3 g = grid;
+            g.z = min(65535, f.B - b0);
+            dfp_splat_kernel<<<g, NT, sizeof(DSmem), stream>>>(a, b0);
+            count_launch();
+            if (check_launch("DepthFlowProjection splat")) return -1;
+        }
+        done = true;
+    }
+    if (!done) {
+        if (f.B > 65535) return -1;
+        dim3 block(BX, BY, 1), grid((f.W + BX - 1) / BX, (f.H + BY - 1) / BY, f.B);
+        dfp_scatter_kernel<<<grid, block, 0, stream>>>(a);
+        count_launch();
+        if (check_launch("DepthFlowProjection scatter")) return -1;
+    }
+    return fp_average_fill(stream, f, 0, f.B, true);  // FlowProjection's average (+ fill-hole when f.fillhole)
+}
+
+int dfp_backward(cudaStream_t stream, const DfpArgs& a, int flags) {
+    const FpArgs& f = a.f;
+    if (f.B <= 0 || f.H <= 0 || f.W <= 0) return 0;
+    if (f.B > 65535) return -1;
+    DeviceGuard guard(f.flowp);
+    if (!guard.ok) return -1;
+    dim3 block(BX, BY, 1), grid((f.W + BX - 1) / BX, (f.H + BY - 1) / BY, f.B);
+    if (flags & MEMC_B200_OVERWRITE) dfp_bwd_kernel<true><<<grid, block, 0, stream>>>(a);
+    else dfp_bwd_kernel<false><<<grid, block, 0, stream>>>(a);
+    count_launch();
+    return check_launch("DepthFlowProjection backward");
+}
+
+}  // namespace
+
+}  // namespace memc
+
+using namespace memc;
+
+extern "C" int memc_b200_depth_flow_projection_forward(
+    memc_stream_t stream, int batch, int h, int w, int fillhole,
+    memc_strides s_flow, memc_strides s_depth, memc_strides s_count, memc_strides s_out,
+    const float* flow, const float* depth, float* count, float* output, int flags) {
+    DfpArgs a{};
+    a.f.B = batch; a.f.H = h; a.f.W = w; a.f.fillhole = fillhole;
+    a.f.flow = mk_view(s_flow); a.f.count = mk_view(s_count); a.f.out = mk_view(s_out);
+    a.depth = mk_view(s_depth);
+    a.f.flowp = flow; a.depthp = depth; a.f.countp = count; a.f.outp = output;
+    return dfp_forward(stream, a, flags);
+}
+
+extern "C" int memc_b200_depth_flow_projection_backward(
+    memc_stream_t stream, int batch, int h, int w,
+    memc_strides s_flow, memc_strides s_depth, memc_strides s_count, memc_strides s_out, memc_strides s_gout,
+    memc_strides s_gi1, memc_strides s_gi2,
+    const float* flow, const float* depth, const float* count, const float* output, const float* gradoutput,
+    float* gradinput1, float* gradinput2, int flags) {
+    DfpArgs a{};
+    a.f.B = batch; a.f.H = h; a.f.W = w;
+    a.f.flow = mk_view(s_flow); a.f.count = mk_view(s_count); a.f.out = mk_view(s_gout); a.f.gi = mk_view(s_gi1);
+    a.depth = mk_view(s_depth); a.fout = mk_view(s_out); a.gi2 = mk_view(s_gi2);
+    a.f.flowp = flow; a.depthp = depth; a.f.countp = const_cast<float*>(count); a.foutp = output;
+    a.f.goutp = gradoutput; a.f.gip = gradinput1; a.gi2p = gradinput2;
+    return dfp_backward(stream, a, flags);
+}
+
+// Reference-named launchers (my_lib_kernel.h:189-220): output / gradoutput / gradinput1 use input1's strides, gradinput2
+// input2's (my_lib_kernel.cu:2103, 2312, 2331); caller-zeroed buffers are accumulated into.
+extern "C" int DepthFlowProjection_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement, const int w, const int h, const int channel, const int batch,
+    const int fillhole,
+    const int i1b, const int i1c, const int i1h, const int i1w,
+    const int i2b, const int i2c, const int i2h, const int i2w,
+    const int cb, const int cc, const int ch, const int cw,
+    const float* input1, const float* input2, float* count, float* output) {
+    (void)nElement; (void)cc; (void)i2c;
+    if (channel != 2 || i1w != 1 || i2w != 1 || cw != 1) return -1;
+    DfpArgs a{};
+    a.f.B = batch; a.f.H = h; a.f.W = w; a.f.fillhole = fillhole;
+    a.f.flow = mk_view(i1b, i1c, i1h); a.f.count = mk_view(cb, 0, ch); a.f.out = a.f.flow;
+    a.depth = mk_view(i2b, 0, i2h);
+    a.f.flowp = input1; a.depthp = input2; a.f.countp = count; a.f.outp = output;
+    return dfp_forward(stream, a, 0);
+}
+
+extern "C" int DepthFlowProjection_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement, const int w, const int h, const int channel, const int batch,
+    const int i1b, const int i1c, const int i1h, const int i1w,
+    const int i2b, const int i2c, const int i2h, const int i2w,
+    const int cb, const int cc, const int ch, const int cw,
+    const float* input1, const float* input2, const float* count, const float* output, const float* gradoutput,
+    float* gradinput1, float* gradinput2) {
+    (void)nElement; (void)cc; (void)i2c;
+    if (channel != 2 || i1w != 1 || i2w != 1 || cw != 1) return -1;
+    DfpArgs a{};
+    a.f.B = batch; a.f.H = h; a.f.W = w;
+    a.f.flow = mk_view(i1b, i1c, i1h); a.f.count = mk_view(cb, 0, ch); a.f.out = a.f.flow; a.f.gi = a.f.flow;
+    a.depth = mk_view(i2b, 0, i2h); a.fout = a.f.flow; a.gi2 = a.depth;
+    a.f.flowp = input1; a.depthp = input2; a.f.countp = const_cast<float*>(count); a.foutp = output;
+    a.f.goutp = gradoutput; a.f.gip = gradinput1; a.gi2p = gradinput2;
+    return dfp_backward(stream, a, 0);
+}

@@ -69,6 +69,8 @@ _EXTENDED = {
     "memc_b200_filter_interpolation_forward_pair": [_P, _I, _I, _I, _I, _I, _I] + [_S] * 6 + [_P] * 6 + [_I],
     "memc_b200_flow_projection_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],
     "memc_b200_flow_projection_backward": [_P, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
+    "memc_b200_depth_flow_projection_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
+    "memc_b200_depth_flow_projection_backward": [_P, _I, _I, _I] + [_S] * 7 + [_P] * 7 + [_I],
     "memc_b200_interpolation_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],
     "memc_b200_interpolation_backward": [_P, _I, _I, _I, _I, _S, _S, _S, _S, _S, _P, _P, _P, _P, _P, _I],
     "memc_b200_separable_conv_forward": [_P, _I, _I, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
@@ -81,6 +83,8 @@ _NAMED = {
     "FilterInterpolationLayer_gpu_backward_kernel": [_P] + [_I] * 6 + [_I] * 12 + [_P] * 7,
     "FlowProjection_gpu_forward_kernel": [_P] + [_I] * 6 + [_I] * 8 + [_P] * 3,
     "FlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 4,
+    "DepthFlowProjection_gpu_forward_kernel": [_P] + [_I] * 6 + [_I] * 12 + [_P] * 4,
+    "DepthFlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 12 + [_P] * 7,
     "InterpolationLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 3,
     "InterpolationLayer_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 5,
     "InterpolationChLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 3,

@@ -21,6 +21,7 @@ from memc_b200 import lib as _lib
 __all__ = [
     "FilterInterpolationLayer_gpu_forward", "FilterInterpolationLayer_gpu_backward",
     "FlowProjectionLayer_gpu_forward", "FlowProjectionLayer_gpu_backward",
+    "DepthFlowProjectionLayer_gpu_forward", "DepthFlowProjectionLayer_gpu_backward",
     "InterpolationLayer_gpu_forward", "InterpolationLayer_gpu_backward",
     "InterpolationChLayer_gpu_forward", "InterpolationChLayer_gpu_backward",
     "SeparableConvLayer_gpu_forward", "SeparableConvLayer_gpu_backward",
@@ -115,6 +116,40 @@ def FlowProjectionLayer_gpu_backward(input1, count, gradoutput, gradinput1):
     return _go("FlowProjection_gpu_backward_kernel",
                [gradoutput.numel(), w, h, channel, batch],
                [input1, count], [input1, count, gradoutput, gradinput1])
+
+
+# ---------------------------------------------------------------- DepthFlowProjection
+def DepthFlowProjectionLayer_gpu_forward(input1, input2, count, output, fillhole):
+    """my_lib_cuda.c:857-914 (declared my_lib_cuda.h:101-107)."""
+    batch, channel, h, w = input1.size()
+    if channel != 2:
+        return _ERR
+    if input2.size(1) != 1:
+        return _ERR
+    if input1.stride(0) != output.stride(0) or input1.stride(1) != output.stride(1):
+        return _ERR
+    return _go("DepthFlowProjection_gpu_forward_kernel",
+               [output.numel(), w, h, channel, batch, int(fillhole)],
+               [input1, input2, count], [input1, input2, count, output])
+
+
+def DepthFlowProjectionLayer_gpu_backward(input1, input2, count, output, gradoutput, gradinput1, gradinput2):
+    """my_lib_cuda.c:916-985 (declared my_lib_cuda.h:109-117)."""
+    batch, channel, h, w = input1.size()
+    if channel != 2:
+        return _ERR
+    if input2.size(1) != 1:
+        return _ERR
+    if count.size(0) != batch or count.size(1) != 1:
+        return _ERR
+    if count.size(2) != h or count.size(3) != w:
+        return _ERR
+    if input1.stride(0) != gradinput1.stride(0) or input1.stride(1) != gradinput1.stride(1):
+        return _ERR
+    return _go("DepthFlowProjection_gpu_backward_kernel",
+               [gradoutput.numel(), w, h, channel, batch],
+               [input1, input2, count],
+               [input1, input2, count, output, gradoutput, gradinput1, gradinput2])
 
 
 # ---------------------------------------------------------------------- Interpolation

@@ -102,6 +102,27 @@ def flow_projection_backward(flow, count, gout, precision="f32"):
     return gi
 
 
+def depth_flow_projection_forward(flow, depth, fillhole, precision="f32"):
+    flow, depth = _f32(flow), _f32(depth)
+    B, two, H, W = flow.shape
+    assert two == 2 and depth.shape == (B, 1, H, W)
+    count = np.zeros((B, 1, H, W), np.float32)
+    out = np.zeros((B, 2, H, W), _real(precision))
+    _check(_lib(precision).oracle_depth_flow_projection_forward(
+        B, H, W, _p(flow), _p(depth), _p(count), _p(out), int(fillhole)), "depth_flow_projection_forward")
+    return out, count
+
+
+def depth_flow_projection_backward(flow, depth, count, fout, gout, precision="f32"):
+    flow, depth, count, fout, gout = _f32(flow), _f32(depth), _f32(count), _f32(fout), _f32(gout)
+    B, _, H, W = flow.shape
+    r = _real(precision)
+    gi1, gi2 = np.zeros(flow.shape, r), np.zeros(depth.shape, r)
+    _check(_lib(precision).oracle_depth_flow_projection_backward(
+        B, H, W, _p(flow), _p(depth), _p(count), _p(fout), _p(gout), _p(gi1), _p(gi2)), "depth_flow_projection_backward")
+    return gi1, gi2
+
+
 def interpolation_forward(in1, flow, precision="f32"):
     in1, flow = _f32(in1), _f32(flow)
     B, C, H, W = in1.shape

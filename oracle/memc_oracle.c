@@ -325,6 +325,112 @@ ORACLE_API int oracle_flow_projection_backward(int B, int H, int W, const float 
 }
 
 /* ------------------------------------------------------------------------------------
+ * DepthFlowProjection: FlowProjection with a per-source weight w = input2[b,0,h,w]
+ * (SURVEY.md section 8(f), rank 4).
+ *   scatter + average : my_lib.c:1690-1735 (CUDA: my_lib_kernel.cu:2088-2118, 2158-2163)
+ *   fill-hole         : my_lib_kernel.cu:2203-2259 ONLY (the CPU twin prints "Not implemented", my_lib.c:1738-1740);
+ *                       the same walks as FlowProjection's, incl. the downward search that never runs (:2228)
+ *   backward          : my_lib.c:1808-1872 (CUDA: my_lib_kernel.cu:2297-2357)
+ * `count` (the accumulated weight) is float in both builds, as in the reference; in the float build every
+ * expression keeps the reference's order of operations (-w * f, go * w / count, go / count * (f - out)).
+ * ---------------------------------------------------------------------------------- */
+ORACLE_API int oracle_depth_flow_projection_forward(int B, int H, int W, const float *flow, const float *depth,
+                                                    float *count, real *out, int fillhole)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *fxp = flow + ((size_t)b * 2 + 0) * plane;
+        const float *fyp = flow + ((size_t)b * 2 + 1) * plane;
+        const float *wp = depth + (size_t)b * plane;
+        real *ox = out + ((size_t)b * 2 + 0) * plane;
+        real *oy = out + ((size_t)b * 2 + 1) * plane;
+        float *cnt = count + (size_t)b * plane;
+
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const float fx = fxp[(size_t)h * W + w], fy = fyp[(size_t)h * W + w];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                const float wt = wp[(size_t)h * W + w];
+                const real vx = -(real)wt * (real)fx, vy = -(real)wt * (real)fy;
+                for (int k = 0; k < 4; ++k) ox[cell[k]] += vx;
+                for (int k = 0; k < 4; ++k) oy[cell[k]] += vy;
+                for (int k = 0; k < 4; ++k) cnt[cell[k]] += wt * 1.0f;
+            }
+
+        for (size_t p = 0; p < plane; ++p) {
+            const float c = cnt[p];
+            if (c > 0.0f) { ox[p] /= (real)c; oy[p] /= (real)c; }
+        }
+
+        if (!fillhole) continue;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                if (cnt[(size_t)h * W + w] > 0.0f) continue;
+                int lo = w, ro = w, uo = h;
+                float lt = 0.0f, rt = 0.0f, ut = 0.0f;
+                while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cnt[(size_t)h * W + lo]; }
+                while (rt == 0.0f && ro + 1 <= W - 1) { ++ro; rt = cnt[(size_t)h * W + ro]; }
+                while (ut == 0.0f && uo - 1 >= 0) { --uo; ut = cnt[(size_t)uo * W + w]; }
+                if (lt + rt + ut <= 0.0f) continue;
+                const real l = lt > 0.0f ? (real)1 : (real)0;
+                const real r = rt > 0.0f ? (real)1 : (real)0;
+                const real u = ut > 0.0f ? (real)1 : (real)0;
+                const real den = l + r + u;
+                real sx = (real)0, sy = (real)0;
+                if (lt > 0.0f) { sx += ox[(size_t)h * W + lo]; sy += oy[(size_t)h * W + lo]; }
+                if (rt > 0.0f) { sx += ox[(size_t)h * W + ro]; sy += oy[(size_t)h * W + ro]; }
+                if (ut > 0.0f) { sx += ox[(size_t)uo * W + w]; sy += oy[(size_t)uo * W + w]; }
+                ox[(size_t)h * W + w] = sx / den;
+                oy[(size_t)h * W + w] = sy / den;
+            }
+    }
+    return 0;
+}
+
+/* `fout` is the forward's output (float: what the forward stored).  gi1 / gi2 are added into. */
+ORACLE_API int oracle_depth_flow_projection_backward(int B, int H, int W, const float *flow, const float *depth,
+                                                     const float *count, const float *fout, const float *gout,
+                                                     real *gi1, real *gi2)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *cnt = count + (size_t)b * plane;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float f[2] = {flow[((size_t)b * 2 + 0) * plane + pix], flow[((size_t)b * 2 + 1) * plane + pix]};
+                const float x2 = (float)w + f[0], y2 = (float)h + f[1];
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                const float wt = depth[(size_t)b * plane + pix];
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float *go = gout + ((size_t)b * 2 + ch) * plane;
+                    real *g = gi1 + ((size_t)b * 2 + ch) * plane + pix;
+                    for (int k = 0; k < 4; ++k) *g += -(real)go[cell[k]] * (real)wt / (real)cnt[cell[k]];
+                }
+                real *gw = gi2 + (size_t)b * plane + pix;
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float *go = gout + ((size_t)b * 2 + ch) * plane;
+                    const float *po = fout + ((size_t)b * 2 + ch) * plane;
+                    for (int k = 0; k < 4; ++k)
+                        *gw += -(real)go[cell[k]] / (real)cnt[cell[k]] * ((real)f[ch] - (real)po[cell[k]]);
+                }
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Interpolation (plain bilinear backward warp), any channel count (the reference's
  * InterpolationCh variant is the same code with the channel==3 check removed,
  * my_lib_cuda.c:490,519).  my_lib.c:480-527 (fwd), 590-660 (bwd).

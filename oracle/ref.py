@@ -113,6 +113,27 @@ def cpu_flow_projection_backward(flow, count, gout):
     return gi
 
 
+def cpu_depth_flow_projection_forward(flow, depth):
+    """scatter + average only: the reference CPU path has no fill-hole (my_lib.c:1738-1740)."""
+    flow, depth = _c(flow), _c(depth)
+    B, _, H, W = flow.shape
+    count = np.zeros((B, 1, H, W), np.float32)
+    out = np.zeros_like(flow)
+    rc = _cpu().DepthFlowProjectionLayer_cpu_forward(_TH(flow).ref, _TH(depth).ref, _TH(count).ref, _TH(out).ref,
+                                                     ctypes.c_int(0))
+    assert rc == 0, rc
+    return out, count
+
+
+def cpu_depth_flow_projection_backward(flow, depth, count, fout, gout):
+    flow, depth, count, fout, gout = _c(flow), _c(depth), _c(count), _c(fout), _c(gout)
+    g1, g2 = np.zeros_like(flow), np.zeros_like(depth)
+    rc = _cpu().DepthFlowProjectionLayer_cpu_backward(_TH(flow).ref, _TH(depth).ref, _TH(count).ref, _TH(fout).ref,
+                                                      _TH(gout).ref, _TH(g1).ref, _TH(g2).ref)
+    assert rc == 0, rc
+    return g1, g2
+
+
 def cpu_interpolation_forward(in1, flow):
     in1, flow = _c(in1), _c(flow)
     out = np.zeros_like(in1)
@@ -226,6 +247,30 @@ def gpu_flow_projection_backward(flow, count, gout, gi=None):
         *_s(flow), *_s(count), _d(flow), _d(count), _d(gout), _d(gi))
     assert rc == 0, rc
     return gi
+
+
+def gpu_depth_flow_projection_forward(flow, depth, fillhole, bufs=None):
+    import torch
+    B, _, H, W = flow.shape
+    if bufs is None:
+        bufs = (torch.zeros(B, 1, H, W, device=flow.device), torch.zeros_like(flow))
+    count, out = bufs
+    rc = _gpu().DepthFlowProjection_gpu_forward_kernel(
+        _stream(), _i(out.numel()), _i(W), _i(H), _i(2), _i(B), _i(fillhole),
+        *_s(flow), *_s(depth), *_s(count), _d(flow), _d(depth), _d(count), _d(out))
+    assert rc == 0, rc
+    return out, count
+
+
+def gpu_depth_flow_projection_backward(flow, depth, count, fout, gout):
+    import torch
+    B, _, H, W = flow.shape
+    g1, g2 = torch.zeros_like(flow), torch.zeros_like(depth)
+    rc = _gpu().DepthFlowProjection_gpu_backward_kernel(
+        _stream(), _i(gout.numel()), _i(W), _i(H), _i(2), _i(B),
+        *_s(flow), *_s(depth), *_s(count), _d(flow), _d(depth), _d(count), _d(fout), _d(gout), _d(g1), _d(g2))
+    assert rc == 0, rc
+    return g1, g2
 
 
 def gpu_interpolation_forward(in1, flow, out=None):

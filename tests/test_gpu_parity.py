@@ -646,6 +646,140 @@ def test_flow_projection_vs_reference_cuda_kernels(L, fillhole):
         close(gi, host(ref.gpu_flow_projection_backward(t, r_count, gout)), what="FlowProjection bwd vs reference CUDA")
 
 
+# ------------------------------------------------------------------- DepthFlowProjection
+def _inverse_depth(shape, seed):
+    rng = np.random.default_rng(seed)
+    return (1e-6 + 1.0 / rng.uniform(0.5, 20.0, shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", FP_SHAPES + [(2, 270, 480, 6.0)])
+@pytest.mark.parametrize("fillhole", [0, 1])
+@pytest.mark.parametrize("no_fast", [False, True])
+def test_depth_flow_projection_vs_oracle(L, shape, fillhole, no_fast):
+    """Function / Module surface (fast shared-memory splat when the frame is at least one box large) and the generic
+    kernels (MEMC_B200_NO_FAST) against the fp64 oracle, forward (+ fill-hole) and backward for both inputs."""
+    from my_package.modules.DepthFlowProjectionModule import DepthFlowProjectionModule
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=41)
+    depth = _inverse_depth((B, 1, H, W), 43)
+    eo, ec = cpu.depth_flow_projection_forward(flow, depth, fillhole, "f64")
+    if no_fast:
+        S, P = L.strides_of, L.ptr
+        t, d = dev(flow), dev(depth)
+        count, out = torch.full((B, 1, H, W), 7.0, device="cuda"), torch.full_like(t, -3.0)  # OVERWRITE ignores it
+        L.call("memc_b200_depth_flow_projection_forward", L.stream_ptr(t), B, H, W, fillhole, S(t), S(d), S(count), S(out),
+               P(t), P(d), P(count), P(out), L.OVERWRITE | L.NO_FAST)
+        close(count, ec, what="DepthFlowProjection count (generic)")
+        close(out, eo, what="DepthFlowProjection out (generic)")
+        return
+    mod = DepthFlowProjectionModule(requires_grad=not fillhole)
+    t, d = dev(flow).requires_grad_(not fillhole), dev(depth).requires_grad_(not fillhole)
+    out = mod(t, d)
+    close(mod.f.count, ec, what="DepthFlowProjection count")
+    close(out, eo, what="DepthFlowProjection out")
+    if not fillhole:
+        gout = np.random.default_rng(3).standard_normal(flow.shape).astype(np.float32)
+        g1, g2 = torch.autograd.grad(out, (t, d), dev(gout))
+        e1, e2 = cpu.depth_flow_projection_backward(flow, depth, host(mod.f.count), host(out), gout, "f64")
+        close(g1, e1, what="DepthFlowProjection gi1")
+        close(g2, e2, what="DepthFlowProjection gi2")
+
+
+def test_depth_flow_projection_named_abi_reference_contract(L):
+    """my_lib_cuda.h:101-117: caller-zeroed count / output, gradients accumulated with += for valid pixels only."""
+    import my_package._ext.my_lib as my_lib
+    B, H, W = 2, 48, 128
+    flow = flow_case(B, H, W, 5.0, seed=47)
+    depth = _inverse_depth((B, 1, H, W), 49)
+    t, d = dev(flow), dev(depth)
+    for fillhole in (0, 1):
+        count, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.DepthFlowProjectionLayer_gpu_forward(t, d, count, out, fillhole) == 0
+        eo, ec = cpu.depth_flow_projection_forward(flow, depth, fillhole, "f64")
+        close(count, ec, what="named DepthFlowProjection count")
+        close(out, eo, what="named DepthFlowProjection fwd fillhole=%d" % fillhole)
+    gout = np.random.default_rng(4).standard_normal(flow.shape).astype(np.float32)
+    x2 = np.arange(W, dtype=np.float32)[None, None, :] + flow[:, 0]
+    y2 = np.arange(H, dtype=np.float32)[None, :, None] + flow[:, 1]
+    with np.errstate(invalid="ignore"):
+        valid = ((x2 >= 0) & (y2 >= 0) & (x2 <= W - 1) & (y2 <= H - 1))[:, None]
+    e1, e2 = cpu.depth_flow_projection_backward(flow, depth, host(count), host(out), gout, "f64")
+    for prefill in (0.0, 1.0):
+        g1, g2 = torch.full_like(t, prefill), torch.full_like(d, prefill)
+        assert my_lib.DepthFlowProjectionLayer_gpu_backward(t, d, count, out, dev(gout), g1, g2) == 0
+        close(g1, np.where(valid, e1 + prefill, prefill), what="named DepthFlowProjection gi1")
+        close(g2, np.where(valid, e2 + prefill, prefill), what="named DepthFlowProjection gi2")
+    assert my_lib.DepthFlowProjectionLayer_gpu_forward(t, dev(np.concatenate([depth, depth], 1)), count, out, 0) == -1
+    assert my_lib.DepthFlowProjectionLayer_gpu_forward(dev(np.concatenate([flow, flow], 1)), d, count, out, 0) == -1
+
+
+@pytest.mark.parametrize("kind", ["contention", "divergent", "uniform", "tear", "wide_weights", "nonfinite_weight"])
+def test_depth_flow_projection_regimes(L, kind):
+    """The FlowProjection regimes with weights, plus the tiles the fixed point must hand to the direct path: weights
+    spanning 2^30 inside a tile, and a NaN / Inf weight (which must land exactly where the generic kernel puts it)."""
+    from memc_b200 import synth
+    S, P = L.strides_of, L.ptr
+    B, H, W = 2, 270, 480
+    if kind == "contention":
+        t = synth.radial_flow(B, H, W, 0.9, device="cuda")
+    elif kind == "divergent":
+        t = synth.radial_flow(B, H, W, -1.5, device="cuda")
+    elif kind == "tear":
+        t = synth.tear_flow(B, H, W, 20.0, seed=4, device="cuda")
+    elif kind == "uniform":
+        t = synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda")
+    else:
+        t = synth.smooth_flow(B, H, W, 5.0, seed=6, device="cuda")
+    depth = _inverse_depth((B, 1, H, W), 53)
+    if kind == "wide_weights":
+        depth[:, :, ::7, ::5] *= np.float32(2.0 ** -30)
+    if kind == "nonfinite_weight":
+        depth[0, 0, 100, 200] = np.nan
+        depth[1, 0, 30, 40] = np.inf
+    d = dev(depth)
+    res = []
+    for flags in (L.OVERWRITE, L.OVERWRITE | L.NO_FAST):
+        count, out = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(t)
+        L.call("memc_b200_depth_flow_projection_forward", L.stream_ptr(t), B, H, W, 1, S(t), S(d), S(count), S(out),
+               P(t), P(d), P(count), P(out), flags)
+        res.append((count, out))
+    torch.cuda.synchronize()
+    if kind == "nonfinite_weight":
+        for fast, gen in zip(res[0], res[1]):
+            assert torch.equal(torch.isnan(fast), torch.isnan(gen)) and torch.equal(torch.isinf(fast), torch.isinf(gen))
+            ok = torch.isfinite(gen)
+            assert float((fast[ok] - gen[ok]).abs().max()) <= 1e-5 * max(1.0, float(gen[ok].abs().max()))
+        assert bool(torch.isnan(res[0][1]).any())
+        return
+    eo, ec = cpu.depth_flow_projection_forward(host(t), depth, 1, "f64")
+    tol = 5e-5 if kind == "contention" else TOL
+    for (count, out), name in zip(res, ("fast", "generic")):
+        close(count, ec, tol=tol, what="%s %s count" % (kind, name))
+        close(out, eo, tol=tol, what="%s %s out" % (kind, name))
+
+
+@pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_depth_flow_projection_vs_reference_cuda_kernels(L, fillhole):
+    import my_package._ext.my_lib as my_lib
+    from memc_b200 import synth
+    B, H, W = 2, 180, 320
+    d = dev(_inverse_depth((B, 1, H, W), 59))
+    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -1.5, device="cuda"),
+              synth.tear_flow(B, H, W, 12.0, seed=3, device="cuda")):
+        r_out, r_count = ref.gpu_depth_flow_projection_forward(t, d, fillhole)
+        count, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.DepthFlowProjectionLayer_gpu_forward(t, d, count, out, fillhole) == 0
+        close(count, host(r_count), what="DepthFlowProjection count vs reference CUDA")
+        close(out, host(r_out), what="DepthFlowProjection vs reference CUDA (fillhole=%d)" % fillhole)
+        gout = torch.randn_like(t)
+        g1, g2 = torch.zeros_like(t), torch.zeros_like(d)
+        assert my_lib.DepthFlowProjectionLayer_gpu_backward(t, d, r_count, r_out, gout, g1, g2) == 0
+        r1, r2 = ref.gpu_depth_flow_projection_backward(t, d, r_count, r_out, gout)
+        close(g1, host(r1), what="DepthFlowProjection gi1 vs reference CUDA")
+        close(g2, host(r2), what="DepthFlowProjection gi2 vs reference CUDA")
+
+
 @pytest.mark.parametrize("shape", [(7, 64, 96), (5, 70, 260), (3, 33, 3840), (1, 1100, 128), (4, 45, 2100)])
 @pytest.mark.parametrize("fillhole", [0, 1])
 def test_flow_projection_pipeline_many_frames(L, shape, fillhole):

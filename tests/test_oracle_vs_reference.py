@@ -52,6 +52,29 @@ def test_flow_projection_bit_exact(shape):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0)])
+@pytest.mark.parametrize("weights", ["inverse_depth", "signed"])
+def test_depth_flow_projection_bit_exact(shape, weights):
+    """the depth-weighted splat against my_lib.c:1637-1877 (forward without fill-hole: the
+    reference's CPU twin has none; backward reads the forward's output)."""
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=13)
+    rng = np.random.default_rng(17)
+    depth = (1e-6 + 1.0 / rng.uniform(0.5, 20.0, (B, 1, H, W))).astype(np.float32)
+    if weights == "signed":  # not an inverse depth: negative and zero weights, cells whose accumulated weight is <= 0
+        depth = rng.standard_normal((B, 1, H, W)).astype(np.float32)
+        depth[rng.random(depth.shape) < 0.1] = 0.0
+    out, count = cpu.depth_flow_projection_forward(flow, depth, fillhole=0)
+    rout, rcount = ref.cpu_depth_flow_projection_forward(flow, depth)
+    assert np.array_equal(count, rcount) and np.array_equal(out, rout, equal_nan=True)
+    gout = rng.standard_normal(flow.shape).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for a, b in zip(cpu.depth_flow_projection_backward(flow, depth, count, out, gout),
+                        ref.cpu_depth_flow_projection_backward(flow, depth, count, out, gout)):
+            assert np.array_equal(a, b, equal_nan=True)
+
+
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0)])
 def test_interpolation_bit_exact(shape):
     B, C, H, W, sigma = shape
