@@ -278,6 +278,38 @@ def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
         del fl, cnt, prj
     torch.cuda.empty_cache()
 
+    # --- DepthFlowProjection: the same splat with a per-source weight (inverse depth), B = 16
+    dw = synth.inverse_depth(FB, H, W, seed=7, device=dev)
+    for kind, make in (regimes[0], regimes[2]):
+        fl = make()
+        cnt, prj = torch.empty(FB, 1, H, W, device=dev), torch.empty_like(fl)
+        t = _timed(torch, lambda: lib.call("memc_b200_depth_flow_projection_forward", st, FB, H, W, 1, S(fl), S(dw), S(cnt), S(prj),
+                                           P(fl), P(dw), P(cnt), P(prj), lib.OVERWRITE))
+        tl = None
+        if have_ref:
+            def l_dfp():
+                cnt.zero_(); prj.zero_()
+                ref.gpu_depth_flow_projection_forward(fl, dw, 1, (cnt, prj))
+            tl = _timed(torch, l_dfp, 3)
+        entry("DepthFlowProjection splat + hole-fill 1920x1080, batch 16, %s flow" % kind, FB * H * W, 24, t, tl)
+        if kind == "smooth":
+            go_, g1_, g2_ = torch.randn_like(fl), torch.empty_like(fl), torch.empty_like(dw)
+            t = _timed(torch, lambda: lib.call("memc_b200_depth_flow_projection_backward", st, FB, H, W, S(fl), S(dw), S(cnt), S(prj),
+                                               S(go_), S(g1_), S(g2_), P(fl), P(dw), P(cnt), P(prj), P(go_), P(g1_), P(g2_),
+                                               lib.OVERWRITE))
+            tl = None
+            if have_ref:
+                def l_dfpb():
+                    g1_.zero_(); g2_.zero_()
+                    ref.gpu_depth_flow_projection_backward(fl, dw, cnt, prj, go_, (g1_, g2_))
+                tl = _timed(torch, l_dfpb, 3)
+            # read flow 8 + weight 4 + count 4 + output 8 + gradoutput 8, write gradinput1 8 + gradinput2 4
+            entry("DepthFlowProjection backward 1920x1080, batch 16", FB * H * W, 44, t, tl)
+            del go_, g1_, g2_
+        del fl, cnt, prj
+    del dw
+    torch.cuda.empty_cache()
+
     # --- the 64-channel context warp of MEMC_Net_star, forward and backward
     c_in, c_flow, c_filt, c_go = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
     c_out = torch.empty_like(c_in)

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BX* BY) fp_fillhole_kernel(const FpArgs p) {
     const int b = blockIdx.z;
     if (w >= p.W || h >= p.H) return;
     const float* cn = p.countp + b * p.count.b;
-    if (cn[h * p.count.h + w] > 0.0f) return;
+    if (!(cn[h * p.count.h + w] <= 0.0f)) return;  // my_lib_kernel.cu:1778 `if(temp <= 0.0f)`: a NaN count is not a hole
     int lo = w, ro = w, uo = h;
     float lt = 0.f, rt = 0.f, ut = 0.f;
     const float* crow = cn + h * p.count.h;

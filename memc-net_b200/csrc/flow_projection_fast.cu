@@ -296,6 +296,10 @@ __global__ void __launch_bounds__(NT, 4) fp_splat_kernel(const FpArgs p, const i
 // The masks turn fill-hole's per-pixel linear walks (O(W) loads when holes are large: the
 // legacy kernel needs 30 ms per 16 frames when the flow converges and most of the frame is a
 // hole) into a few word loads plus clz / ffs -- with exactly the same result.
+// SIGNED (DepthFlowProjection: count is an accumulated WEIGHT and may be negative or NaN where something landed): the
+// bit is count != 0 -- where the reference's walks stop (my_lib_kernel.cu:2210-2225) -- and the fill kernel looks at
+// the sign of what it found.
+template <bool SIGNED>
 __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict__ out, const float* __restrict__ count,
                                                               unsigned* __restrict__ rowmask, unsigned* __restrict__ colmask,
                                                               int W, int H, int Wt, int Ht, int64_t out_c) {
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict_
         }
         // nibble of this lane -> the 32-pixel word of its 8-lane group (bit = pixel x % 32)
         unsigned nib = (c.x > 0.f ? 1u : 0u) | (c.y > 0.f ? 2u : 0u) | (c.z > 0.f ? 4u : 0u) | (c.w > 0.f ? 8u : 0u);
+        if (SIGNED) nib = (c.x != 0.f ? 1u : 0u) | (c.y != 0.f ? 2u : 0u) | (c.z != 0.f ? 4u : 0u) | (c.w != 0.f ? 8u : 0u);
         unsigned word = nib << (4 * (lane & 7));
         word |= __shfl_xor_sync(0xffffffffu, word, 1);
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
@@ -348,16 +353,24 @@ __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict_
 // fill-hole with the masks: identical semantics to flow_projection.cu's fp_fillhole_kernel
 // (nearest counted pixel to the left, right and above; never below, my_lib_kernel.cu:1799).
 // The word walks fetch four words per step (independent loads) and stop at the first hit.
+// SIGNED: the masks mark count != 0; a marked pixel is still a hole when its count is negative, and what a walk finds
+// contributes only when it is positive -- the reference's arithmetic on the found counts (my_lib_kernel.cu:2230-2258).
+template <bool SIGNED>
 __global__ void __launch_bounds__(256) fp_fillhole_mask_kernel(float* __restrict__ out, const unsigned* __restrict__ rowmask,
                                                                const unsigned* __restrict__ colmask, int W, int H, int Wt,
-                                                               int Ht, int64_t out_b, int64_t out_c) {
+                                                               int Ht, int64_t out_b, int64_t out_c,
+                                                               const float* __restrict__ count, int64_t cnt_b) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int b = blockIdx.z;
     if (x >= W || y >= H) return;
     const unsigned* rm = rowmask + ((int64_t)b * H + y) * Wt;
     const int wi0 = x >> 5, bit = x & 31;
     const unsigned word = rm[wi0];
-    if ((word >> bit) & 1u) return;  // counted pixel: not a hole
+    const float* cn = SIGNED ? count + (int64_t)b * cnt_b : nullptr;
+    if ((word >> bit) & 1u) {
+        if (!SIGNED) return;  // counted pixel: not a hole
+        if (!(cn[(int64_t)y * W + x] <= 0.0f)) return;  // positive (or NaN) accumulated weight: not a hole
+    }
     int lo = -1, ro = -1, uo = -1;
     {   // left: highest set bit below x
         unsigned m = word & ((1u << bit) - 1u);
@@ -404,6 +417,17 @@ __global__ void __launch_bounds__(256) fp_fillhole_mask_kernel(float* __restrict
     float* oy = ox + out_c;
     float sx = 0.f, sy = 0.f, den = 0.f;
     const int64_t row = (int64_t)y * W;
+    if (SIGNED) {
+        const float lt = lo >= 0 ? cn[row + lo] : 0.f, rt = ro >= 0 ? cn[row + ro] : 0.f;
+        const float ut = uo >= 0 ? cn[(int64_t)uo * W + x] : 0.f;
+        if (lt + rt + ut <= 0.0f) return;
+        if (lt > 0.0f) { sx += ox[row + lo]; sy += oy[row + lo]; den += 1.f; }
+        if (rt > 0.0f) { sx += ox[row + ro]; sy += oy[row + ro]; den += 1.f; }
+        if (ut > 0.0f) { sx += ox[(int64_t)uo * W + x]; sy += oy[(int64_t)uo * W + x]; den += 1.f; }
+        ox[row + x] = sx / den;
+        oy[row + x] = sy / den;
+        return;
+    }
     if (lo >= 0) { sx += ox[row + lo]; sy += oy[row + lo]; den += 1.f; }
     if (ro >= 0) { sx += ox[row + ro]; sy += oy[row + ro]; den += 1.f; }
     if (uo >= 0) { sx += ox[(int64_t)uo * W + x]; sy += oy[(int64_t)uo * W + x]; den += 1.f; }
@@ -816,23 +840,42 @@ int fp_forward_pipeline(cudaStream_t stream, const FpArgs& a, int l2_hints) {
 
 }  // namespace
 
-int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, int variant) {
-    // variant (MEMC_B200_VARIANT field of the flags): 0 production, 1 = frame-by-frame launches even for B >= 3
-    if (a.W < SW || a.H < SH || a.W % 4) return 0;
+static bool fp_fast_layout_ok(const FpArgs& a) {
+    if (a.W < SW || a.H < SH || a.W % 4) return false;
     // dense frames only: per-frame memset and the 128-bit averaging pass want contiguous planes
     const int64_t plane = (int64_t)a.H * a.W;
-    if (a.out.h != a.W || a.out.c != plane || a.count.h != a.W) return 0;
-    if ((reinterpret_cast<uintptr_t>(a.outp) & 15u) || (reinterpret_cast<uintptr_t>(a.countp) & 15u)) return 0;
-    if (a.out.b % 4 || a.count.b % 4) return 0;
+    if (a.out.h != a.W || a.out.c != plane || a.count.h != a.W) return false;
+    if ((reinterpret_cast<uintptr_t>(a.outp) & 15u) || (reinterpret_cast<uintptr_t>(a.countp) & 15u)) return false;
+    if (a.out.b % 4 || a.count.b % 4) return false;
+    return true;
+}
+
+static int fp_splat_frame(cudaStream_t stream, const void* ctx, int b) {
+    const FpArgs& a = *static_cast<const FpArgs*>(ctx);
+    const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
+    fp_splat_kernel<<<grid, NT, sizeof(Smem), stream>>>(a, b);
+    return 0;
+}
+
+int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, int variant) {
+    // variant (MEMC_B200_VARIANT field of the flags): 0 production, 1 = frame-by-frame launches even for B >= 3
+    if (!fp_fast_layout_ok(a)) return 0;
     // the library produces every element: persistent pipeline (from 3 frames on; below that its phases
     // cannot overlap across frames and the per-frame launches are quicker: 43 vs 58 us at B = 1, 720p)
     if (overwrite && a.B >= 3 && variant != 1) {
         const int r = fp_forward_pipeline(stream, a, variant == 2 ? 0 : 1);  // variant 2: without the L2 eviction hints
         if (r != 0) return r;
     }
-    const size_t smem = sizeof(Smem);
-    if (!ensure_dynamic_smem(fp_splat_kernel, smem)) return 0;
-    const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
+    if (!ensure_dynamic_smem(fp_splat_kernel, sizeof(Smem))) return 0;
+    return fp_frames_fast(stream, a, overwrite, no_zero, false, fp_splat_frame, &a);
+}
+
+// frame by frame: [zero fills] -> splat(b) (the caller's kernel) -> average + occupancy masks, then ONE mask-based fill-hole
+// launch over the batch.  A frame's count + output planes (25 MB at 1080p) stay L2-resident between its passes.
+int fp_frames_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, bool signed_counts, FpSplatFn splat,
+                   const void* ctx) {
+    if (!fp_fast_layout_ok(a)) return 0;
+    const int64_t plane = (int64_t)a.H * a.W;
     // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
     const int Wt = (a.W + 31) / 32, Ht = (a.H + 31) / 32;
     const size_t n_row = (size_t)a.B * a.H * Wt, n_col = (size_t)a.B * a.W * Ht;
@@ -850,16 +893,25 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
             if (cudaMemsetAsync(cntb, 0, sizeof(float) * plane, stream) != cudaSuccess) rc = -1;
             count_launch(2);
         }
-        fp_splat_kernel<<<grid, NT, smem, stream>>>(a, b);
-        fp_average_mask_kernel<<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
-                                                           colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
+        if (splat(stream, ctx, b) != 0) rc = -1;
+        if (signed_counts)
+            fp_average_mask_kernel<true><<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
+                                                                     colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
+        else
+            fp_average_mask_kernel<false><<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
+                                                                      colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
         count_launch(2);
         if (check_launch("FlowProjection splat/average (fast)")) rc = -1;
     }
     // fill-hole once over the whole batch (it only needs the masks and the averaged output)
     if (rc == 1 && a.fillhole) {
         const dim3 fgrid(Wt, (a.H + 7) / 8, a.B);
-        fp_fillhole_mask_kernel<<<fgrid, 256, 0, stream>>>(a.outp, rowmask, colmask, a.W, a.H, Wt, Ht, a.out.b, a.out.c);
+        if (signed_counts)
+            fp_fillhole_mask_kernel<true><<<fgrid, 256, 0, stream>>>(a.outp, rowmask, colmask, a.W, a.H, Wt, Ht, a.out.b, a.out.c,
+                                                                     a.countp, a.count.b);
+        else
+            fp_fillhole_mask_kernel<false><<<fgrid, 256, 0, stream>>>(a.outp, rowmask, colmask, a.W, a.H, Wt, Ht, a.out.b, a.out.c,
+                                                                      nullptr, 0);
         count_launch();
         if (check_launch("FlowProjection fill-hole (masks)")) rc = -1;
     }

@@ -25,6 +25,22 @@ def smooth_flow(B, H, W, sigma, seed=0, device="cpu", jitter=0.25, grid=16):
     return flow.contiguous()
 
 
+def inverse_depth(B, H, W, seed=0, device="cpu", grid=64, spread=0.7, objects=True):
+    """A weight map for DepthFlowProjection shaped like what a depth network delivers: 1e-6 + 1 / depth with
+    depth = 4 * exp(spread * smooth N(0,1) field on a (H/grid, W/grid) lattice) -- slowly varying over a 64 x 16 source tile --
+    and, with `objects`, a few rectangles 3x nearer than their surroundings (depth edges: weight jumps inside a tile)."""
+    g = _gen(seed, device)
+    lh, lw = max(2, H // grid), max(2, W // grid)
+    low = torch.randn(B, 1, lh, lw, generator=g, device=device)
+    depth = 4.0 * torch.exp(spread * F.interpolate(low, size=(H, W), mode="bilinear", align_corners=True))
+    if objects and H >= 64 and W >= 64:
+        for k in range(6):
+            y0 = int(torch.randint(0, H - H // 4, (1,), generator=g, device=device))
+            x0 = int(torch.randint(0, W - W // 4, (1,), generator=g, device=device))
+            depth[:, :, y0:y0 + H // 6 + 8 * k, x0:x0 + W // 8 + 8 * k] *= 1.0 / 3.0
+    return (1e-6 + 1.0 / depth).contiguous()
+
+
 def uniform_flow(B, H, W, amplitude, seed=0, device="cpu"):
     g = _gen(seed, device)
     return ((torch.rand(B, 2, H, W, generator=g, device=device) * 2 - 1) * amplitude).contiguous()

@@ -271,7 +271,7 @@ ORACLE_API int oracle_flow_projection_forward(int B, int H, int W, const float *
          * contributes.  Holes only read non-hole pixels, so the result is order-free. */
         for (int h = 0; h < H; ++h)
             for (int w = 0; w < W; ++w) {
-                if (cnt[(size_t)h * W + w] > 0.0f) continue;
+                if (!(cnt[(size_t)h * W + w] <= 0.0f)) continue; /* `if(temp <= 0.0f)`: NaN is not a hole */
                 int lo = w, ro = w, uo = h;
                 float lt = 0.0f, rt = 0.0f, ut = 0.0f;
                 while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cnt[(size_t)h * W + lo]; }
@@ -371,7 +371,7 @@ ORACLE_API int oracle_depth_flow_projection_forward(int B, int H, int W, const f
         if (!fillhole) continue;
         for (int h = 0; h < H; ++h)
             for (int w = 0; w < W; ++w) {
-                if (cnt[(size_t)h * W + w] > 0.0f) continue;
+                if (!(cnt[(size_t)h * W + w] <= 0.0f)) continue; /* `if(temp <= 0.0f)`: NaN is not a hole */
                 int lo = w, ro = w, uo = h;
                 float lt = 0.0f, rt = 0.0f, ut = 0.0f;
                 while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cnt[(size_t)h * W + lo]; }

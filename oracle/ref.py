@@ -262,10 +262,10 @@ def gpu_depth_flow_projection_forward(flow, depth, fillhole, bufs=None):
     return out, count
 
 
-def gpu_depth_flow_projection_backward(flow, depth, count, fout, gout):
+def gpu_depth_flow_projection_backward(flow, depth, count, fout, gout, grads=None):
     import torch
     B, _, H, W = flow.shape
-    g1, g2 = torch.zeros_like(flow), torch.zeros_like(depth)
+    g1, g2 = grads if grads is not None else (torch.zeros_like(flow), torch.zeros_like(depth))
     rc = _gpu().DepthFlowProjection_gpu_backward_kernel(
         _stream(), _i(gout.numel()), _i(W), _i(H), _i(2), _i(B),
         *_s(flow), *_s(depth), *_s(count), _d(flow), _d(depth), _d(count), _d(fout), _d(gout), _d(g1), _d(g2))

@@ -145,6 +145,40 @@ def test_flow_projection_cfg3_vs_reference_kernels(L, kind):
         assert r["max_abs"] <= bound, "FP %s %s: unscaled max-abs %.3e > %.3e" % (kind, r["tensor"], r["max_abs"], bound)
 
 
+@pytest.mark.parametrize("kind", ["smooth", "convergent"])
+def test_depth_flow_projection_at_size_vs_reference_kernels(L, kind):
+    """DepthFlowProjection at B=4 x 1920x1080 with fill-hole, forward and backward, against the
+    reference kernels and their own run-to-run spread; the fp64 oracle arbitrates on the first frame."""
+    from my_package.functions.DepthFlowProjectionLayer import DepthFlowProjectionLayer
+    B, H, W = 4, 1080, 1920
+    t = _regime(kind, B, H, W)
+    from memc_b200 import synth
+    d = synth.inverse_depth(B, H, W, seed=7, device="cuda")
+    layer = DepthFlowProjectionLayer(requires_grad=False)
+    with torch.no_grad():
+        out = layer(t, d)
+    r_out, r_count = ref.gpu_depth_flow_projection_forward(t, d, 1)
+    r_out2, r_count2 = ref.gpu_depth_flow_projection_forward(t, d, 1)
+    rows = [_row("output", out, r_out, r_out2), _row("count", layer.count, r_count, r_count2)]
+    gout = torch.randn_like(t)
+    import my_package._ext.my_lib as my_lib
+    g1, g2 = torch.zeros_like(t), torch.zeros_like(d)
+    assert my_lib.DepthFlowProjectionLayer_gpu_backward(t, d, r_count, r_out, gout, g1, g2) == 0
+    ra = ref.gpu_depth_flow_projection_backward(t, d, r_count, r_out, gout)
+    rb = ref.gpu_depth_flow_projection_backward(t, d, r_count, r_out, gout)
+    rows += [_row("gradinput1", g1, ra[0], rb[0]), _row("gradinput2", g2, ra[1], rb[1])]
+    eo, ec = cpu.depth_flow_projection_forward(t[:1].cpu().numpy(), d[:1].cpu().numpy(), 1, "f64")
+    e_ours = float(np.abs(out[:1].cpu().numpy().astype(np.float64) - eo).max())
+    e_ref = float(np.abs(r_out[:1].cpu().numpy().astype(np.float64) - eo).max())
+    print("DFP %-11s frame 0 vs fp64 oracle: ours %.3e   reference kernels %.3e" % (kind, e_ours, e_ref))
+    rows.append({"tensor": "frame0 vs fp64 oracle", "max_abs": e_ours, "ref_spread": e_ref, "ref_max": float(np.abs(eo).max())})
+    _report("DFP B=4x1080p " + kind, rows)
+    assert e_ours <= e_ref + TOL, "ours is further from the exact result (%.3e) than the reference kernels (%.3e)" % (e_ours, e_ref)
+    for r in rows[:4]:
+        bound = max(TOL, 3.0 * r["ref_spread"], 2.0 * e_ref, 2e-6 * r["ref_max"])
+        assert r["max_abs"] <= bound, "DFP %s %s: unscaled max-abs %.3e > %.3e" % (kind, r["tensor"], r["max_abs"], bound)
+
+
 def test_context_warp_c64_at_size_vs_reference_kernels(L):
     """The 64-channel context warp of MEMC_Net_star (networks/MEMC_Net_star.py:280-285) at the
     padded 1080p size the demo uses (1984 x 1152), forward and backward."""

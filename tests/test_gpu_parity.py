@@ -647,7 +647,13 @@ def test_flow_projection_vs_reference_cuda_kernels(L, fillhole):
 
 
 # ------------------------------------------------------------------- DepthFlowProjection
-def _inverse_depth(shape, seed):
+def _inverse_depth(shape, seed, kind="iid"):
+    """iid: every pixel its own depth in [0.5, 20] (weights span 40:1 inside every tile: the splat's direct path);
+    smooth: memc_b200.synth.inverse_depth (slowly varying + object edges: the fixed-point box for most tiles)."""
+    if kind == "smooth":
+        from memc_b200 import synth
+        B, _, H, W = shape
+        return synth.inverse_depth(B, H, W, seed=seed).numpy()
     rng = np.random.default_rng(seed)
     return (1e-6 + 1.0 / rng.uniform(0.5, 20.0, shape)).astype(np.float32)
 
@@ -655,13 +661,14 @@ def _inverse_depth(shape, seed):
 @pytest.mark.parametrize("shape", FP_SHAPES + [(2, 270, 480, 6.0)])
 @pytest.mark.parametrize("fillhole", [0, 1])
 @pytest.mark.parametrize("no_fast", [False, True])
-def test_depth_flow_projection_vs_oracle(L, shape, fillhole, no_fast):
+@pytest.mark.parametrize("weights", ["iid", "smooth"])
+def test_depth_flow_projection_vs_oracle(L, shape, fillhole, no_fast, weights):
     """Function / Module surface (fast shared-memory splat when the frame is at least one box large) and the generic
     kernels (MEMC_B200_NO_FAST) against the fp64 oracle, forward (+ fill-hole) and backward for both inputs."""
     from my_package.modules.DepthFlowProjectionModule import DepthFlowProjectionModule
     B, H, W, sigma = shape
     flow = flow_case(B, H, W, sigma, seed=41)
-    depth = _inverse_depth((B, 1, H, W), 43)
+    depth = _inverse_depth((B, 1, H, W), 43, weights)
     eo, ec = cpu.depth_flow_projection_forward(flow, depth, fillhole, "f64")
     if no_fast:
         S, P = L.strides_of, L.ptr
@@ -730,7 +737,7 @@ def test_depth_flow_projection_regimes(L, kind):
         t = synth.uniform_flow(B, H, W, 32.0, seed=2, device="cuda")
     else:
         t = synth.smooth_flow(B, H, W, 5.0, seed=6, device="cuda")
-    depth = _inverse_depth((B, 1, H, W), 53)
+    depth = _inverse_depth((B, 1, H, W), 53, "smooth")
     if kind == "wide_weights":
         depth[:, :, ::7, ::5] *= np.float32(2.0 ** -30)
     if kind == "nonfinite_weight":
@@ -764,7 +771,7 @@ def test_depth_flow_projection_vs_reference_cuda_kernels(L, fillhole):
     import my_package._ext.my_lib as my_lib
     from memc_b200 import synth
     B, H, W = 2, 180, 320
-    d = dev(_inverse_depth((B, 1, H, W), 59))
+    d = dev(_inverse_depth((B, 1, H, W), 59, "smooth"))
     for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -1.5, device="cuda"),
               synth.tear_flow(B, H, W, 12.0, seed=3, device="cuda")):
         r_out, r_count = ref.gpu_depth_flow_projection_forward(t, d, fillhole)
