@@ -41,6 +41,16 @@ def main():
         gi = ref.cpu_flow_projection_backward(flow, count, gout)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), op="flow_projection", flow=flow, out=out,
                             count=count, gout=gout, gi=gi)
+    for name, (B, H, W, sigma, seed) in {"dfp_small": (2, 12, 16, 3.0, 112), "dfp_wild": (1, 10, 10, 15.0, 113)}.items():
+        flow = flow_case(B, H, W, sigma, seed)
+        rng = np.random.default_rng(seed)
+        depth = (1e-6 + 1.0 / rng.uniform(0.5, 20.0, (B, 1, H, W))).astype(np.float32)
+        out, count = ref.cpu_depth_flow_projection_forward(flow, depth)
+        gout = rng.standard_normal(flow.shape).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g1, g2 = ref.cpu_depth_flow_projection_backward(flow, depth, count, out, gout)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="depth_flow_projection", flow=flow, depth=depth, out=out,
+                            count=count, gout=gout, g1=g1, g2=g2)
     for name, (B, C, H, W, sigma, seed) in {"ip_rgb": (2, 3, 12, 16, 3.0, 120), "ip_c7": (1, 7, 9, 13, 2.0, 121)}.items():
         in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed)
         out = ref.cpu_interpolation_forward(in1, flow)

@@ -935,6 +935,18 @@ def test_cuda_path_matches_golden_fixtures(L):
             assert my_lib.FlowProjectionLayer_gpu_forward(t, count, out, fh) == 0
             assert np.array_equal(host(count), z["count"])
             close(out, z["out"], what=path)
+        elif op == "depth_flow_projection":
+            t, d = dev(z["flow"]), dev(z["depth"])
+            count, out = torch.zeros(t.shape[0], 1, *t.shape[2:], device="cuda"), torch.zeros_like(t)
+            assert my_lib.DepthFlowProjectionLayer_gpu_forward(t, d, count, out, 0) == 0
+            close(count, z["count"], what=path), close(out, z["out"], what=path)
+            g1, g2 = torch.zeros_like(t), torch.zeros_like(d)
+            assert my_lib.DepthFlowProjectionLayer_gpu_backward(t, d, dev(z["count"]), dev(z["out"]), dev(z["gout"]), g1, g2) == 0
+            ok = np.isfinite(z["g1"])   # a source whose cell has no accumulated weight divides by 0 in the reference too
+            assert np.array_equal(np.isfinite(host(g1)), ok)
+            close(np.where(ok, host(g1), 0), np.where(ok, z["g1"], 0), what=path)
+            ok2 = np.isfinite(z["g2"])
+            close(np.where(ok2, host(g2), 0), np.where(ok2, z["g2"], 0), what=path)
         elif op == "interpolation":
             t1, t2 = dev(z["in1"]), dev(z["flow"])
             out = torch.zeros_like(t1)
