@@ -141,6 +141,31 @@ MEMC_B200_API int DepthFlowProjection_gpu_backward_kernel(
     const float *input1, const float *input2, const float *count, const float *output, const float *gradoutput,
     float *gradinput1, float *gradinput2);
 
+/* replaces my_lib_kernel.h:222-236 (called from my_lib_cuda.c:1041): FlowProjection in which a source votes only if its
+ * brightness-constancy error mean_c|input2[h,w] - input3[(h,w) + 2 flow]| + 1e-8 is <= threshhold; the error is splatted
+ * and averaged into `weight` [B,1,H,W] as well.  input2 / input3 are [B,3,H,W].  SURVEY section 8(f) rank 4. */
+MEMC_B200_API int WeightedFlowProjection_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int fillhole, const float threshhold,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const int weight_b_stride, const int weight_c_stride, const int weight_h_stride, const int weight_w_stride,
+    const float *input1, const float *input2, const float *input3, float *count, float *weight, float *output);
+
+/* replaces my_lib_kernel.h:238-255 (called from my_lib_cuda.c:1122) */
+MEMC_B200_API int WeightedFlowProjection_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const float threshhold,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int count_b_stride, const int count_c_stride, const int count_h_stride, const int count_w_stride,
+    const int weight_b_stride, const int weight_c_stride, const int weight_h_stride, const int weight_w_stride,
+    const float *input1, const float *input2, const float *input3, const float *count, const float *weight,
+    const float *gradoutput, float *gradinput1);
+
 /* replaces my_lib_kernel.h:67-81 (called from my_lib_cuda.c:402 and, for the Ch variant,
  * :519) */
 MEMC_B200_API int InterpolationLayer_gpu_forward_kernel(
@@ -272,6 +297,19 @@ MEMC_B200_API int memc_b200_depth_flow_projection_backward(
     memc_strides s_gi1, memc_strides s_gi2,
     const float *flow, const float *depth, const float *count, const float *output, const float *gradoutput,
     float *gradinput1, float *gradinput2, int flags);
+
+MEMC_B200_API int memc_b200_weighted_flow_projection_forward(
+    memc_stream_t stream, int batch, int h, int w, int fillhole, float threshold,
+    memc_strides s_flow, memc_strides s_frame0, memc_strides s_frame1, memc_strides s_count, memc_strides s_weight,
+    memc_strides s_out,
+    const float *flow, const float *frame0, const float *frame1, float *count, float *weight, float *output, int flags);
+
+MEMC_B200_API int memc_b200_weighted_flow_projection_backward(
+    memc_stream_t stream, int batch, int h, int w, float threshold,
+    memc_strides s_flow, memc_strides s_frame0, memc_strides s_frame1, memc_strides s_count, memc_strides s_gout,
+    memc_strides s_gi,
+    const float *flow, const float *frame0, const float *frame1, const float *count, const float *gradoutput,
+    float *gradinput, int flags);
 
 MEMC_B200_API int memc_b200_interpolation_forward(
     memc_stream_t stream, int batch, int channel, int h, int w,

@@ -58,7 +58,7 @@ class Strides(ctypes.Structure):
     _fields_ = [("b", ctypes.c_int64), ("c", ctypes.c_int64), ("h", ctypes.c_int64)]
 
 
-_I, _P, _S = ctypes.c_int, ctypes.c_void_p, Strides
+_I, _P, _S, _F = ctypes.c_int, ctypes.c_void_p, Strides, ctypes.c_float
 
 # name -> argtypes, straight from include/memc_b200.h
 _EXTENDED = {
@@ -71,6 +71,8 @@ _EXTENDED = {
     "memc_b200_flow_projection_backward": [_P, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
     "memc_b200_depth_flow_projection_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
     "memc_b200_depth_flow_projection_backward": [_P, _I, _I, _I] + [_S] * 7 + [_P] * 7 + [_I],
+    "memc_b200_weighted_flow_projection_forward": [_P, _I, _I, _I, _I, _F] + [_S] * 6 + [_P] * 6 + [_I],
+    "memc_b200_weighted_flow_projection_backward": [_P, _I, _I, _I, _F] + [_S] * 6 + [_P] * 6 + [_I],
     "memc_b200_interpolation_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],
     "memc_b200_interpolation_backward": [_P, _I, _I, _I, _I, _S, _S, _S, _S, _S, _P, _P, _P, _P, _P, _I],
     "memc_b200_separable_conv_forward": [_P, _I, _I, _I, _I, _I, _S, _S, _S, _S, _P, _P, _P, _P, _I],
@@ -85,6 +87,8 @@ _NAMED = {
     "FlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 4,
     "DepthFlowProjection_gpu_forward_kernel": [_P] + [_I] * 6 + [_I] * 12 + [_P] * 4,
     "DepthFlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 12 + [_P] * 7,
+    "WeightedFlowProjection_gpu_forward_kernel": [_P] + [_I] * 6 + [_F] + [_I] * 20 + [_P] * 6,
+    "WeightedFlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_F] + [_I] * 20 + [_P] * 7,
     "InterpolationLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 3,
     "InterpolationLayer_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 5,
     "InterpolationChLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 8 + [_P] * 3,

@@ -22,6 +22,7 @@ __all__ = [
     "FilterInterpolationLayer_gpu_forward", "FilterInterpolationLayer_gpu_backward",
     "FlowProjectionLayer_gpu_forward", "FlowProjectionLayer_gpu_backward",
     "DepthFlowProjectionLayer_gpu_forward", "DepthFlowProjectionLayer_gpu_backward",
+    "WeightedFlowProjectionLayer_gpu_forward", "WeightedFlowProjectionLayer_gpu_backward",
     "InterpolationLayer_gpu_forward", "InterpolationLayer_gpu_backward",
     "InterpolationChLayer_gpu_forward", "InterpolationChLayer_gpu_backward",
     "SeparableConvLayer_gpu_forward", "SeparableConvLayer_gpu_backward",
@@ -150,6 +151,49 @@ def DepthFlowProjectionLayer_gpu_backward(input1, input2, count, output, gradout
                [gradoutput.numel(), w, h, channel, batch],
                [input1, input2, count],
                [input1, input2, count, output, gradoutput, gradinput1, gradinput2])
+
+
+# ------------------------------------------------------------- WeightedFlowProjection
+def _go_thr(name, head, threshold, tensors_for_strides, pointers):
+    import ctypes
+    for t in pointers:
+        _lib.check_tensor(t, name)
+    fn = getattr(_lib.load(), name)
+    return int(fn(_lib.stream_ptr(pointers[0]), *head, ctypes.c_float(threshold), *_ints(*tensors_for_strides),
+                  *[_lib.ptr(t) for t in pointers]))
+
+
+def WeightedFlowProjectionLayer_gpu_forward(input1, input2, input3, count, weight, output, fillhole, threshhold):
+    """my_lib_cuda.c:986-1060 (declared my_lib_cuda.h:119-128)."""
+    batch, channel, h, w = input1.size()
+    if channel != 2:
+        return _ERR
+    if input2.size(1) != 3 or input3.size(1) != 3:
+        return _ERR
+    if input1.stride(0) != output.stride(0) or input1.stride(1) != output.stride(1):
+        return _ERR
+    return _go_thr("WeightedFlowProjection_gpu_forward_kernel",
+                   [output.numel(), w, h, channel, batch, int(fillhole)], float(threshhold),
+                   [input1, input2, input3, count, weight], [input1, input2, input3, count, weight, output])
+
+
+def WeightedFlowProjectionLayer_gpu_backward(input1, input2, input3, count, weight, gradoutput, gradinput1, threshhold):
+    """my_lib_cuda.c:1062-1140 (declared my_lib_cuda.h:130-139)."""
+    batch, channel, h, w = input1.size()
+    if channel != 2:
+        return _ERR
+    if input2.size(1) != 3 or input3.size(1) != 3:
+        return _ERR
+    if count.size(0) != batch or count.size(1) != 1:
+        return _ERR
+    if count.size(2) != h or count.size(3) != w:
+        return _ERR
+    if input1.stride(0) != gradinput1.stride(0) or input1.stride(1) != gradinput1.stride(1):
+        return _ERR
+    return _go_thr("WeightedFlowProjection_gpu_backward_kernel",
+                   [gradoutput.numel(), w, h, channel, batch], float(threshhold),
+                   [input1, input2, input3, count, weight],
+                   [input1, input2, input3, count, weight, gradoutput, gradinput1])
 
 
 # ---------------------------------------------------------------------- Interpolation

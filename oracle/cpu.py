@@ -123,6 +123,29 @@ def depth_flow_projection_backward(flow, depth, count, fout, gout, precision="f3
     return gi1, gi2
 
 
+def weighted_flow_projection_forward(flow, im0, im1, fillhole, threshold, precision="f32"):
+    flow, im0, im1 = _f32(flow), _f32(im0), _f32(im1)
+    B, two, H, W = flow.shape
+    assert two == 2 and im0.shape == (B, 3, H, W) and im1.shape == (B, 3, H, W)
+    r = _real(precision)
+    count = np.zeros((B, 1, H, W), np.float32)
+    weight, out = np.zeros((B, 1, H, W), r), np.zeros((B, 2, H, W), r)
+    _check(_lib(precision).oracle_weighted_flow_projection_forward(
+        B, H, W, _p(flow), _p(im0), _p(im1), _p(count), _p(weight), _p(out), int(fillhole), ctypes.c_float(threshold)),
+        "weighted_flow_projection_forward")
+    return out, count, weight
+
+
+def weighted_flow_projection_backward(flow, im0, im1, count, gout, threshold, precision="f32"):
+    flow, im0, im1, count, gout = _f32(flow), _f32(im0), _f32(im1), _f32(count), _f32(gout)
+    B, _, H, W = flow.shape
+    gi = np.zeros(flow.shape, _real(precision))
+    _check(_lib(precision).oracle_weighted_flow_projection_backward(
+        B, H, W, _p(flow), _p(im0), _p(im1), _p(count), _p(gout), _p(gi), ctypes.c_float(threshold)),
+        "weighted_flow_projection_backward")
+    return gi
+
+
 def interpolation_forward(in1, flow, precision="f32"):
     in1, flow = _f32(in1), _f32(flow)
     B, C, H, W = in1.shape

@@ -431,6 +431,122 @@ ORACLE_API int oracle_depth_flow_projection_backward(int B, int H, int W, const 
 }
 
 /* ------------------------------------------------------------------------------------
+ * WeightedFlowProjection: FlowProjection in which a source votes only if its brightness-constancy error is
+ * <= threshold; the error is splatted and averaged into `weight` as well.
+ *   scatter + average : my_lib.c:1941-2010 (CUDA: my_lib_kernel.cu:2557-2612, 2646-2654)
+ *   fill-hole         : my_lib_kernel.cu:2705-2757 ONLY (CPU twin: "Not implemented"); output only, weight untouched
+ *   backward          : my_lib.c:2106-2160 (CUDA: my_lib_kernel.cu:2800-2838)
+ * The gate is an fp32 decision in BOTH builds, evaluated the way the reference's C code evaluates it: `fabs` is the
+ * double function there, so each channel's term is (double)|d1 - d2| / 3.0 added to the float sum in double and rounded
+ * back to float (my_lib.c:1960); the CUDA source has the same line but resolves fabs to the float overload -- the two
+ * can differ in the last bit of the error, which only matters for a source sitting exactly on the threshold.
+ * The error that is ACCUMULATED is that float value (both builds accumulate it in `real`).
+ * ---------------------------------------------------------------------------------- */
+static inline float wfp_error(int H, int W, const float *im0, const float *im1, size_t plane, int h, int w, float fx,
+                              float fy)
+{
+    const float tx = (float)w + 2.0f * fx, ty = (float)h + 2.0f * fy;
+    const float mx = tx < (float)W - 1.0f ? tx : (float)W - 1.0f, my = ty < (float)H - 1.0f ? ty : (float)H - 1.0f;
+    const int x3 = (int)(mx > 0.0f ? mx : 0.0f), y3 = (int)(my > 0.0f ? my : 0.0f);
+    float e = 0.0f;
+    for (int c = 0; c < 3; ++c) {
+        const float d1 = im0[c * plane + (size_t)h * W + w], d2 = im1[c * plane + (size_t)y3 * W + x3];
+        e = (float)((double)e + fabs((double)(d1 - d2)) / 3.0);
+    }
+    e += 1e-8f;
+    return e;
+}
+
+ORACLE_API int oracle_weighted_flow_projection_forward(int B, int H, int W, const float *flow, const float *im0,
+                                                       const float *im1, float *count, real *weight, real *out,
+                                                       int fillhole, float threshold)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *fxp = flow + ((size_t)b * 2 + 0) * plane;
+        const float *fyp = flow + ((size_t)b * 2 + 1) * plane;
+        real *ox = out + ((size_t)b * 2 + 0) * plane;
+        real *oy = out + ((size_t)b * 2 + 1) * plane;
+        real *wg = weight + (size_t)b * plane;
+        float *cnt = count + (size_t)b * plane;
+
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const float fx = fxp[(size_t)h * W + w], fy = fyp[(size_t)h * W + w];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const float e = wfp_error(H, W, im0 + (size_t)b * 3 * plane, im1 + (size_t)b * 3 * plane, plane, h, w, fx, fy);
+                if (!(e <= threshold)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                for (int k = 0; k < 4; ++k) ox[cell[k]] += -(real)fx;
+                for (int k = 0; k < 4; ++k) oy[cell[k]] += -(real)fy;
+                for (int k = 0; k < 4; ++k) cnt[cell[k]] += 1.0f;
+                for (int k = 0; k < 4; ++k) wg[cell[k]] += (real)e;
+            }
+
+        for (size_t p = 0; p < plane; ++p) {
+            const float c = cnt[p];
+            if (c > 0.0f) { ox[p] /= (real)c; oy[p] /= (real)c; wg[p] /= (real)c; }
+        }
+
+        if (!fillhole) continue;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                if (!(cnt[(size_t)h * W + w] <= 0.0f)) continue;
+                int lo = w, ro = w, uo = h;
+                float lt = 0.0f, rt = 0.0f, ut = 0.0f;
+                while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cnt[(size_t)h * W + lo]; }
+                while (rt == 0.0f && ro + 1 <= W - 1) { ++ro; rt = cnt[(size_t)h * W + ro]; }
+                while (ut == 0.0f && uo - 1 >= 0) { --uo; ut = cnt[(size_t)uo * W + w]; }
+                if (lt + rt + ut <= 0.0f) continue;
+                const real den = (real)((lt > 0.0f) + (rt > 0.0f) + (ut > 0.0f));
+                real sx = (real)0, sy = (real)0;
+                if (lt > 0.0f) { sx += ox[(size_t)h * W + lo]; sy += oy[(size_t)h * W + lo]; }
+                if (rt > 0.0f) { sx += ox[(size_t)h * W + ro]; sy += oy[(size_t)h * W + ro]; }
+                if (ut > 0.0f) { sx += ox[(size_t)uo * W + w]; sy += oy[(size_t)uo * W + w]; }
+                ox[(size_t)h * W + w] = sx / den;
+                oy[(size_t)h * W + w] = sy / den;
+            }
+    }
+    return 0;
+}
+
+ORACLE_API int oracle_weighted_flow_projection_backward(int B, int H, int W, const float *flow, const float *im0,
+                                                        const float *im1, const float *count, const float *gout,
+                                                        real *gi, float threshold)
+{
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const float *cnt = count + (size_t)b * plane;
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const size_t pix = (size_t)h * W + w;
+                const float fx = flow[((size_t)b * 2 + 0) * plane + pix];
+                const float fy = flow[((size_t)b * 2 + 1) * plane + pix];
+                const float x2 = (float)w + fx, y2 = (float)h + fy;
+                if (!fp_valid(x2, y2, H, W)) continue;
+                const float e = wfp_error(H, W, im0 + (size_t)b * 3 * plane, im1 + (size_t)b * 3 * plane, plane, h, w, fx, fy);
+                if (!(e <= threshold)) continue;
+                const int L = (int)x2, T = (int)y2;
+                const int R = mini(L + 1, W - 1), Bm = mini(T + 1, H - 1);
+                const size_t cell[4] = {(size_t)T * W + L, (size_t)T * W + R,
+                                        (size_t)Bm * W + L, (size_t)Bm * W + R};
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float *go = gout + ((size_t)b * 2 + ch) * plane;
+                    real *g = gi + ((size_t)b * 2 + ch) * plane + pix;
+                    for (int k = 0; k < 4; ++k) *g += -(real)go[cell[k]] / (real)cnt[cell[k]];
+                }
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Interpolation (plain bilinear backward warp), any channel count (the reference's
  * InterpolationCh variant is the same code with the channel==3 check removed,
  * my_lib_cuda.c:490,519).  my_lib.c:480-527 (fwd), 590-660 (bwd).

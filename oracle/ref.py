@@ -134,6 +134,29 @@ def cpu_depth_flow_projection_backward(flow, depth, count, fout, gout):
     return g1, g2
 
 
+def cpu_weighted_flow_projection_forward(flow, im0, im1, threshold):
+    """scatter + average only (no fill-hole in the reference's CPU path, my_lib.c:2012-2014)."""
+    flow, im0, im1 = _c(flow), _c(im0), _c(im1)
+    B, _, H, W = flow.shape
+    count, weight = np.zeros((B, 1, H, W), np.float32), np.zeros((B, 1, H, W), np.float32)
+    out = np.zeros_like(flow)
+    rc = _cpu().WeightedFlowProjectionLayer_cpu_forward(_TH(flow).ref, _TH(im0).ref, _TH(im1).ref, _TH(count).ref,
+                                                        _TH(weight).ref, _TH(out).ref, ctypes.c_int(0),
+                                                        ctypes.c_float(threshold))
+    assert rc == 0, rc
+    return out, count, weight
+
+
+def cpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, threshold):
+    flow, im0, im1, count, weight, gout = _c(flow), _c(im0), _c(im1), _c(count), _c(weight), _c(gout)
+    gi = np.zeros_like(flow)
+    rc = _cpu().WeightedFlowProjectionLayer_cpu_backward(_TH(flow).ref, _TH(im0).ref, _TH(im1).ref, _TH(count).ref,
+                                                         _TH(weight).ref, _TH(gout).ref, _TH(gi).ref,
+                                                         ctypes.c_float(threshold))
+    assert rc == 0, rc
+    return gi
+
+
 def cpu_interpolation_forward(in1, flow):
     in1, flow = _c(in1), _c(flow)
     out = np.zeros_like(in1)
@@ -271,6 +294,33 @@ def gpu_depth_flow_projection_backward(flow, depth, count, fout, gout, grads=Non
         *_s(flow), *_s(depth), *_s(count), _d(flow), _d(depth), _d(count), _d(fout), _d(gout), _d(g1), _d(g2))
     assert rc == 0, rc
     return g1, g2
+
+
+def gpu_weighted_flow_projection_forward(flow, im0, im1, fillhole, threshold, bufs=None):
+    import torch
+    B, _, H, W = flow.shape
+    if bufs is None:
+        bufs = (torch.zeros(B, 1, H, W, device=flow.device), torch.zeros(B, 1, H, W, device=flow.device), torch.zeros_like(flow))
+    count, weight, out = bufs
+    rc = _gpu().WeightedFlowProjection_gpu_forward_kernel(
+        _stream(), _i(out.numel()), _i(W), _i(H), _i(2), _i(B), _i(fillhole), ctypes.c_float(threshold),
+        *_s(flow), *_s(im0), *_s(im1), *_s(count), *_s(weight),
+        _d(flow), _d(im0), _d(im1), _d(count), _d(weight), _d(out))
+    assert rc == 0, rc
+    return out, count, weight
+
+
+def gpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, threshold, gi=None):
+    import torch
+    B, _, H, W = flow.shape
+    if gi is None:
+        gi = torch.zeros_like(flow)
+    rc = _gpu().WeightedFlowProjection_gpu_backward_kernel(
+        _stream(), _i(gout.numel()), _i(W), _i(H), _i(2), _i(B), ctypes.c_float(threshold),
+        *_s(flow), *_s(im0), *_s(im1), *_s(count), *_s(weight),
+        _d(flow), _d(im0), _d(im1), _d(count), _d(weight), _d(gout), _d(gi))
+    assert rc == 0, rc
+    return gi
 
 
 def gpu_interpolation_forward(in1, flow, out=None):

@@ -787,6 +787,118 @@ def test_depth_flow_projection_vs_reference_cuda_kernels(L, fillhole):
         close(g2, host(r2), what="DepthFlowProjection gi2 vs reference CUDA")
 
 
+# ---------------------------------------------------------------- WeightedFlowProjection
+def _frames_and_threshold(flow, seed, quantile=0.5):
+    """Two random frames and a gate threshold that no source sits on: the middle of the widest gap between neighbouring
+    brightness errors around the given quantile (the fp32 error of the CUDA source and of the C source can differ in the
+    last bit, my_lib.c:1960 vs my_lib_kernel.cu:2575; the tests must not depend on which side of the gate that lands)."""
+    B, _, H, W = flow.shape
+    rng = np.random.default_rng(seed)
+    im0, im1 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+    xs, ys = np.arange(W, dtype=np.float32)[None, None, :], np.arange(H, dtype=np.float32)[None, :, None]
+    with np.errstate(invalid="ignore"):   # NaN / Inf flows (tests/cases.py edge cases) never reach the gate: any cell will do
+        x3 = np.clip(np.nan_to_num(xs + np.float32(2) * flow[:, 0], nan=0.0), 0, W - 1).astype(np.int64)
+        y3 = np.clip(np.nan_to_num(ys + np.float32(2) * flow[:, 1], nan=0.0), 0, H - 1).astype(np.int64)
+    bi = np.arange(B)[:, None, None]
+    err = sum(np.abs(im0[:, c].astype(np.float64) - im1[bi, c, y3, x3]) for c in range(3)) / 3.0
+    e = np.sort(err[np.isfinite(err)].ravel())
+    if len(e) < 2:
+        return im0, im1, 1.0
+    lo, hi = int(len(e) * max(0.0, quantile - 0.1)), min(len(e), max(int(len(e) * min(1.0, quantile + 0.1)), 2))
+    lo = min(lo, hi - 2)
+    k = lo + int(np.argmax(np.diff(e[lo:hi])))
+    return im0, im1, float(0.5 * (e[k] + e[k + 1]))
+
+
+@pytest.mark.parametrize("shape", FP_SHAPES + [(2, 270, 480, 6.0)])
+@pytest.mark.parametrize("fillhole", [0, 1])
+@pytest.mark.parametrize("no_fast", [False, True])
+def test_weighted_flow_projection_vs_oracle(L, shape, fillhole, no_fast):
+    from my_package.modules.WeightedFlowProjectionModule import WeightedFlowProjectionModule
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=61)
+    im0, im1, thr = _frames_and_threshold(flow, 63)
+    eo, ec, ew = cpu.weighted_flow_projection_forward(flow, im0, im1, fillhole, thr, "f64")
+    t, a, b = dev(flow), dev(im0), dev(im1)
+    if no_fast:
+        S, P = L.strides_of, L.ptr
+        count, weight = torch.full((B, 1, H, W), 7.0, device="cuda"), torch.full((B, 1, H, W), 5.0, device="cuda")
+        out = torch.full_like(t, -3.0)  # OVERWRITE ignores what is there
+        L.call("memc_b200_weighted_flow_projection_forward", L.stream_ptr(t), B, H, W, fillhole, thr, S(t), S(a), S(b),
+               S(count), S(weight), S(out), P(t), P(a), P(b), P(count), P(weight), P(out), L.OVERWRITE | L.NO_FAST)
+        assert np.array_equal(host(count), ec), "count must be exact"
+        close(out, eo, what="WeightedFlowProjection out (generic)")
+        close(weight, ew, what="WeightedFlowProjection weight (generic)")
+        return
+    mod = WeightedFlowProjectionModule(requires_grad=not fillhole, threshold=thr)
+    t.requires_grad_(not fillhole)
+    out = mod(t, a, b)
+    assert np.array_equal(host(mod.f.count), ec), "count must be exact"
+    assert 0 < ec.sum() < 4 * B * H * W or H * W == 1
+    close(out, eo, what="WeightedFlowProjection out")
+    close(mod.f.weight, ew, what="WeightedFlowProjection weight")
+    if not fillhole:
+        gout = np.random.default_rng(3).standard_normal(flow.shape).astype(np.float32)
+        (gi,) = torch.autograd.grad(out, (t,), dev(gout))
+        close(gi, cpu.weighted_flow_projection_backward(flow, im0, im1, ec, gout, thr, "f64"), what="WeightedFlowProjection gi")
+
+
+def test_weighted_flow_projection_named_abi_reference_contract(L):
+    """my_lib_cuda.h:119-139: caller-zeroed count / weight / output, gradinput accumulated with += for voting pixels only;
+    thresholds that admit nobody and everybody."""
+    import my_package._ext.my_lib as my_lib
+    B, H, W = 2, 48, 128
+    flow = flow_case(B, H, W, 5.0, seed=67)
+    im0, im1, thr = _frames_and_threshold(flow, 69, 0.4)
+    t, a, b = dev(flow), dev(im0), dev(im1)
+    for fillhole in (0, 1):
+        count, weight, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.WeightedFlowProjectionLayer_gpu_forward(t, a, b, count, weight, out, fillhole, thr) == 0
+        eo, ec, ew = cpu.weighted_flow_projection_forward(flow, im0, im1, fillhole, thr, "f64")
+        assert np.array_equal(host(count), ec)
+        close(out, eo, what="named WeightedFlowProjection fwd fillhole=%d" % fillhole)
+        close(weight, ew, what="named WeightedFlowProjection weight")
+    gout = np.random.default_rng(4).standard_normal(flow.shape).astype(np.float32)
+    e = cpu.weighted_flow_projection_backward(flow, im0, im1, ec, gout, thr, "f64")
+    for prefill in (0.0, 1.0):
+        gi = torch.full_like(t, prefill)
+        assert my_lib.WeightedFlowProjectionLayer_gpu_backward(t, a, b, count, weight, dev(gout), gi, thr) == 0
+        close(gi, e + prefill, what="named WeightedFlowProjection bwd")   # non-voting pixels: e == 0 there
+    for thr2, want in ((0.0, 0.0), (10.0, None)):
+        count, weight, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.WeightedFlowProjectionLayer_gpu_forward(t, a, b, count, weight, out, 0, thr2) == 0
+        if want is not None:
+            assert float(count.abs().max()) == want and float(out.abs().max()) == want
+        else:   # everybody votes: FlowProjection's count and output
+            fo, fc = cpu.flow_projection_forward(flow, 0, "f64")
+            assert np.array_equal(host(count), fc)
+            close(out, fo, what="threshold above every error = FlowProjection")
+    assert my_lib.WeightedFlowProjectionLayer_gpu_forward(t, a[:, :2], b, count, weight, out, 0, thr) == -1
+
+
+@pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
+@pytest.mark.parametrize("fillhole", [0, 1])
+def test_weighted_flow_projection_vs_reference_cuda_kernels(L, fillhole):
+    import my_package._ext.my_lib as my_lib
+    from memc_b200 import synth
+    B, H, W = 2, 180, 320
+    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, -1.5, device="cuda"),
+              synth.radial_flow(B, H, W, 0.9, device="cuda")):
+        im0, im1, thr = _frames_and_threshold(host(t), 71)
+        a, b = dev(im0), dev(im1)
+        r_out, r_count, r_weight = ref.gpu_weighted_flow_projection_forward(t, a, b, fillhole, thr)
+        count, weight, out = torch.zeros(B, 1, H, W, device="cuda"), torch.zeros(B, 1, H, W, device="cuda"), torch.zeros_like(t)
+        assert my_lib.WeightedFlowProjectionLayer_gpu_forward(t, a, b, count, weight, out, fillhole, thr) == 0
+        assert torch.equal(count, r_count)
+        close(out, host(r_out), tol=5e-5, what="WeightedFlowProjection vs reference CUDA (fillhole=%d)" % fillhole)
+        close(weight, host(r_weight), what="WeightedFlowProjection weight vs reference CUDA")
+        gout = torch.randn_like(t)
+        gi = torch.zeros_like(t)
+        assert my_lib.WeightedFlowProjectionLayer_gpu_backward(t, a, b, count, weight, gout, gi, thr) == 0
+        close(gi, host(ref.gpu_weighted_flow_projection_backward(t, a, b, r_count, r_weight, gout, thr)),
+              what="WeightedFlowProjection bwd vs reference CUDA")
+
+
 @pytest.mark.parametrize("shape", [(7, 64, 96), (5, 70, 260), (3, 33, 3840), (1, 1100, 128), (4, 45, 2100)])
 @pytest.mark.parametrize("fillhole", [0, 1])
 def test_flow_projection_pipeline_many_frames(L, shape, fillhole):

@@ -75,6 +75,28 @@ def test_depth_flow_projection_bit_exact(shape, weights):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0)])
+@pytest.mark.parametrize("threshold", [0.0, 0.25, 0.4, 2.0])
+def test_weighted_flow_projection_bit_exact(shape, threshold):
+    """the brightness-gated splat against my_lib.c:1879-2250 (forward without fill-hole: the
+    reference's CPU twin has none).  Thresholds: nobody votes / about a third / most / everybody."""
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=19)
+    rng = np.random.default_rng(23)
+    im0, im1 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+    out, count, weight = cpu.weighted_flow_projection_forward(flow, im0, im1, 0, threshold)
+    rout, rcount, rweight = ref.cpu_weighted_flow_projection_forward(flow, im0, im1, threshold)
+    assert np.array_equal(count, rcount) and np.array_equal(out, rout) and np.array_equal(weight, rweight)
+    if threshold == 2.0:
+        assert count.sum() > 0
+    gout = rng.standard_normal(flow.shape).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        assert np.array_equal(cpu.weighted_flow_projection_backward(flow, im0, im1, count, gout, threshold),
+                              ref.cpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, threshold),
+                              equal_nan=True)
+
+
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0)])
 def test_interpolation_bit_exact(shape):
     B, C, H, W, sigma = shape
