@@ -310,6 +310,31 @@ def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
     del dw
     torch.cuda.empty_cache()
 
+    # --- WeightedFlowProjection: the splat gated by brightness constancy between two frames, B = 16;
+    # frame 2 = frame 0 moved along the flow plus noise, threshold = the median error of the smooth case
+    g7 = torch.Generator(device=dev).manual_seed(9)
+    f0 = torch.nn.functional.interpolate(torch.rand(FB, 3, H // 30, W // 30, device=dev, generator=g7), size=(H, W), mode="bilinear",
+                                         align_corners=True).contiguous()   # a smooth image: brightness constancy roughly holds
+    f2 = (f0 + 0.2 * torch.randn(FB, 3, H, W, device=dev, generator=g7)).contiguous()
+    for kind, make in (regimes[0], regimes[2]):
+        fl = make()
+        cnt, wgt, prj = torch.empty(FB, 1, H, W, device=dev), torch.empty(FB, 1, H, W, device=dev), torch.empty_like(fl)
+        thr = 0.16
+        t = _timed(torch, lambda: lib.call("memc_b200_weighted_flow_projection_forward", st, FB, H, W, 1, thr, S(fl), S(f0), S(f2),
+                                           S(cnt), S(wgt), S(prj), P(fl), P(f0), P(f2), P(cnt), P(wgt), P(prj), lib.OVERWRITE))
+        tl = None
+        if have_ref:
+            def l_wfp():
+                cnt.zero_(); wgt.zero_(); prj.zero_()
+                ref.gpu_weighted_flow_projection_forward(fl, f0, f2, 1, thr, (cnt, wgt, prj))
+            tl = _timed(torch, l_wfp, 3)
+        # read flow 8 + two frames 24, write out 8 + count 4 + weight 4
+        entry("WeightedFlowProjection splat + hole-fill 1920x1080, batch 16, %s flow (%.0f %% of the sources vote)"
+              % (kind, 25.0 * float(cnt.sum()) / (FB * H * W)), FB * H * W, 48, t, tl)
+        del fl, cnt, wgt, prj
+    del f0, f2
+    torch.cuda.empty_cache()
+
     # --- the 64-channel context warp of MEMC_Net_star, forward and backward
     c_in, c_flow, c_filt, c_go = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
     c_out = torch.empty_like(c_in)

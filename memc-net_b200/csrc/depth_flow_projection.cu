@@ -31,6 +31,7 @@ struct DfpArgs {
     const float* foutp;
     View gi2;              // bwd: gradinput2 [B,1,H,W]
     float* gi2p;
+    int variant;           // MEMC_B200_VARIANT: 1 = the generic scatter kernel inside the fast frame driver
 };
 
 __device__ __forceinline__ bool dfp_valid(float x2, float y2, int W, int H) {
@@ -40,10 +41,10 @@ __device__ __forceinline__ bool dfp_valid(float x2, float y2, int W, int H) {
 // ------------------------------------------------------------------------------ scatter (generic)
 // one source pixel per thread: 4 cells x (out.x, out.y, count); a clamped R / Bm hits the same cell twice, as in the
 // reference (my_lib_kernel.cu:2103-2117)
-__global__ void __launch_bounds__(BX* BY) dfp_scatter_kernel(const DfpArgs p) {
+__global__ void __launch_bounds__(BX* BY) dfp_scatter_kernel(const DfpArgs p, const int b0) {  // frame b0 + blockIdx.z
     const int w = blockIdx.x * BX + threadIdx.x;
     const int h = blockIdx.y * BY + threadIdx.y;
-    const int b = blockIdx.z;
+    const int b = b0 + blockIdx.z;
     const FpArgs& f = p.f;
     if (w >= f.W || h >= f.H) return;
     const float* fl = f.flowp + b * f.flow.b + (int64_t)h * f.flow.h + w;
@@ -321,12 +322,19 @@ __global__ void __launch_bounds__(BX* BY, 6) dfp_bwd_kernel(const DfpArgs p) {
 
 int dfp_splat_frame(cudaStream_t stream, const void* ctx, int b) {
     const DfpArgs& a = *static_cast<const DfpArgs*>(ctx);
+    if (a.variant == 1) {
+        dim3 block(BX, BY, 1), g((a.f.W + BX - 1) / BX, (a.f.H + BY - 1) / BY, 1);
+        dfp_scatter_kernel<<<g, block, 0, stream>>>(a, b);
+        return 0;
+    }
     const dim3 grid((a.f.W + TW - 1) / TW, (a.f.H + TH - 1) / TH, 1);
     dfp_splat_kernel<<<grid, NT, sizeof(DSmem), stream>>>(a, b);
     return 0;
 }
 
-int dfp_forward(cudaStream_t stream, const DfpArgs& a, int flags) {
+int dfp_forward(cudaStream_t stream, const DfpArgs& a_in, int flags) {
+    DfpArgs a = a_in;
+    a.variant = (flags >> 16) & 0xff;
     const FpArgs& f = a.f;
     if (f.B <= 0 || f.H <= 0 || f.W <= 0) return 0;
     if (f.B > 65535) return -1;
@@ -345,7 +353,7 @@ int dfp_forward(cudaStream_t stream, const DfpArgs& a, int flags) {
         if (zero_fill(stream, f.outp, f.out, f.B, 2, f.H, f.W) != 0) return -1;
     }
     dim3 block(BX, BY, 1), grid((f.W + BX - 1) / BX, (f.H + BY - 1) / BY, f.B);
-    dfp_scatter_kernel<<<grid, block, 0, stream>>>(a);
+    dfp_scatter_kernel<<<grid, block, 0, stream>>>(a, 0);
     count_launch();
     if (check_launch("DepthFlowProjection scatter")) return -1;
     return fp_average_fill(stream, f, 0, f.B, true);  // FlowProjection's average (+ fill-hole when f.fillhole)

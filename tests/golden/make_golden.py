@@ -51,6 +51,15 @@ def main():
             g1, g2 = ref.cpu_depth_flow_projection_backward(flow, depth, count, out, gout)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), op="depth_flow_projection", flow=flow, depth=depth, out=out,
                             count=count, gout=gout, g1=g1, g2=g2)
+    for name, (B, H, W, sigma, seed, thr) in {"wfp_small": (2, 12, 16, 3.0, 114, 0.3), "wfp_all": (1, 10, 10, 2.0, 115, 5.0)}.items():
+        flow = flow_case(B, H, W, sigma, seed)
+        rng = np.random.default_rng(seed)
+        im0, im1 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+        out, count, weight = ref.cpu_weighted_flow_projection_forward(flow, im0, im1, thr)
+        gout = rng.standard_normal(flow.shape).astype(np.float32)
+        gi = ref.cpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, thr)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="weighted_flow_projection", flow=flow, im0=im0, im1=im1,
+                            threshold=np.float32(thr), out=out, count=count, weight=weight, gout=gout, gi=gi)
     for name, (B, C, H, W, sigma, seed) in {"ip_rgb": (2, 3, 12, 16, 3.0, 120), "ip_c7": (1, 7, 9, 13, 2.0, 121)}.items():
         in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed)
         out = ref.cpu_interpolation_forward(in1, flow)

@@ -1059,6 +1059,17 @@ def test_cuda_path_matches_golden_fixtures(L):
             close(np.where(ok, host(g1), 0), np.where(ok, z["g1"], 0), what=path)
             ok2 = np.isfinite(z["g2"])
             close(np.where(ok2, host(g2), 0), np.where(ok2, z["g2"], 0), what=path)
+        elif op == "weighted_flow_projection":
+            t, a, b, thr = dev(z["flow"]), dev(z["im0"]), dev(z["im1"]), float(z["threshold"])
+            count, weight = torch.zeros(t.shape[0], 1, *t.shape[2:], device="cuda"), torch.zeros(t.shape[0], 1, *t.shape[2:], device="cuda")
+            out = torch.zeros_like(t)
+            assert my_lib.WeightedFlowProjectionLayer_gpu_forward(t, a, b, count, weight, out, 0, thr) == 0
+            # (a source exactly on the gate could land on either side: fixtures were checked to have none within 1e-6)
+            assert np.array_equal(host(count), z["count"])
+            close(out, z["out"], what=path), close(weight, z["weight"], what=path)
+            gi = torch.zeros_like(t)
+            assert my_lib.WeightedFlowProjectionLayer_gpu_backward(t, a, b, count, weight, dev(z["gout"]), gi, thr) == 0
+            close(gi, z["gi"], what=path)
         elif op == "interpolation":
             t1, t2 = dev(z["in1"]), dev(z["flow"])
             out = torch.zeros_like(t1)
