@@ -66,7 +66,8 @@ typedef void *memc_stream_t; /* a cudaStream_t */
  * measurements and for the tests' cross-checks (FilterInterpolation forward, C <= 4: 1 row segments, 2 patches with
  * a TMA-staged output; C > 4: 1 generic kernel, 2 the round-1 patch kernel; backward: 1 the round-1
  * one-pixel-per-lane kernel, 2-4 other tile shapes; FlowProjection forward: 1 frame-by-frame launches instead of the
- * persistent pipeline).  Nothing in the library reads environment variables. */
+ * persistent pipeline, 2 the pipeline without its L2 eviction policies; DepthFlowProjection forward: 1 the generic
+ * scatter inside the frame driver).  Nothing in the library reads environment variables. */
 #define MEMC_B200_VARIANT(n) (((n) & 0xff) << 16)
 
 /* ---- library info ------------------------------------------------------------------ */

@@ -15,6 +15,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:fp_p
     python tools/run_one.py fp_fwd 16 > $O/ncu_fp.log 2>&1
 C=64 timeout 300 ncu --set full --clock-control none -k regex:fi_fwd_cols_chunked -s 2 -c 1 -o $O/fi_fwd_c64 -f \
     python tools/run_one.py fi_fwd 1 > $O/ncu_c64.log 2>&1
+C=64 timeout 300 ncu --set full --clock-control none -k regex:fi_bwd_chunked -s 1 -c 1 -o $O/fi_bwd_c64 -f \
+    python tools/run_one.py fi_bwd 1 > $O/ncu_bwd_c64.log 2>&1
 timeout 200 python tools/sweep_fi.py --iters 20 --out $O/sweep_fi.json > $O/sweep_fi.log 2>&1
 timeout 200 python tools/sweep_c64.py > $O/sweep_c64.log 2>&1
 cat $O/bench_n1.json
