@@ -167,6 +167,72 @@ MEMC_B200_API int WeightedFlowProjection_gpu_backward_kernel(
     const float *input1, const float *input2, const float *input3, const float *count, const float *weight,
     const float *gradoutput, float *gradinput1);
 
+/* ---- the 4x4 "pixel splat" family (no Python class or caller in the reference) ----
+ * Every source pixel lands at (w, h) + flow / 2 and spreads over the 4x4 cells around it with the window weight
+ * (1 - ((beta - m)^2 + (alpha - n)^2) / (2 sigma_d^2))^2:  PixelValue adds flow_weight * weight * input1[c], PixelWeight
+ * flow_weight * weight, ReliableWeight the weight itself.  Prowindow must be 2 and tao_r is unused (as in the reference).
+ * replaces my_lib_kernel.h:297-308 (called from my_lib_cuda.c:1413) */
+MEMC_B200_API int PixelValueLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_weights_b_stride, const int flow_weights_c_stride, const int flow_weights_h_stride, const int flow_weights_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input3, const float *flow_weights, float *output,
+    float sigma_d, float tao_r, float Prowindow);
+
+/* replaces my_lib_kernel.h:309-322 (called from my_lib_cuda.c:1510) */
+MEMC_B200_API int PixelValueLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_weights_b_stride, const int flow_weights_c_stride, const int flow_weights_h_stride, const int flow_weights_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input3, const float *flow_weights,
+    const float *gradoutput, float *gradinput1, float *gradinput3, float *gradflow_weights,
+    float sigma_d, float tao_r, float Prowindow);
+
+/* replaces my_lib_kernel.h:323-334 (called from my_lib_cuda.c:1604) */
+MEMC_B200_API int PixelWeightLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int batch,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_weights_b_stride, const int flow_weights_c_stride, const int flow_weights_h_stride, const int flow_weights_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input3, const float *flow_weights, float *output,
+    float sigma_d, float tao_r, float Prowindow);
+
+/* replaces my_lib_kernel.h:335-349 (called from my_lib_cuda.c:1697): cells whose forward output is below threshhold give no gradient */
+MEMC_B200_API int PixelWeightLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int batch,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_weights_b_stride, const int flow_weights_c_stride, const int flow_weights_h_stride, const int flow_weights_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input3, const float *flow_weights, const float *output,
+    const float *gradoutput, float *gradinput3, float *gradflow_weights,
+    float threshhold, float sigma_d, float tao_r, float Prowindow);
+
+/* replaces my_lib_kernel.h:350-361 (called from my_lib_cuda.c:1809) */
+MEMC_B200_API int ReliableWeightLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int batch,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input3, float *output,
+    float sigma_d, float tao_r, float Prowindow);
+
+/* replaces my_lib_kernel.h:362-377 (called from my_lib_cuda.c:1904) */
+MEMC_B200_API int ReliableWeightLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int batch,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input3, const float *output, const float *gradoutput, float *gradinput3,
+    float threshhold, float sigma_d, float tao_r, float Prowindow);
+
 /* replaces my_lib_kernel.h:67-81 (called from my_lib_cuda.c:402 and, for the Ch variant,
  * :519) */
 MEMC_B200_API int InterpolationLayer_gpu_forward_kernel(
@@ -311,6 +377,38 @@ MEMC_B200_API int memc_b200_weighted_flow_projection_backward(
     memc_strides s_gi,
     const float *flow, const float *frame0, const float *frame1, const float *count, const float *gradoutput,
     float *gradinput, int flags);
+
+MEMC_B200_API int memc_b200_pixel_value_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, float sigma_d,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_fw, memc_strides s_out,
+    const float *input1, const float *flow, const float *flow_weights, float *output, int flags);
+
+MEMC_B200_API int memc_b200_pixel_value_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w, float sigma_d,
+    memc_strides s_in1, memc_strides s_flow, memc_strides s_fw, memc_strides s_gout, memc_strides s_gi1, memc_strides s_gi3,
+    memc_strides s_gfw,
+    const float *input1, const float *flow, const float *flow_weights, const float *gradoutput, float *gradinput1,
+    float *gradinput3, float *gradflow_weights, int flags);
+
+MEMC_B200_API int memc_b200_pixel_weight_forward(
+    memc_stream_t stream, int batch, int h, int w, float sigma_d,
+    memc_strides s_flow, memc_strides s_fw, memc_strides s_out,
+    const float *flow, const float *flow_weights, float *output, int flags);
+
+MEMC_B200_API int memc_b200_pixel_weight_backward(
+    memc_stream_t stream, int batch, int h, int w, float sigma_d, float threshold,
+    memc_strides s_flow, memc_strides s_fw, memc_strides s_out, memc_strides s_gout, memc_strides s_gi3, memc_strides s_gfw,
+    const float *flow, const float *flow_weights, const float *output, const float *gradoutput, float *gradinput3,
+    float *gradflow_weights, int flags);
+
+MEMC_B200_API int memc_b200_reliable_weight_forward(
+    memc_stream_t stream, int batch, int h, int w, float sigma_d,
+    memc_strides s_flow, memc_strides s_out, const float *flow, float *output, int flags);
+
+MEMC_B200_API int memc_b200_reliable_weight_backward(
+    memc_stream_t stream, int batch, int h, int w, float sigma_d, float threshold,
+    memc_strides s_flow, memc_strides s_out, memc_strides s_gout, memc_strides s_gi3,
+    const float *flow, const float *output, const float *gradoutput, float *gradinput3, int flags);
 
 MEMC_B200_API int memc_b200_interpolation_forward(
     memc_stream_t stream, int batch, int channel, int h, int w,

@@ -23,6 +23,9 @@ __all__ = [
     "FlowProjectionLayer_gpu_forward", "FlowProjectionLayer_gpu_backward",
     "DepthFlowProjectionLayer_gpu_forward", "DepthFlowProjectionLayer_gpu_backward",
     "WeightedFlowProjectionLayer_gpu_forward", "WeightedFlowProjectionLayer_gpu_backward",
+    "PixelValueLayer_gpu_forward", "PixelValueLayer_gpu_backward",
+    "PixelWeightLayer_gpu_forward", "PixelWeightLayer_gpu_backward",
+    "ReliableWeightLayer_gpu_forward", "ReliableWeightLayer_gpu_backward",
     "InterpolationLayer_gpu_forward", "InterpolationLayer_gpu_backward",
     "InterpolationChLayer_gpu_forward", "InterpolationChLayer_gpu_backward",
     "SeparableConvLayer_gpu_forward", "SeparableConvLayer_gpu_backward",
@@ -194,6 +197,112 @@ def WeightedFlowProjectionLayer_gpu_backward(input1, input2, input3, count, weig
                    [gradoutput.numel(), w, h, channel, batch], float(threshhold),
                    [input1, input2, input3, count, weight],
                    [input1, input2, input3, count, weight, gradoutput, gradinput1])
+
+
+# ------------------------------------- PixelValue / PixelWeight / ReliableWeight (4x4 splat family)
+def _go_tail(name, head, tensors_for_strides, pointers, floats):
+    import ctypes
+    for t in pointers:
+        _lib.check_tensor(t, name)
+    fn = getattr(_lib.load(), name)
+    return int(fn(_lib.stream_ptr(pointers[0]), *head, *_ints(*tensors_for_strides), *[_lib.ptr(t) for t in pointers],
+                  *[ctypes.c_float(v) for v in floats]))
+
+
+def PixelValueLayer_gpu_forward(input1, input3, flow_weights, output, sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1335-1433 (declared my_lib_cuda.h:163-166)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input1.size()
+    if channel != 3:
+        return _ERR
+    if input3.size(1) != 2 or flow_weights.size(1) != 1 or output.size(1) != 3:
+        return _ERR
+    if input1.stride(3) != 1 or input3.stride(3) != 1 or flow_weights.stride(3) != 1:
+        return _ERR
+    if input1.stride(0) != output.stride(0) or input1.stride(1) != output.stride(1):
+        return _ERR
+    return _go_tail("PixelValueLayer_gpu_forward_kernel", [output.numel(), w, h, channel, batch],
+                    [input1, input3, flow_weights, output], [input1, input3, flow_weights, output],
+                    [sigma_d, tao_r, Prowindow])
+
+
+def PixelValueLayer_gpu_backward(input1, input3, flow_weights, gradoutput, gradinput1, gradinput3, gradflow_weights,
+                                 sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1435-1538 (declared my_lib_cuda.h:167-172)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input1.size()
+    if channel != 3:
+        return _ERR
+    if input3.size(1) != 2 or flow_weights.size(1) != 1:
+        return _ERR
+    if input1.stride(3) != 1 or input3.stride(3) != 1:
+        return _ERR
+    if input1.stride(0) != gradinput1.stride(0) or input1.stride(1) != gradinput1.stride(1):
+        return _ERR
+    if input3.stride(1) != gradinput3.stride(1) or flow_weights.stride(0) != gradflow_weights.stride(0):
+        return _ERR
+    return _go_tail("PixelValueLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, channel, batch],
+                    [input1, input3, flow_weights, gradoutput],
+                    [input1, input3, flow_weights, gradoutput, gradinput1, gradinput3, gradflow_weights],
+                    [sigma_d, tao_r, Prowindow])
+
+
+def PixelWeightLayer_gpu_forward(input3, flow_weights, output, sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1540-1624 (declared my_lib_cuda.h:173-176)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input3.size()
+    if channel != 2 or flow_weights.size(1) != 1 or output.size(1) != 1:
+        return _ERR
+    if input3.stride(3) != 1 or flow_weights.stride(3) != 1:
+        return _ERR
+    return _go_tail("PixelWeightLayer_gpu_forward_kernel", [output.numel(), w, h, batch],
+                    [input3, flow_weights, output], [input3, flow_weights, output], [sigma_d, tao_r, Prowindow])
+
+
+def PixelWeightLayer_gpu_backward(input3, flow_weights, output, gradoutput, gradinput3, gradflow_weights,
+                                  threshhold, sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1626-1726 (declared my_lib_cuda.h:177-183)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input3.size()
+    if channel != 2 or flow_weights.size(1) != 1:
+        return _ERR
+    if input3.stride(3) != 1 or input3.stride(1) != gradinput3.stride(1):
+        return _ERR
+    return _go_tail("PixelWeightLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, batch],
+                    [input3, flow_weights, output],
+                    [input3, flow_weights, output, gradoutput, gradinput3, gradflow_weights],
+                    [threshhold, sigma_d, tao_r, Prowindow])
+
+
+def ReliableWeightLayer_gpu_forward(input3, output, sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1744-1829 (declared my_lib_cuda.h:194-197)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input3.size()
+    if channel != 2 or output.size(1) != 1:
+        return _ERR
+    if input3.stride(3) != 1:
+        return _ERR
+    return _go_tail("ReliableWeightLayer_gpu_forward_kernel", [output.numel(), w, h, batch],
+                    [input3, output], [input3, output], [sigma_d, tao_r, Prowindow])
+
+
+def ReliableWeightLayer_gpu_backward(input3, output, gradoutput, gradinput3, threshhold, sigma_d, tao_r, Prowindow):
+    """my_lib_cuda.c:1831-1932 (declared my_lib_cuda.h:198-203)."""
+    if Prowindow != 2.0:
+        return _ERR
+    batch, channel, h, w = input3.size()
+    if channel != 2:
+        return _ERR
+    if input3.stride(3) != 1 or input3.stride(1) != gradinput3.stride(1):
+        return _ERR
+    return _go_tail("ReliableWeightLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, batch],
+                    [input3, output], [input3, output, gradoutput, gradinput3],
+                    [threshhold, sigma_d, tao_r, Prowindow])
 
 
 # ---------------------------------------------------------------------- Interpolation

@@ -146,6 +146,39 @@ def weighted_flow_projection_backward(flow, im0, im1, count, gout, threshold, pr
     return gi
 
 
+_PX_MODES = {"value": 0, "weight": 1, "reliable": 2}
+
+
+def pixel_splat_forward(mode, flow, in1=None, fw=None, sigma_d=1.0, precision="f32"):
+    """PixelValue ("value": in1 [B,C,H,W] + fw [B,1,H,W]), PixelWeight ("weight": fw), ReliableWeight ("reliable")."""
+    flow = _f32(flow)
+    B, _, H, W = flow.shape
+    C = in1.shape[1] if mode == "value" else 1
+    in1 = _f32(in1) if in1 is not None else np.zeros(1, np.float32)
+    fw = _f32(fw) if fw is not None else np.zeros(1, np.float32)
+    out = np.zeros((B, C, H, W), _real(precision))
+    _check(_lib(precision).oracle_pixel_splat_forward(_PX_MODES[mode], B, C, H, W, _p(in1), _p(flow), _p(fw), _p(out),
+                                                      ctypes.c_float(sigma_d)), "pixel_splat_forward")
+    return out
+
+
+def pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sigma_d=1.0, threshold=0.0, precision="f32"):
+    """-> (gi1 | None, gi3, gfw | None) as the op has them."""
+    flow, gout = _f32(flow), _f32(gout)
+    B, _, H, W = flow.shape
+    r = _real(precision)
+    C = in1.shape[1] if mode == "value" else 1
+    in1_ = _f32(in1) if in1 is not None else np.zeros(1, np.float32)
+    fw_ = _f32(fw) if fw is not None else np.zeros(1, np.float32)
+    fout_ = _f32(fout) if fout is not None else np.zeros(1, np.float32)
+    gi1 = np.zeros((B, C, H, W), r)
+    gi3, gfw = np.zeros((B, 2, H, W), r), np.zeros((B, 1, H, W), r)
+    _check(_lib(precision).oracle_pixel_splat_backward(
+        _PX_MODES[mode], B, C, H, W, _p(in1_), _p(flow), _p(fw_), _p(fout_), _p(gout), _p(gi1), _p(gi3), _p(gfw),
+        ctypes.c_float(sigma_d), ctypes.c_float(threshold)), "pixel_splat_backward")
+    return (gi1 if mode == "value" else None), gi3, (gfw if mode != "reliable" else None)
+
+
 def interpolation_forward(in1, flow, precision="f32"):
     in1, flow = _f32(in1), _f32(flow)
     B, C, H, W = in1.shape

@@ -547,6 +547,108 @@ ORACLE_API int oracle_weighted_flow_projection_backward(int B, int H, int W, con
 }
 
 /* ------------------------------------------------------------------------------------
+ * PixelValue / PixelWeight / ReliableWeight: the 4x4 "pixel splat" family.
+ * A source (h, w) lands at (w, h) + flow / 2; the 16 cells (T + m, L + n), m, n = -1..2, clamped to the frame, receive
+ * the window weight g^2, g = 1 - ((beta - m)^2 + (alpha - n)^2) / (2 sigma_d^2), times flow_weight * input1[c] (mode 0,
+ * PixelValue: my_lib.c:2680-2735), flow_weight (mode 1, PixelWeight: :2950-3003) or 1 (mode 2, ReliableWeight:
+ * :3228-3284).  Backward (my_lib.c:2820-2884, 3085-3164, 3355-3397): sums over the same cells into the source pixel, in
+ * the reference's loop nesting (m, n, c) and order of operations; modes 1 / 2 skip cells whose forward output is below
+ * `threshold`.  Everything is added into the caller's buffers, like the reference.
+ * ---------------------------------------------------------------------------------- */
+static inline int px_geometry(int H, int W, const float *flow, size_t plane, int h, int w, int *L, int *T, float *alpha,
+                              float *beta)
+{
+    const float fx = flow[(size_t)h * W + w], fy = flow[plane + (size_t)h * W + w];
+    const float x2 = (float)w + fx / 2.0f, y2 = (float)h + fy / 2.0f;
+    if (!(x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1))) return 0;
+    *L = (int)x2; *T = (int)y2;
+    *alpha = x2 - (int)x2; *beta = y2 - (int)y2;
+    return 1;
+}
+
+/* window weight before squaring, in `real` (float build: the reference's expression, operation for operation) */
+static inline real px_window(float alpha, float beta, int m, int n, float sigma_d)
+{
+    const real bm = (real)beta - (real)m, an = (real)alpha - (real)n, sd = (real)sigma_d;
+    return (real)1 - (bm * bm + an * an) / ((real)2 * sd * sd);
+}
+
+ORACLE_API int oracle_pixel_splat_forward(int mode, int B, int C, int H, int W, const float *in1, const float *flow,
+                                          const float *fw, real *out, float sigma_d)
+{
+    if (B < 0 || H <= 0 || W <= 0 || mode < 0 || mode > 2) return -1;
+    if (mode != 0) C = 1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                int L, T; float alpha, beta;
+                if (!px_geometry(H, W, flow + (size_t)b * 2 * plane, plane, h, w, &L, &T, &alpha, &beta)) continue;
+                for (int m = -1; m <= 2; ++m)
+                    for (int n = -1; n <= 2; ++n) {
+                        const int pm = clampi(m + T, 0, H - 1), pn = clampi(n + L, 0, W - 1);
+                        real g = px_window(alpha, beta, m, n, sigma_d);
+                        g = g * g;
+                        if (mode == 2) { out[(size_t)b * plane + (size_t)pm * W + pn] += g; continue; }
+                        const real f_w = (real)fw[(size_t)b * plane + (size_t)h * W + w];
+                        if (mode == 1) { out[(size_t)b * plane + (size_t)pm * W + pn] += f_w * g; continue; }
+                        for (int c = 0; c < C; ++c)
+                            out[((size_t)b * C + c) * plane + (size_t)pm * W + pn] +=
+                                f_w * g * (real)in1[((size_t)b * C + c) * plane + (size_t)h * W + w];
+                    }
+            }
+    return 0;
+}
+
+/* fout: the forward's output (modes 1 / 2, threshold test); gi1 / gfw may be NULL where the mode has none */
+ORACLE_API int oracle_pixel_splat_backward(int mode, int B, int C, int H, int W, const float *in1, const float *flow,
+                                           const float *fw, const float *fout, const float *gout, real *gi1, real *gi3,
+                                           real *gfw, float sigma_d, float threshold)
+{
+    if (B < 0 || H <= 0 || W <= 0 || mode < 0 || mode > 2) return -1;
+    if (mode != 0) C = 1;
+    const size_t plane = (size_t)H * W;
+    const real s2 = (real)sigma_d * (real)sigma_d;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                int L, T; float alpha, beta;
+                if (!px_geometry(H, W, flow + (size_t)b * 2 * plane, plane, h, w, &L, &T, &alpha, &beta)) continue;
+                const size_t pix = (size_t)h * W + w;
+                real *gx = gi3 + (size_t)b * 2 * plane + pix, *gy = gx + plane;
+                const real f_w = mode == 2 ? (real)1 : (real)fw[(size_t)b * plane + pix];
+                for (int m = -1; m <= 2; ++m)
+                    for (int n = -1; n <= 2; ++n) {
+                        const int pm = clampi(m + T, 0, H - 1), pn = clampi(n + L, 0, W - 1);
+                        const real g = px_window(alpha, beta, m, n, sigma_d);
+                        const real dn = (real)n - (real)alpha, dm = (real)m - (real)beta;
+                        if (mode == 0) {
+                            for (int c = 0; c < C; ++c) {
+                                const real go = (real)gout[((size_t)b * C + c) * plane + (size_t)pm * W + pn];
+                                const real v = (real)in1[((size_t)b * C + c) * plane + pix];
+                                gi1[((size_t)b * C + c) * plane + pix] += go * f_w * g * g;
+                                gfw[(size_t)b * plane + pix] += go * g * g * v;
+                                *gx += -go * f_w * v * g * dn / s2 * (real)2;
+                                *gy += -go * f_w * v * g * dm / s2 * (real)2;
+                            }
+                            continue;
+                        }
+                        const real go = (real)gout[(size_t)b * plane + (size_t)pm * W + pn];
+                        if (fout[(size_t)b * plane + (size_t)pm * W + pn] < threshold) continue;
+                        if (mode == 1) {
+                            gfw[(size_t)b * plane + pix] += go * g * g;
+                            *gx += -go * f_w * g * dn / s2 * (real)2;
+                            *gy += -go * f_w * g * dm / s2 * (real)2;
+                        } else {   /* the reference's expression has no flow weight here: -go * g * (n - alpha) ... */
+                            *gx += -go * g * dn / s2 * (real)2;
+                            *gy += -go * g * dm / s2 * (real)2;
+                        }
+                    }
+            }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Interpolation (plain bilinear backward warp), any channel count (the reference's
  * InterpolationCh variant is the same code with the channel==3 check removed,
  * my_lib_cuda.c:490,519).  my_lib.c:480-527 (fwd), 590-660 (bwd).

@@ -157,6 +157,54 @@ def cpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, t
     return gi
 
 
+def _f(v):
+    return ctypes.c_float(v)
+
+
+def cpu_pixel_splat_forward(mode, flow, in1=None, fw=None, sigma_d=1.0):
+    """PixelValueLayer / PixelWeightLayer / ReliableWeightLayer _cpu_forward (my_lib.c:2615-3400); tao_r = 0, Prowindow = 2."""
+    flow = _c(flow)
+    B, _, H, W = flow.shape
+    if mode == "value":
+        in1, fw = _c(in1), _c(fw)
+        out = np.zeros_like(in1)
+        rc = _cpu().PixelValueLayer_cpu_forward(_TH(in1).ref, _TH(flow).ref, _TH(fw).ref, _TH(out).ref, _f(sigma_d), _f(0), _f(2))
+    elif mode == "weight":
+        fw = _c(fw)
+        out = np.zeros((B, 1, H, W), np.float32)
+        rc = _cpu().PixelWeightLayer_cpu_forward(_TH(flow).ref, _TH(fw).ref, _TH(out).ref, _f(sigma_d), _f(0), _f(2))
+    else:
+        out = np.zeros((B, 1, H, W), np.float32)
+        rc = _cpu().ReliableWeightLayer_cpu_forward(_TH(flow).ref, _TH(out).ref, _f(sigma_d), _f(0), _f(2))
+    assert rc == 0, rc
+    return out
+
+
+def cpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sigma_d=1.0, threshold=0.0):
+    flow, gout = _c(flow), _c(gout)
+    B, _, H, W = flow.shape
+    g3 = np.zeros_like(flow)
+    if mode == "value":
+        in1, fw = _c(in1), _c(fw)
+        g1, gw = np.zeros_like(in1), np.zeros_like(fw)
+        rc = _cpu().PixelValueLayer_cpu_backward(_TH(in1).ref, _TH(flow).ref, _TH(fw).ref, _TH(gout).ref, _TH(g1).ref,
+                                                 _TH(g3).ref, _TH(gw).ref, _f(sigma_d), _f(0), _f(2))
+        assert rc == 0, rc
+        return g1, g3, gw
+    fout = _c(fout)
+    if mode == "weight":
+        fw = _c(fw)
+        gw = np.zeros_like(fw)
+        rc = _cpu().PixelWeightLayer_cpu_backward(_TH(flow).ref, _TH(fw).ref, _TH(fout).ref, _TH(gout).ref, _TH(g3).ref,
+                                                  _TH(gw).ref, _f(threshold), _f(sigma_d), _f(0), _f(2))
+        assert rc == 0, rc
+        return None, g3, gw
+    rc = _cpu().ReliableWeightLayer_cpu_backward(_TH(flow).ref, _TH(fout).ref, _TH(gout).ref, _TH(g3).ref, _f(threshold),
+                                                 _f(sigma_d), _f(0), _f(2))
+    assert rc == 0, rc
+    return None, g3, None
+
+
 def cpu_interpolation_forward(in1, flow):
     in1, flow = _c(in1), _c(flow)
     out = np.zeros_like(in1)
@@ -321,6 +369,56 @@ def gpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, t
         _d(flow), _d(im0), _d(im1), _d(count), _d(weight), _d(gout), _d(gi))
     assert rc == 0, rc
     return gi
+
+
+def gpu_pixel_splat_forward(mode, flow, in1=None, fw=None, sigma_d=1.0, out=None):
+    """reference kernels of the 4x4 splat family (my_lib_kernel.h:297-398); tao_r = 0, Prowindow = 2."""
+    import torch
+    B, _, H, W = flow.shape
+    f3 = (_f(sigma_d), _f(0), _f(2))
+    if mode == "value":
+        C = in1.shape[1]
+        out = torch.zeros_like(in1) if out is None else out
+        rc = _gpu().PixelValueLayer_gpu_forward_kernel(
+            _stream(), _i(out.numel()), _i(W), _i(H), _i(C), _i(B), *_s(in1), *_s(flow), *_s(fw), *_s(out),
+            _d(in1), _d(flow), _d(fw), _d(out), *f3)
+    elif mode == "weight":
+        out = torch.zeros(B, 1, H, W, device=flow.device) if out is None else out
+        rc = _gpu().PixelWeightLayer_gpu_forward_kernel(
+            _stream(), _i(out.numel()), _i(W), _i(H), _i(B), *_s(flow), *_s(fw), *_s(out), _d(flow), _d(fw), _d(out), *f3)
+    else:
+        out = torch.zeros(B, 1, H, W, device=flow.device) if out is None else out
+        rc = _gpu().ReliableWeightLayer_gpu_forward_kernel(
+            _stream(), _i(out.numel()), _i(W), _i(H), _i(B), *_s(flow), *_s(out), _d(flow), _d(out), *f3)
+    assert rc == 0, rc
+    return out
+
+
+def gpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sigma_d=1.0, threshold=0.0):
+    import torch
+    B, _, H, W = flow.shape
+    f3 = (_f(sigma_d), _f(0), _f(2))
+    g3 = torch.zeros_like(flow)
+    if mode == "value":
+        C = in1.shape[1]
+        g1, gw = torch.zeros_like(in1), torch.zeros_like(fw)
+        rc = _gpu().PixelValueLayer_gpu_backward_kernel(
+            _stream(), _i(gout.numel()), _i(W), _i(H), _i(C), _i(B), *_s(in1), *_s(flow), *_s(fw), *_s(gout),
+            _d(in1), _d(flow), _d(fw), _d(gout), _d(g1), _d(g3), _d(gw), *f3)
+        assert rc == 0, rc
+        return g1, g3, gw
+    if mode == "weight":
+        gw = torch.zeros_like(fw)
+        rc = _gpu().PixelWeightLayer_gpu_backward_kernel(
+            _stream(), _i(gout.numel()), _i(W), _i(H), _i(B), *_s(flow), *_s(fw), *_s(fout),
+            _d(flow), _d(fw), _d(fout), _d(gout), _d(g3), _d(gw), _f(threshold), *f3)
+        assert rc == 0, rc
+        return None, g3, gw
+    rc = _gpu().ReliableWeightLayer_gpu_backward_kernel(
+        _stream(), _i(gout.numel()), _i(W), _i(H), _i(B), *_s(flow), *_s(fout),
+        _d(flow), _d(fout), _d(gout), _d(g3), _f(threshold), *f3)
+    assert rc == 0, rc
+    return None, g3, None
 
 
 def gpu_interpolation_forward(in1, flow, out=None):

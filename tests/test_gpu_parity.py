@@ -899,6 +899,120 @@ def test_weighted_flow_projection_vs_reference_cuda_kernels(L, fillhole):
               what="WeightedFlowProjection bwd vs reference CUDA")
 
 
+# ------------------------------------------- PixelValue / PixelWeight / ReliableWeight
+def _px_case(mode, shape, seed):
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    in1 = rng.random((B, 3, H, W), dtype=np.float32) if mode == "value" else None
+    fw = rng.random((B, 1, H, W), dtype=np.float32) if mode != "reliable" else None
+    return flow, in1, fw
+
+
+@pytest.mark.parametrize("shape", FP_SHAPES)
+@pytest.mark.parametrize("mode", ["value", "weight", "reliable"])
+def test_pixel_splat_family_vs_oracle(L, shape, mode):
+    """Extended entry points (OVERWRITE: garbage in the outputs) and the reference-named FFI entries (caller-zeroed
+    outputs, gradients accumulated with +=) against the fp64 oracle, forward and backward."""
+    import my_package._ext.my_lib as my_lib
+    S, P = L.strides_of, L.ptr
+    B, H, W, _ = shape
+    flow, in1, fw = _px_case(mode, shape, 73)
+    sd = 1.3
+    eo = cpu.pixel_splat_forward(mode, flow, in1, fw, sd, "f64")
+    t = dev(flow)
+    a = dev(in1) if in1 is not None else None
+    f = dev(fw) if fw is not None else None
+    C = 3 if mode == "value" else 1
+    out = torch.full((B, C, H, W), 7.0, device="cuda")
+    st = L.stream_ptr(t)
+    if mode == "value":
+        L.call("memc_b200_pixel_value_forward", st, B, C, H, W, sd, S(a), S(t), S(f), S(out), P(a), P(t), P(f), P(out), L.OVERWRITE)
+    elif mode == "weight":
+        L.call("memc_b200_pixel_weight_forward", st, B, H, W, sd, S(t), S(f), S(out), P(t), P(f), P(out), L.OVERWRITE)
+    else:
+        L.call("memc_b200_reliable_weight_forward", st, B, H, W, sd, S(t), S(out), P(t), P(out), L.OVERWRITE)
+    close(out, eo, what="%s forward" % mode)
+    # named entry, caller-zeroed
+    o2 = torch.zeros_like(out)
+    if mode == "value":
+        assert my_lib.PixelValueLayer_gpu_forward(a, t, f, o2, sd, 0.0, 2.0) == 0
+        assert my_lib.PixelValueLayer_gpu_forward(a, t, f, o2, sd, 0.0, 3.0) == -1   # Prowindow must be 2
+    elif mode == "weight":
+        assert my_lib.PixelWeightLayer_gpu_forward(t, f, o2, sd, 0.0, 2.0) == 0
+    else:
+        assert my_lib.ReliableWeightLayer_gpu_forward(t, o2, sd, 0.0, 2.0) == 0
+    close(o2, eo, what="%s forward (named)" % mode)
+    # backward: the forward output handed to ours and to the oracle is the same tensor (threshold test)
+    fout = host(out)
+    rng = np.random.default_rng(5)
+    gout = rng.standard_normal(fout.shape).astype(np.float32)
+    thr = float(np.quantile(fout, 0.35)) if mode != "value" else 0.0
+    e1, e3, ew = cpu.pixel_splat_backward(mode, flow, gout, in1, fw, fout, sd, thr, "f64")
+    go = dev(gout)
+    g3 = torch.full_like(t, 7.0)
+    gw = torch.full((B, 1, H, W), 7.0, device="cuda")
+    g1 = torch.full((B, C, H, W), 7.0, device="cuda")
+    if mode == "value":
+        L.call("memc_b200_pixel_value_backward", st, B, C, H, W, sd, S(a), S(t), S(f), S(go), S(g1), S(g3), S(gw),
+               P(a), P(t), P(f), P(go), P(g1), P(g3), P(gw), L.OVERWRITE)
+        close(g1, e1, what="value gi1"), close(gw, ew, what="value gfw")
+    elif mode == "weight":
+        L.call("memc_b200_pixel_weight_backward", st, B, H, W, sd, thr, S(t), S(f), S(out), S(go), S(g3), S(gw),
+               P(t), P(f), P(out), P(go), P(g3), P(gw), L.OVERWRITE)
+        close(gw, ew, what="weight gfw")
+    else:
+        L.call("memc_b200_reliable_weight_backward", st, B, H, W, sd, thr, S(t), S(out), S(go), S(g3),
+               P(t), P(out), P(go), P(g3), L.OVERWRITE)
+    close(g3, e3, what="%s gi3" % mode)
+    # named entries accumulate into what the caller passes
+    h3, hw, h1 = torch.ones_like(t), torch.ones(B, 1, H, W, device="cuda"), torch.ones(B, C, H, W, device="cuda")
+    if mode == "value":
+        assert my_lib.PixelValueLayer_gpu_backward(a, t, f, go, h1, h3, hw, sd, 0.0, 2.0) == 0
+        close(h1, e1 + 1.0, what="value gi1 (named, +=)"), close(hw, ew + 1.0, what="value gfw (named, +=)")
+    elif mode == "weight":
+        assert my_lib.PixelWeightLayer_gpu_backward(t, f, out, go, h3, hw, thr, sd, 0.0, 2.0) == 0
+        close(hw, ew + 1.0, what="weight gfw (named, +=)")
+    else:
+        assert my_lib.ReliableWeightLayer_gpu_backward(t, out, go, h3, thr, sd, 0.0, 2.0) == 0
+    close(h3, e3 + 1.0, what="%s gi3 (named, +=)" % mode)
+
+
+@pytest.mark.skipif(not ref.available_gpu(), reason="oracle/_ref/libmemc_ref_gpu.so not present")
+@pytest.mark.parametrize("mode", ["value", "weight", "reliable"])
+def test_pixel_splat_family_vs_reference_cuda_kernels(L, mode):
+    import my_package._ext.my_lib as my_lib
+    from memc_b200 import synth
+    B, H, W = 2, 180, 320
+    sd = 1.0
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.rand(B, 3, H, W, device="cuda", generator=g) if mode == "value" else None
+    f = torch.rand(B, 1, H, W, device="cuda", generator=g) if mode != "reliable" else None
+    for t in (synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda"), synth.radial_flow(B, H, W, 1.6, device="cuda")):
+        r_out = ref.gpu_pixel_splat_forward(mode, t, a, f, sd)
+        out = torch.zeros_like(r_out)
+        if mode == "value":
+            assert my_lib.PixelValueLayer_gpu_forward(a, t, f, out, sd, 0.0, 2.0) == 0
+        elif mode == "weight":
+            assert my_lib.PixelWeightLayer_gpu_forward(t, f, out, sd, 0.0, 2.0) == 0
+        else:
+            assert my_lib.ReliableWeightLayer_gpu_forward(t, out, sd, 0.0, 2.0) == 0
+        close(out, host(r_out), tol=3e-5, what="%s forward vs reference CUDA" % mode)
+        gout = torch.randn_like(r_out)
+        thr = float(torch.quantile(r_out.flatten()[:1000000], 0.35)) if mode != "value" else 0.0
+        r1, r3, rw = ref.gpu_pixel_splat_backward(mode, t, gout, a, f, r_out, sd, thr)
+        g3, gw, g1 = torch.zeros_like(t), torch.zeros(B, 1, H, W, device="cuda"), torch.zeros(B, 3, H, W, device="cuda")
+        if mode == "value":
+            assert my_lib.PixelValueLayer_gpu_backward(a, t, f, gout, g1, g3, gw, sd, 0.0, 2.0) == 0
+            close(g1, host(r1), what="value gi1 vs reference CUDA"), close(gw, host(rw), what="value gfw vs reference CUDA")
+        elif mode == "weight":
+            assert my_lib.PixelWeightLayer_gpu_backward(t, f, r_out, gout, g3, gw, thr, sd, 0.0, 2.0) == 0
+            close(gw, host(rw), what="weight gfw vs reference CUDA")
+        else:
+            assert my_lib.ReliableWeightLayer_gpu_backward(t, r_out, gout, g3, thr, sd, 0.0, 2.0) == 0
+        close(g3, host(r3), what="%s gi3 vs reference CUDA" % mode)
+
+
 @pytest.mark.parametrize("shape", [(7, 64, 96), (5, 70, 260), (3, 33, 3840), (1, 1100, 128), (4, 45, 2100)])
 @pytest.mark.parametrize("fillhole", [0, 1])
 def test_flow_projection_pipeline_many_frames(L, shape, fillhole):

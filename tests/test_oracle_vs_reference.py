@@ -97,6 +97,31 @@ def test_weighted_flow_projection_bit_exact(shape, threshold):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0)])
+@pytest.mark.parametrize("mode", ["value", "weight", "reliable"])
+def test_pixel_splat_family_bit_exact(shape, mode):
+    """PixelValue / PixelWeight / ReliableWeight against my_lib.c:2615-3400, forward and
+    backward (the threshold of the weight ops' backward set so that about a third of the cells are skipped)."""
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=29)
+    rng = np.random.default_rng(31)
+    in1 = rng.random((B, 3, H, W), dtype=np.float32) if mode == "value" else None
+    fw = rng.random((B, 1, H, W), dtype=np.float32) if mode != "reliable" else None
+    sigma_d = 1.3
+    out = cpu.pixel_splat_forward(mode, flow, in1, fw, sigma_d)
+    rout = ref.cpu_pixel_splat_forward(mode, flow, in1, fw, sigma_d)
+    assert np.array_equal(out, rout)
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    thr = float(np.quantile(out, 0.35)) if mode != "value" else 0.0
+    got = cpu.pixel_splat_backward(mode, flow, gout, in1, fw, out, sigma_d, thr)
+    exp = ref.cpu_pixel_splat_backward(mode, flow, gout, in1, fw, out, sigma_d, thr)
+    for a, b in zip(got, exp):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b)
+
+
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0)])
 def test_interpolation_bit_exact(shape):
     B, C, H, W, sigma = shape

@@ -7,7 +7,7 @@ d = json.load(open(sys.argv[1]))
 leg = {e["op"].replace(" (incl. zero fills)", ""): e for e in d.get("legacy_gpu", [])}
 out = ["# Kernel table (one B200, `python bench.py`, CUDA events, back-to-back launches on inputs larger than L2)", "",
        "Source: `%s` (`other_ops`, `legacy_gpu`, `roofline`, `roofline_fwd`).  `frac` = algorithmic bytes / time / %.1f GB/s" % (sys.argv[1], d["roofline"]["peak"]),
-       "(`MEASURED_PEAKS.json`).  legacy = the reference's `my_lib_kernel.cu` recompiled for sm_100a (`oracle/_ref/libmemc_ref_gpu.so`), same inputs and",
+       "(`MEASURED_PEAKS.json`).  legacy = the reference's `my_lib_kernel.cu` recompiled for sm_100a (the `legacy_gpu` leg of bench.py), same inputs and",
        "harness, including the zero fills its contract needs.", "",
        "| op | B/px | ours ms | ours frac | legacy ms | speed-up |", "|---|---|---|---|---|---|"]
 
