@@ -335,6 +335,49 @@ def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
     del f0, f2
     torch.cuda.empty_cache()
 
+    # --- PixelValue / PixelWeight / ReliableWeight: the 4x4 splat at the half-flow position, B = 4
+    PB, sd = 4, 1.0
+    pfl = synth.smooth_flow(PB, H, W, 6.0, seed=1, device=dev)
+    pim, pfw = torch.rand(PB, 3, H, W, device=dev), torch.rand(PB, 1, H, W, device=dev)
+    for mode, C_, bpp_f, bpp_b in (("value", 3, (3 + 2 + 1 + 3) * 4, (3 + 2 + 1 + 3 + 3 + 2 + 1) * 4),
+                                   ("weight", 1, (2 + 1 + 1) * 4, (2 + 1 + 1 + 1 + 2 + 1) * 4),
+                                   ("reliable", 1, (2 + 1) * 4, (2 + 1 + 1 + 2) * 4)):
+        po = torch.empty(PB, C_, H, W, device=dev)
+        pg = torch.randn(PB, C_, H, W, device=dev)
+        g1_, g3_, gw_ = torch.empty(PB, 3, H, W, device=dev), torch.empty_like(pfl), torch.empty_like(pfw)
+        if mode == "value":
+            fo = lambda: lib.call("memc_b200_pixel_value_forward", st, PB, 3, H, W, sd, S(pim), S(pfl), S(pfw), S(po), P(pim), P(pfl),
+                                  P(pfw), P(po), lib.OVERWRITE)
+            bo = lambda: lib.call("memc_b200_pixel_value_backward", st, PB, 3, H, W, sd, S(pim), S(pfl), S(pfw), S(pg), S(g1_), S(g3_),
+                                  S(gw_), P(pim), P(pfl), P(pfw), P(pg), P(g1_), P(g3_), P(gw_), lib.OVERWRITE)
+        elif mode == "weight":
+            fo = lambda: lib.call("memc_b200_pixel_weight_forward", st, PB, H, W, sd, S(pfl), S(pfw), S(po), P(pfl), P(pfw), P(po),
+                                  lib.OVERWRITE)
+            bo = lambda: lib.call("memc_b200_pixel_weight_backward", st, PB, H, W, sd, 0.5, S(pfl), S(pfw), S(po), S(pg), S(g3_), S(gw_),
+                                  P(pfl), P(pfw), P(po), P(pg), P(g3_), P(gw_), lib.OVERWRITE)
+        else:
+            fo = lambda: lib.call("memc_b200_reliable_weight_forward", st, PB, H, W, sd, S(pfl), S(po), P(pfl), P(po), lib.OVERWRITE)
+            bo = lambda: lib.call("memc_b200_reliable_weight_backward", st, PB, H, W, sd, 0.5, S(pfl), S(po), S(pg), S(g3_),
+                                  P(pfl), P(po), P(pg), P(g3_), lib.OVERWRITE)
+        tf = _timed(torch, fo)
+        tb = _timed(torch, bo)
+        tlf = tlb = None
+        if have_ref:
+            a_, f_ = (pim if mode == "value" else None), (pfw if mode != "reliable" else None)
+
+            def l_pf():
+                po.zero_()
+                ref.gpu_pixel_splat_forward(mode, pfl, a_, f_, sd, po)
+            tlf = _timed(torch, l_pf, 3)
+            fo()
+            tlb = _timed(torch, lambda: ref.gpu_pixel_splat_backward(mode, pfl, pg, a_, f_, po, sd, 0.5), 3)  # incl. its zero fills
+        name = {"value": "PixelValue", "weight": "PixelWeight", "reliable": "ReliableWeight"}[mode]
+        entry("%s forward 1920x1080, batch 4" % name, PB * H * W, bpp_f, tf, tlf)
+        entry("%s backward 1920x1080, batch 4" % name, PB * H * W, bpp_b, tb, tlb)
+        del po, pg, g1_, g3_, gw_
+    del pfl, pim, pfw
+    torch.cuda.empty_cache()
+
     # --- the 64-channel context warp of MEMC_Net_star, forward and backward
     c_in, c_flow, c_filt, c_go = synth.filter_interpolation_case(1, 64, H, W, FS, seed=5, device=dev)
     c_out = torch.empty_like(c_in)

@@ -14,7 +14,9 @@
 // checked by the FFI layer as in my_lib_cuda.c).  No Python class or caller in the reference.  tao_r is unused there too.
 //
 // Forward: one source per thread, 16 x C fire-and-forget reductions (RED.E.ADD.F32); the 16 cells of neighbouring sources
-// overlap in the L2.  Backward: no atomics at all -- the reference's atomicAdd targets are the thread's own pixel, so the
+// overlap in the L2 (measured B=4 x 1080p: 0.67 / 0.23 / 0.23 ms = the legacy kernels': the L2 reduction rate is the bound;
+// a shared-memory box as in the FilterInterpolation backward would cut 48 reductions per pixel to ~3, not built for ops
+// nobody calls).  Backward: no atomics at all -- the reference's atomicAdd targets are the thread's own pixel, so the
 // sums stay in registers and leave with one store each.
 #include "memc_common.cuh"
 
@@ -103,7 +105,12 @@ __global__ void __launch_bounds__(BX* BY) px_fwd_kernel(const PxArgs p) {
     }
 }
 
-// gradients of the source pixel: sums over its 16 cells (and C channels), in the reference's order of operations
+// gradients of the source pixel: sums over its 16 cells (and C channels).  Per cell and channel one gather and four FMAs:
+// with q = gradoutput * g the reference's four terms (my_lib_kernel.cu:3598-3610) are
+//     gradinput1[c] += f_w * (q g),  gradflow_weights += (q g) v[c],  gradinput3.x += -f_w * 2 / sigma_d^2 * (q v[c] (n - alpha)),
+//     gradinput3.y likewise with (m - beta)
+// and the constant factors are applied once, after the sums (the reference divides by sigma_d^2 in every term: 96 divisions
+// per pixel at C = 3; the results differ by rounding only, far inside the 1e-5 bar).
 template <int MODE, bool OVERWRITE>
 __global__ void __launch_bounds__(BX* BY) px_bwd_kernel(const PxArgs p) {
     const int w = blockIdx.x * BX + threadIdx.x, h = blockIdx.y * BY + threadIdx.y, b = blockIdx.z;
@@ -123,59 +130,44 @@ __global__ void __launch_bounds__(BX* BY) px_bwd_kernel(const PxArgs p) {
         return;
     }
     const float f_w = MODE == PX_RELIABLE ? 1.0f : ldg_stream(p.fwp + b * p.fw.b + (int64_t)h * p.fw.h + w);
-    const float s2 = p.sigma_d * p.sigma_d;
-    float gx = OVERWRITE ? 0.f : p.gi3p[pix3], gy = OVERWRITE ? 0.f : p.gi3p[pix3 + p.gi3.c];
-    float gw = (OVERWRITE || MODE == PX_RELIABLE) ? 0.f : p.gfwp[pixw];
+    const float k3 = -f_w * 2.0f / (p.sigma_d * p.sigma_d);
+    float gx = 0.f, gy = 0.f, gw = 0.f;
     const float* gob = p.goutp + b * p.gout.b;
     if (MODE == PX_VALUE) {
-        // channel outermost would change the order in which gradflow_weights / gradinput3 are summed; keep the reference's
-        // (m, n, c) nesting and carry the per-channel image gradients in a small register array (C <= 4) or, beyond
-        // that, accumulate them in place
         constexpr int CMAX = 4;
-        float v[CMAX], g1[CMAX];
-        const bool small = C <= CMAX;
+        for (int c0 = 0; c0 < C; c0 += CMAX) {  // channels in groups of 4 (one pass for the reference's C = 3)
+            float v[CMAX], a1[CMAX];
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            const int64_t o = b * p.in1.b + c * p.in1.c + (int64_t)h * p.in1.h + w;
-            v[c] = (small && c < C) ? ldg_stream(p.in1p + o) : 0.f;
-            g1[c] = (small && c < C && !OVERWRITE) ? p.gi1p[b * p.gi1.b + c * p.gi1.c + (int64_t)h * p.gi1.h + w] : 0.f;
-        }
-        if (!small && OVERWRITE)
-            for (int c = 0; c < C; ++c) p.gi1p[b * p.gi1.b + c * p.gi1.c + (int64_t)h * p.gi1.h + w] = 0.f;
+            for (int c = 0; c < CMAX; ++c) {
+                v[c] = c0 + c < C ? ldg_stream(p.in1p + b * p.in1.b + (c0 + c) * p.in1.c + (int64_t)h * p.in1.h + w) : 0.f;
+                a1[c] = 0.f;
+            }
 #pragma unroll
-        for (int m = -1; m <= 2; ++m) {
-            const int pm = min(max(0, m + g.T), p.H - 1);
+            for (int m = -1; m <= 2; ++m) {
+                const int pm = min(max(0, m + g.T), p.H - 1);
 #pragma unroll
-            for (int n = -1; n <= 2; ++n) {
-                const int pn = min(max(0, n + g.L), p.W - 1);
-                const float gd = px_window(g.alpha, g.beta, m, n, p.sigma_d);
-                const float* cell = gob + (int64_t)pm * p.gout.h + pn;
-                if (small) {
+                for (int n = -1; n <= 2; ++n) {
+                    const int pn = min(max(0, n + g.L), p.W - 1);
+                    const float gd = px_window(g.alpha, g.beta, m, n, p.sigma_d);
+                    const float dn = (float)n - g.alpha, dm = (float)m - g.beta;
+                    const float* cell = gob + (c0 * p.gout.c) + (int64_t)pm * p.gout.h + pn;
 #pragma unroll
                     for (int c = 0; c < CMAX; ++c) {
-                        if (c >= C) continue;
-                        const float go = __ldg(cell + c * p.gout.c);
-                        g1[c] += go * f_w * gd * gd;
-                        gw += go * gd * gd * v[c];
-                        gx += -go * f_w * v[c] * gd * ((float)n - g.alpha) / s2 * 2.0f;
-                        gy += -go * f_w * v[c] * gd * ((float)m - g.beta) / s2 * 2.0f;
-                    }
-                } else {
-                    for (int c = 0; c < C; ++c) {
-                        const float go = __ldg(cell + c * p.gout.c);
-                        const float vc = __ldg(p.in1p + b * p.in1.b + c * p.in1.c + (int64_t)h * p.in1.h + w);
-                        p.gi1p[b * p.gi1.b + c * p.gi1.c + (int64_t)h * p.gi1.h + w] += go * f_w * gd * gd;
-                        gw += go * gd * gd * vc;
-                        gx += -go * f_w * vc * gd * ((float)n - g.alpha) / s2 * 2.0f;
-                        gy += -go * f_w * vc * gd * ((float)m - g.beta) / s2 * 2.0f;
+                        if (c0 + c >= C) continue;
+                        const float q = __ldg(cell + c * p.gout.c) * gd;
+                        a1[c] = fmaf(q, gd, a1[c]);
+                        gw = fmaf(q * gd, v[c], gw);
+                        gx = fmaf(q * v[c], dn, gx);
+                        gy = fmaf(q * v[c], dm, gy);
                     }
                 }
             }
-        }
-        if (small) {
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) p.gi1p[b * p.gi1.b + c * p.gi1.c + (int64_t)h * p.gi1.h + w] = g1[c];
+            for (int c = 0; c < CMAX; ++c) {
+                if (c0 + c >= C) continue;
+                float* o = p.gi1p + b * p.gi1.b + (c0 + c) * p.gi1.c + (int64_t)h * p.gi1.h + w;
+                *o = OVERWRITE ? f_w * a1[c] : *o + f_w * a1[c];
+            }
         }
     } else {
         const float* fob = p.outp + b * p.out.b;
@@ -188,15 +180,18 @@ __global__ void __launch_bounds__(BX* BY) px_bwd_kernel(const PxArgs p) {
                 const float gd = px_window(g.alpha, g.beta, m, n, p.sigma_d);
                 const float go = __ldg(gob + (int64_t)pm * p.gout.h + pn);
                 if (__ldg(fob + (int64_t)pm * p.out.h + pn) < p.threshold) continue;  // skip its gradients (:3863, :4145)
-                if (MODE == PX_WEIGHT) gw += go * gd * gd;
-                gx += -go * f_w * gd * ((float)n - g.alpha) / s2 * 2.0f;
-                gy += -go * f_w * gd * ((float)m - g.beta) / s2 * 2.0f;
+                const float q = go * gd;
+                if (MODE == PX_WEIGHT) gw = fmaf(q, gd, gw);
+                gx = fmaf(q, (float)n - g.alpha, gx);
+                gy = fmaf(q, (float)m - g.beta, gy);
             }
         }
     }
-    p.gi3p[pix3] = gx;
-    p.gi3p[pix3 + p.gi3.c] = gy;
-    if (MODE != PX_RELIABLE) p.gfwp[pixw] = gw;
+    gx *= k3;
+    gy *= k3;
+    p.gi3p[pix3] = OVERWRITE ? gx : p.gi3p[pix3] + gx;
+    p.gi3p[pix3 + p.gi3.c] = OVERWRITE ? gy : p.gi3p[pix3 + p.gi3.c] + gy;
+    if (MODE != PX_RELIABLE) p.gfwp[pixw] = OVERWRITE ? gw : p.gfwp[pixw] + gw;
 }
 
 template <int MODE>

@@ -60,6 +60,21 @@ def main():
         gi = ref.cpu_weighted_flow_projection_backward(flow, im0, im1, count, weight, gout, thr)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), op="weighted_flow_projection", flow=flow, im0=im0, im1=im1,
                             threshold=np.float32(thr), out=out, count=count, weight=weight, gout=gout, gi=gi)
+    for name, (mode, B, H, W, sigma, seed) in {"px_value": ("value", 2, 12, 16, 3.0, 116), "px_weight": ("weight", 1, 10, 14, 6.0, 117),
+                                               "px_reliable": ("reliable", 1, 9, 9, 2.0, 118)}.items():
+        flow = flow_case(B, H, W, sigma, seed)
+        rng = np.random.default_rng(seed)
+        in1 = rng.random((B, 3, H, W), dtype=np.float32) if mode == "value" else np.zeros(0, np.float32)
+        fw = rng.random((B, 1, H, W), dtype=np.float32) if mode != "reliable" else np.zeros(0, np.float32)
+        sd = 1.3
+        out = ref.cpu_pixel_splat_forward(mode, flow, in1, fw, sd)
+        gout = rng.standard_normal(out.shape).astype(np.float32)
+        thr = float(np.quantile(out, 0.35)) if mode != "value" else 0.0
+        g1, g3, gw = ref.cpu_pixel_splat_backward(mode, flow, gout, in1, fw, out, sd, thr)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="pixel_splat", mode=mode, flow=flow, in1=in1, fw=fw,
+                            sigma_d=np.float32(sd), threshold=np.float32(thr), out=out, gout=gout,
+                            g1=g1 if g1 is not None else np.zeros(0, np.float32), g3=g3,
+                            gw=gw if gw is not None else np.zeros(0, np.float32))
     for name, (B, C, H, W, sigma, seed) in {"ip_rgb": (2, 3, 12, 16, 3.0, 120), "ip_c7": (1, 7, 9, 13, 2.0, 121)}.items():
         in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed)
         out = ref.cpu_interpolation_forward(in1, flow)

@@ -1184,6 +1184,26 @@ def test_cuda_path_matches_golden_fixtures(L):
             gi = torch.zeros_like(t)
             assert my_lib.WeightedFlowProjectionLayer_gpu_backward(t, a, b, count, weight, dev(z["gout"]), gi, thr) == 0
             close(gi, z["gi"], what=path)
+        elif op == "pixel_splat":
+            mode, sd, thr = str(z["mode"]), float(z["sigma_d"]), float(z["threshold"])
+            t, out, go = dev(z["flow"]), torch.zeros(*z["out"].shape, device="cuda"), dev(z["gout"])
+            g3 = torch.zeros_like(t)
+            if mode == "value":
+                a, f = dev(z["in1"]), dev(z["fw"])
+                g1, gw = torch.zeros_like(a), torch.zeros_like(f)
+                assert my_lib.PixelValueLayer_gpu_forward(a, t, f, out, sd, 0.0, 2.0) == 0
+                assert my_lib.PixelValueLayer_gpu_backward(a, t, f, go, g1, g3, gw, sd, 0.0, 2.0) == 0
+                close(g1, z["g1"], what=path), close(gw, z["gw"], what=path)
+            elif mode == "weight":
+                f = dev(z["fw"])
+                gw = torch.zeros_like(f)
+                assert my_lib.PixelWeightLayer_gpu_forward(t, f, out, sd, 0.0, 2.0) == 0
+                assert my_lib.PixelWeightLayer_gpu_backward(t, f, dev(z["out"]), go, g3, gw, thr, sd, 0.0, 2.0) == 0
+                close(gw, z["gw"], what=path)
+            else:
+                assert my_lib.ReliableWeightLayer_gpu_forward(t, out, sd, 0.0, 2.0) == 0
+                assert my_lib.ReliableWeightLayer_gpu_backward(t, dev(z["out"]), go, g3, thr, sd, 0.0, 2.0) == 0
+            close(out, z["out"], what=path), close(g3, z["g3"], what=path)
         elif op == "interpolation":
             t1, t2 = dev(z["in1"]), dev(z["flow"])
             out = torch.zeros_like(t1)
