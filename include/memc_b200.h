@@ -167,6 +167,30 @@ MEMC_B200_API int WeightedFlowProjection_gpu_backward_kernel(
     const float *input1, const float *input2, const float *input3, const float *count, const float *weight,
     const float *gradoutput, float *gradinput1);
 
+/* replaces my_lib_kernel.h:6-19 (called from my_lib_cuda.c:80): the flow a pair of separable filters encodes -- centroid of
+ * input2's taps minus (fs-1)/2 -> channel 1, of input3's -> channel 0, on the (h-fs+1) x (w-fs+1) valid region; -2000 where
+ * the taps sum to 0.  input1 only carries the frame size.  No Python class or caller in the reference. */
+MEMC_B200_API int SeparableConvFlowLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_output_b_stride, const int flow_output_c_stride, const int flow_output_h_stride, const int flow_output_w_stride,
+    const float *input1, const float *input2, const float *input3, float *flow_output);
+
+/* replaces my_lib_kernel.h:21-35: gradinput2 is ASSIGNED, gradinput3 accumulated (my_lib_kernel.cu:131, 155);
+ * gradinput1 is not touched */
+MEMC_B200_API int SeparableConvFlowLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch, const int filter_size,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int flow_output_b_stride, const int flow_output_c_stride, const int flow_output_h_stride, const int flow_output_w_stride,
+    const float *input1, const float *input2, const float *input3, const float *gradflow_output,
+    float *gradinput1, float *gradinput2, float *gradinput3);
+
 /* ---- the 4x4 "pixel splat" family (no Python class or caller in the reference) ----
  * Every source pixel lands at (w, h) + flow / 2 and spreads over the 4x4 cells around it with the window weight
  * (1 - ((beta - m)^2 + (alpha - n)^2) / (2 sigma_d^2))^2:  PixelValue adds flow_weight * weight * input1[c], PixelWeight
@@ -377,6 +401,17 @@ MEMC_B200_API int memc_b200_weighted_flow_projection_backward(
     memc_strides s_gi,
     const float *flow, const float *frame0, const float *frame1, const float *count, const float *gradoutput,
     float *gradinput, int flags);
+
+MEMC_B200_API int memc_b200_separable_conv_flow_forward(
+    memc_stream_t stream, int batch, int h, int w, int filter_size,
+    memc_strides s_vert, memc_strides s_horiz, memc_strides s_flow,
+    const float *vertical, const float *horizontal, float *flow_output, int flags);
+
+MEMC_B200_API int memc_b200_separable_conv_flow_backward(
+    memc_stream_t stream, int batch, int h, int w, int filter_size,
+    memc_strides s_vert, memc_strides s_horiz, memc_strides s_gflow, memc_strides s_gvert, memc_strides s_ghoriz,
+    const float *vertical, const float *horizontal, const float *gradflow_output, float *gradvertical, float *gradhorizontal,
+    int flags);
 
 MEMC_B200_API int memc_b200_pixel_value_forward(
     memc_stream_t stream, int batch, int channel, int h, int w, float sigma_d,

@@ -24,6 +24,7 @@ __all__ = [
     "DepthFlowProjectionLayer_gpu_forward", "DepthFlowProjectionLayer_gpu_backward",
     "WeightedFlowProjectionLayer_gpu_forward", "WeightedFlowProjectionLayer_gpu_backward",
     "PixelValueLayer_gpu_forward", "PixelValueLayer_gpu_backward",
+    "SeparableConvFlowLayer_gpu_forward", "SeparableConvFlowLayer_gpu_backward",
     "PixelWeightLayer_gpu_forward", "PixelWeightLayer_gpu_backward",
     "ReliableWeightLayer_gpu_forward", "ReliableWeightLayer_gpu_backward",
     "InterpolationLayer_gpu_forward", "InterpolationLayer_gpu_backward",
@@ -303,6 +304,47 @@ def ReliableWeightLayer_gpu_backward(input3, output, gradoutput, gradinput3, thr
     return _go_tail("ReliableWeightLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, batch],
                     [input3, output], [input3, output, gradoutput, gradinput3],
                     [threshhold, sigma_d, tao_r, Prowindow])
+
+
+# ------------------------------------------------------------------ SeparableConvFlow
+def _scf_checks(input1, input2, input3, flow_output):
+    # my_lib_cuda.c:24-34, 65-73
+    batch, channel, h, w = input1.size()
+    fs = input2.size(1)
+    if channel != 3 or input2.size(0) != batch:
+        return None
+    if input2.size(2) != h - fs + 1 or input2.size(3) != w - fs + 1:
+        return None
+    if input1.stride(3) != 1 or input2.stride(3) != 1 or input3.stride(3) != 1 or flow_output.stride(3) != 1:
+        return None
+    if input2.stride(0) != input3.stride(0) or input2.stride(1) != input3.stride(1):
+        return None
+    return batch, channel, h, w, fs
+
+
+def SeparableConvFlowLayer_gpu_forward(input1, input2, input3, flow_output):
+    """my_lib_cuda.c:12-102 (declared my_lib_cuda.h:2-8)."""
+    d = _scf_checks(input1, input2, input3, flow_output)
+    if d is None:
+        return _ERR
+    batch, channel, h, w, fs = d
+    return _go("SeparableConvFlowLayer_gpu_forward_kernel", [flow_output.numel(), w, h, channel, batch, fs],
+               [input1, input2, input3, flow_output], [input1, input2, input3, flow_output])
+
+
+def SeparableConvFlowLayer_gpu_backward(input1, input2, input3, gradflow_output, gradinput1, gradinput2, gradinput3):
+    """my_lib_cuda.c:104-198 (declared my_lib_cuda.h:10-17)."""
+    d = _scf_checks(input1, input2, input3, gradflow_output)
+    if d is None:
+        return _ERR
+    batch, channel, h, w, fs = d
+    if input2.stride(0) != gradinput2.stride(0) or input2.stride(1) != gradinput2.stride(1):
+        return _ERR
+    if input3.stride(0) != gradinput3.stride(0) or input3.stride(1) != gradinput3.stride(1):
+        return _ERR
+    return _go("SeparableConvFlowLayer_gpu_backward_kernel", [gradflow_output.numel(), w, h, channel, batch, fs],
+               [input1, input2, input3, gradflow_output],
+               [input1, input2, input3, gradflow_output, gradinput1, gradinput2, gradinput3])
 
 
 # ---------------------------------------------------------------------- Interpolation

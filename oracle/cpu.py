@@ -179,6 +179,25 @@ def pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sigma_d
     return (gi1 if mode == "value" else None), gi3, (gfw if mode != "reliable" else None)
 
 
+def separable_conv_flow_forward(vert, horiz, precision="f32"):
+    vert, horiz = _f32(vert), _f32(horiz)
+    B, fs, Ho, Wo = vert.shape
+    flow = np.zeros((B, 2, Ho, Wo), _real(precision))
+    _check(_lib(precision).oracle_separable_conv_flow_forward(B, fs, Ho, Wo, _p(vert), _p(horiz), _p(flow)),
+           "separable_conv_flow_forward")
+    return flow
+
+
+def separable_conv_flow_backward(vert, horiz, gflow, precision="f32"):
+    vert, horiz, gflow = _f32(vert), _f32(horiz), _f32(gflow)
+    B, fs, Ho, Wo = vert.shape
+    r = _real(precision)
+    gv, gh = np.zeros(vert.shape, r), np.zeros(horiz.shape, r)
+    _check(_lib(precision).oracle_separable_conv_flow_backward(B, fs, Ho, Wo, _p(vert), _p(horiz), _p(gflow), _p(gv), _p(gh)),
+           "separable_conv_flow_backward")
+    return gv, gh
+
+
 def interpolation_forward(in1, flow, precision="f32"):
     in1, flow = _f32(in1), _f32(flow)
     B, C, H, W = in1.shape

@@ -649,6 +649,55 @@ ORACLE_API int oracle_pixel_splat_backward(int mode, int B, int C, int H, int W,
 }
 
 /* ------------------------------------------------------------------------------------
+ * SeparableConvFlow: the flow a pair of separable filters encodes (centroid of the taps minus (fs-1)/2) on the valid
+ * region Ho x Wo = (H-fs+1) x (W-fs+1); -2000 where the taps sum to 0.  Follows the CUDA source my_lib_kernel.cu:52-80
+ * (forward), :108-160 (backward); the CPU twin my_lib.c:53-66 divides by |sum| instead of the signed sum, so the two
+ * reference implementations agree only for filters with a positive sum -- that is where this restatement is pinned
+ * against the CPU twin.  gv is ASSIGNED, gh accumulated, as in the CUDA source (:131, :155); the CPU twin assigns both.
+ * ---------------------------------------------------------------------------------- */
+ORACLE_API int oracle_separable_conv_flow_forward(int B, int fs, int Ho, int Wo, const float *vert, const float *horiz,
+                                                  real *flow)
+{
+    if (B < 0 || fs <= 0 || Ho <= 0 || Wo <= 0) return -1;
+    const size_t plane = (size_t)Ho * Wo;
+    const double half = ((double)(float)fs - 1.0) / 2.0;
+    for (int b = 0; b < B; ++b)
+        for (size_t p = 0; p < plane; ++p)
+            for (int which = 0; which < 2; ++which) {   /* 0: vertical -> channel 1, 1: horizontal -> channel 0 */
+                const float *f = (which ? horiz : vert) + (size_t)b * fs * plane + p;
+                real cen = (real)0, sum = (real)0;
+                for (int k = 0; k < fs; ++k) { cen += (real)k * (real)f[k * plane]; sum += (real)f[k * plane]; }
+                real *o = flow + ((size_t)b * 2 + (which ? 0 : 1)) * plane + p;
+                if (sizeof(real) == sizeof(float)) *o = fabs((double)sum) > 0.0 ? (real)(float)((double)(float)(cen / sum) - half) : (real)-2000;
+                else *o = fabs((double)sum) > 0.0 ? (real)((double)(cen / sum) - half) : (real)-2000;
+            }
+    return 0;
+}
+
+ORACLE_API int oracle_separable_conv_flow_backward(int B, int fs, int Ho, int Wo, const float *vert, const float *horiz,
+                                                   const float *gflow, real *gv, real *gh)
+{
+    if (B < 0 || fs <= 0 || Ho <= 0 || Wo <= 0) return -1;
+    const size_t plane = (size_t)Ho * Wo;
+    for (int b = 0; b < B; ++b)
+        for (size_t p = 0; p < plane; ++p)
+            for (int which = 0; which < 2; ++which) {
+                const float *f = (which ? horiz : vert) + (size_t)b * fs * plane + p;
+                real cen = (real)0, sum = (real)0;
+                for (int k = 0; k < fs; ++k) { cen += (real)k * (real)f[k * plane]; sum += (real)f[k * plane]; }
+                if (!(fabs((double)sum) > 0.0)) continue;
+                const real g = (real)gflow[((size_t)b * 2 + (which ? 0 : 1)) * plane + p];
+                const real off = cen / (sum * sum);
+                real *o = (which ? gh : gv) + (size_t)b * fs * plane + p;
+                for (int k = 0; k < fs; ++k) {
+                    const real v = g * ((real)k / sum - off);
+                    if (which) o[k * plane] += v; else o[k * plane] = v;
+                }
+            }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * Interpolation (plain bilinear backward warp), any channel count (the reference's
  * InterpolationCh variant is the same code with the channel==3 check removed,
  * my_lib_cuda.c:490,519).  my_lib.c:480-527 (fwd), 590-660 (bwd).

@@ -205,6 +205,23 @@ def cpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sig
     return None, g3, None
 
 
+def cpu_separable_conv_flow_forward(in1, vert, horiz):
+    in1, vert, horiz = _c(in1), _c(vert), _c(horiz)
+    flow = np.zeros((vert.shape[0], 2) + vert.shape[2:], np.float32)
+    rc = _cpu().SeparableConvFlowLayer_cpu_forward(_TH(in1).ref, _TH(vert).ref, _TH(horiz).ref, _TH(flow).ref)
+    assert rc == 0, rc
+    return flow
+
+
+def cpu_separable_conv_flow_backward(in1, vert, horiz, gflow):
+    in1, vert, horiz, gflow = _c(in1), _c(vert), _c(horiz), _c(gflow)
+    g1, gv, gh = np.zeros_like(in1), np.zeros_like(vert), np.zeros_like(horiz)
+    rc = _cpu().SeparableConvFlowLayer_cpu_backward(_TH(in1).ref, _TH(vert).ref, _TH(horiz).ref, _TH(gflow).ref,
+                                                    _TH(g1).ref, _TH(gv).ref, _TH(gh).ref)
+    assert rc == 0, rc
+    return gv, gh
+
+
 def cpu_interpolation_forward(in1, flow):
     in1, flow = _c(in1), _c(flow)
     out = np.zeros_like(in1)
@@ -419,6 +436,30 @@ def gpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sig
         _d(flow), _d(fout), _d(gout), _d(g3), _f(threshold), *f3)
     assert rc == 0, rc
     return None, g3, None
+
+
+def gpu_separable_conv_flow_forward(in1, vert, horiz):
+    import torch
+    B, C, H, W = in1.shape
+    fs = vert.shape[1]
+    flow = torch.zeros(B, 2, H - fs + 1, W - fs + 1, device=in1.device)
+    rc = _gpu().SeparableConvFlowLayer_gpu_forward_kernel(
+        _stream(), _i(flow.numel()), _i(W), _i(H), _i(C), _i(B), _i(fs), *_s(in1), *_s(vert), *_s(horiz), *_s(flow),
+        _d(in1), _d(vert), _d(horiz), _d(flow))
+    assert rc == 0, rc
+    return flow
+
+
+def gpu_separable_conv_flow_backward(in1, vert, horiz, gflow):
+    import torch
+    B, C, H, W = in1.shape
+    fs = vert.shape[1]
+    g1, gv, gh = torch.zeros_like(in1), torch.zeros_like(vert), torch.zeros_like(horiz)
+    rc = _gpu().SeparableConvFlowLayer_gpu_backward_kernel(
+        _stream(), _i(gflow.numel()), _i(W), _i(H), _i(C), _i(B), _i(fs), *_s(in1), *_s(vert), *_s(horiz), *_s(gflow),
+        _d(in1), _d(vert), _d(horiz), _d(gflow), _d(g1), _d(gv), _d(gh))
+    assert rc == 0, rc
+    return gv, gh
 
 
 def gpu_interpolation_forward(in1, flow, out=None):

@@ -899,6 +899,56 @@ def test_weighted_flow_projection_vs_reference_cuda_kernels(L, fillhole):
               what="WeightedFlowProjection bwd vs reference CUDA")
 
 
+# ------------------------------------------------------------------------------- SeparableConvFlow
+@pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3), (1, 3, 4, 4, 4), (2, 3, 64, 96, 4)])
+def test_separable_conv_flow_vs_oracle_and_reference_cuda(L, shape):
+    """Signed tap sums (the CUDA source's semantics, which the oracle follows), a zero-sum filter (-2000, no gradient),
+    the reference contract (gradinput2 assigned, gradinput3 accumulated) and OVERWRITE; vs the reference kernels too."""
+    import my_package._ext.my_lib as my_lib
+    S, P = L.strides_of, L.ptr
+    B, C, H, W, fs = shape
+    in1, v, hz, _ = sepconv_case(B, C, H, W, fs, seed=39)
+    v[0, :, 0, 0] = 0.0
+    Ho, Wo = H - fs + 1, W - fs + 1
+    t1, tv, th = dev(in1), dev(v), dev(hz)
+    e = cpu.separable_conv_flow_forward(v, hz, "f64")
+    flow = torch.full((B, 2, Ho, Wo), 7.0, device="cuda")
+    assert my_lib.SeparableConvFlowLayer_gpu_forward(t1, tv, th, flow) == 0
+    assert float(flow[0, 1, 0, 0]) == -2000.0
+    # a centroid divides by the tap sum, and signed taps cancel: compare where the sum is well conditioned (|sum| > 0.5
+    # against sum|tap| ~ 3: the fp32 rounding of the sum itself is amplified by sum|tap| / |sum| elsewhere)
+    ok = np.concatenate([(np.abs(hz.sum(1)) > 0.5)[:, None], (np.abs(v.sum(1)) > 0.5)[:, None]], 1)
+    got = host(flow)
+    assert np.abs(np.where(ok, got - e, 0)).max() <= 1e-5 * max(1.0, np.abs(np.where(ok, e, 0)).max())
+    f2 = torch.empty_like(flow)
+    L.call("memc_b200_separable_conv_flow_forward", L.stream_ptr(tv), B, H, W, fs, S(tv), S(th), S(f2), P(tv), P(th), P(f2), L.OVERWRITE)
+    assert torch.equal(f2, flow)
+    gflow = np.random.default_rng(9).standard_normal((B, 2, Ho, Wo)).astype(np.float32)
+    tg = dev(gflow)
+    ev, eh = cpu.separable_conv_flow_backward(v, hz, gflow, "f64")
+    okv, okh = np.broadcast_to(ok[:, 1:2], v.shape), np.broadcast_to(ok[:, 0:1], hz.shape)
+    gv, gh = torch.full_like(tv, 7.0), torch.full_like(th, 7.0)
+    L.call("memc_b200_separable_conv_flow_backward", L.stream_ptr(tv), B, H, W, fs, S(tv), S(th), S(tg), S(gv), S(gh),
+           P(tv), P(th), P(tg), P(gv), P(gh), L.OVERWRITE)
+    for got, exp, m in ((host(gv), ev, okv), (host(gh), eh, okh)):
+        assert np.abs(np.where(m, got - exp, 0)).max() <= 1e-5 * max(1.0, np.abs(np.where(m, exp, 0)).max())
+    assert float(gv[0, :, 0, 0].abs().max()) == 0.0   # zero-sum filter: no gradient (OVERWRITE writes the zeros)
+    # reference contract: gradinput2 assigned, gradinput3 accumulated
+    g1, hv, hh = torch.zeros_like(t1), torch.ones_like(tv), torch.ones_like(th)
+    assert my_lib.SeparableConvFlowLayer_gpu_backward(t1, tv, th, tg, g1, hv, hh) == 0
+    nz = dev(np.broadcast_to((v.sum(1) != 0)[:, None], v.shape).copy())
+    assert torch.equal(hv[nz], gv[nz])                                      # assigned: the prefill is gone
+    assert float((hh - 1.0 - gh).abs().max()) <= 1e-5 * max(1.0, float(gh.abs().max()))   # accumulated onto the prefill
+    assert float(hv[0, :, 0, 0].min()) == 1.0 and float(g1.abs().max()) == 0.0   # untouched
+    if ref.available_gpu():
+        r = ref.gpu_separable_conv_flow_forward(t1, tv, th)
+        assert np.abs(np.where(ok, host(flow) - host(r), 0)).max() <= 1e-5 * max(1.0, np.abs(np.where(ok, host(r), 0)).max())
+        rv, rh = ref.gpu_separable_conv_flow_backward(t1, tv, th, tg)
+        for a, b_, m in ((gv, rv, okv), (gh, rh, okh)):
+            d = np.where(m, host(a) - host(b_), 0)
+            assert np.abs(d).max() <= 1e-5 * max(1.0, np.abs(np.where(m, host(b_), 0)).max())
+
+
 # ------------------------------------------- PixelValue / PixelWeight / ReliableWeight (SURVEY 8(f) rank 4)
 def _px_case(mode, shape, seed):
     B, H, W, sigma = shape

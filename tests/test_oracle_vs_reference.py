@@ -122,6 +122,23 @@ def test_pixel_splat_family_bit_exact(shape, mode):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3), (1, 3, 4, 4, 4)])
+def test_separable_conv_flow_bit_exact(shape):
+    """SeparableConvFlow against my_lib.c:13-249 on filters with a positive tap sum (the reference's C source divides by
+    |sum|, its CUDA source -- which the oracle follows -- by the signed sum: they agree there), plus taps that sum to
+    exactly 0 (-2000 / no gradient in both)."""
+    B, C, H, W, fs = shape
+    in1, v, hz, _ = sepconv_case(B, C, H, W, fs, seed=37)
+    v, hz = np.abs(v) + np.float32(0.01), np.abs(hz) + np.float32(0.01)
+    v[0, :, 0, 0] = 0.0
+    hz[-1, :, -1, -1] = 0.0
+    assert np.array_equal(cpu.separable_conv_flow_forward(v, hz), ref.cpu_separable_conv_flow_forward(in1, v, hz))
+    gflow = np.random.default_rng(7).standard_normal((B, 2, H - fs + 1, W - fs + 1)).astype(np.float32)
+    for a, b in zip(cpu.separable_conv_flow_backward(v, hz, gflow), ref.cpu_separable_conv_flow_backward(in1, v, hz, gflow)):
+        assert np.array_equal(a, b)
+
+
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 3, 64, 64, 3.0), (2, 3, 37, 53, 8.0), (1, 7, 20, 31, 2.0)])
 def test_interpolation_bit_exact(shape):
     B, C, H, W, sigma = shape
