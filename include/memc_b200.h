@@ -167,6 +167,32 @@ MEMC_B200_API int WeightedFlowProjection_gpu_backward_kernel(
     const float *input1, const float *input2, const float *input3, const float *count, const float *weight,
     const float *gradoutput, float *gradinput1);
 
+/* replaces my_lib_kernel.h:257-270 (called from my_lib_cuda.c:1218): a per-pixel matching confidence, output [B,1,H,W] =
+ * (1 - err / lambda_e)^2 with err = the mean absolute difference over the 3x3 neighbourhood and the channels between input1
+ * around the pixel and input2 bilinearly sampled around pixel + flow (input3); 1e-4 where the target is outside the frame.
+ * Nw must be 3; lambda_v is unused (as in the reference).  No Python class or caller in the reference. */
+MEMC_B200_API int WeightLayer_gpu_forward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input2, const float *input3, float *output,
+    float lambda_e, float lambda_v, float Nw);
+
+/* replaces my_lib_kernel.h:271-286 (called from my_lib_cuda.c:1318); `output` is the forward's result */
+MEMC_B200_API int WeightLayer_gpu_backward_kernel(
+    memc_stream_t stream, const int nElement,
+    const int w, const int h, const int channel, const int batch,
+    const int input1_b_stride, const int input1_c_stride, const int input1_h_stride, const int input1_w_stride,
+    const int input2_b_stride, const int input2_c_stride, const int input2_h_stride, const int input2_w_stride,
+    const int input3_b_stride, const int input3_c_stride, const int input3_h_stride, const int input3_w_stride,
+    const int output_b_stride, const int output_c_stride, const int output_h_stride, const int output_w_stride,
+    const float *input1, const float *input2, const float *input3, const float *output, const float *gradoutput,
+    float *gradinput1, float *gradinput2, float *gradinput3,
+    float lambda_e, float lambda_v, float Nw);
+
 /* replaces my_lib_kernel.h:6-19 (called from my_lib_cuda.c:80): the flow a pair of separable filters encodes -- centroid of
  * input2's taps minus (fs-1)/2 -> channel 1, of input3's -> channel 0, on the (h-fs+1) x (w-fs+1) valid region; -2000 where
  * the taps sum to 0.  input1 only carries the frame size.  No Python class or caller in the reference. */
@@ -401,6 +427,18 @@ MEMC_B200_API int memc_b200_weighted_flow_projection_backward(
     memc_strides s_gi,
     const float *flow, const float *frame0, const float *frame1, const float *count, const float *gradoutput,
     float *gradinput, int flags);
+
+MEMC_B200_API int memc_b200_weight_layer_forward(
+    memc_stream_t stream, int batch, int channel, int h, int w, float lambda_e, float Nw,
+    memc_strides s_in1, memc_strides s_in2, memc_strides s_flow, memc_strides s_out,
+    const float *input1, const float *input2, const float *flow, float *output, int flags);
+
+/* gradients share their inputs' strides, gradoutput the output's */
+MEMC_B200_API int memc_b200_weight_layer_backward(
+    memc_stream_t stream, int batch, int channel, int h, int w, float lambda_e, float Nw,
+    memc_strides s_in1, memc_strides s_in2, memc_strides s_flow, memc_strides s_out,
+    const float *input1, const float *input2, const float *flow, const float *output, const float *gradoutput,
+    float *gradinput1, float *gradinput2, float *gradinput3, int flags);
 
 MEMC_B200_API int memc_b200_separable_conv_flow_forward(
     memc_stream_t stream, int batch, int h, int w, int filter_size,

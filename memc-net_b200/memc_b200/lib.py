@@ -73,6 +73,8 @@ _EXTENDED = {
     "memc_b200_depth_flow_projection_backward": [_P, _I, _I, _I] + [_S] * 7 + [_P] * 7 + [_I],
     "memc_b200_weighted_flow_projection_forward": [_P, _I, _I, _I, _I, _F] + [_S] * 6 + [_P] * 6 + [_I],
     "memc_b200_weighted_flow_projection_backward": [_P, _I, _I, _I, _F] + [_S] * 6 + [_P] * 6 + [_I],
+    "memc_b200_weight_layer_forward": [_P, _I, _I, _I, _I, _F, _F] + [_S] * 4 + [_P] * 4 + [_I],
+    "memc_b200_weight_layer_backward": [_P, _I, _I, _I, _I, _F, _F] + [_S] * 4 + [_P] * 8 + [_I],
     "memc_b200_separable_conv_flow_forward": [_P, _I, _I, _I, _I, _S, _S, _S, _P, _P, _P, _I],
     "memc_b200_separable_conv_flow_backward": [_P, _I, _I, _I, _I] + [_S] * 5 + [_P] * 5 + [_I],
     "memc_b200_pixel_value_forward": [_P, _I, _I, _I, _I, _F] + [_S] * 4 + [_P] * 4 + [_I],
@@ -97,6 +99,8 @@ _NAMED = {
     "DepthFlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 12 + [_P] * 7,
     "WeightedFlowProjection_gpu_forward_kernel": [_P] + [_I] * 6 + [_F] + [_I] * 20 + [_P] * 6,
     "WeightedFlowProjection_gpu_backward_kernel": [_P] + [_I] * 5 + [_F] + [_I] * 20 + [_P] * 7,
+    "WeightLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 16 + [_P] * 4 + [_F] * 3,
+    "WeightLayer_gpu_backward_kernel": [_P] + [_I] * 5 + [_I] * 16 + [_P] * 8 + [_F] * 3,
     "SeparableConvFlowLayer_gpu_forward_kernel": [_P] + [_I] * 6 + [_I] * 16 + [_P] * 4,
     "SeparableConvFlowLayer_gpu_backward_kernel": [_P] + [_I] * 6 + [_I] * 16 + [_P] * 7,
     "PixelValueLayer_gpu_forward_kernel": [_P] + [_I] * 5 + [_I] * 16 + [_P] * 4 + [_F] * 3,

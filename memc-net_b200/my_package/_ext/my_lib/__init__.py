@@ -25,6 +25,7 @@ __all__ = [
     "WeightedFlowProjectionLayer_gpu_forward", "WeightedFlowProjectionLayer_gpu_backward",
     "PixelValueLayer_gpu_forward", "PixelValueLayer_gpu_backward",
     "SeparableConvFlowLayer_gpu_forward", "SeparableConvFlowLayer_gpu_backward",
+    "WeightLayer_gpu_forward", "WeightLayer_gpu_backward",
     "PixelWeightLayer_gpu_forward", "PixelWeightLayer_gpu_backward",
     "ReliableWeightLayer_gpu_forward", "ReliableWeightLayer_gpu_backward",
     "InterpolationLayer_gpu_forward", "InterpolationLayer_gpu_backward",
@@ -304,6 +305,52 @@ def ReliableWeightLayer_gpu_backward(input3, output, gradoutput, gradinput3, thr
     return _go_tail("ReliableWeightLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, batch],
                     [input3, output], [input3, output, gradoutput, gradinput3],
                     [threshhold, sigma_d, tao_r, Prowindow])
+
+
+# ------------------------------------------------------------------------ WeightLayer
+def _wl_checks(input1, input2, input3, output, Nw):
+    # my_lib_cuda.c:1160-1215
+    if Nw != 3.0:
+        return None
+    batch, channel, h, w = input1.size()
+    if channel != 3 or input2.size(0) != batch or input2.size(2) != h or input2.size(3) != w:
+        return None
+    if input3.size(1) != 2 or output.size(1) != 1:
+        return None
+    if input1.stride(3) != 1 or input2.stride(3) != 1 or input3.stride(3) != 1:
+        return None
+    if input1.stride(0) != input2.stride(0):
+        return None
+    return batch, channel, h, w
+
+
+def WeightLayer_gpu_forward(input1, input2, input3, output, lambda_e, lambda_v, Nw):
+    """my_lib_cuda.c:1142-1238 (declared my_lib_cuda.h:147-152)."""
+    d = _wl_checks(input1, input2, input3, output, Nw)
+    if d is None:
+        return _ERR
+    batch, channel, h, w = d
+    return _go_tail("WeightLayer_gpu_forward_kernel", [output.numel(), w, h, channel, batch],
+                    [input1, input2, input3, output], [input1, input2, input3, output], [lambda_e, lambda_v, Nw])
+
+
+def WeightLayer_gpu_backward(input1, input2, input3, output, gradoutput, gradinput1, gradinput2, gradinput3,
+                             lambda_e, lambda_v, Nw):
+    """my_lib_cuda.c:1240-1333 (declared my_lib_cuda.h:153-160)."""
+    d = _wl_checks(input1, input2, input3, output, Nw)
+    if d is None:
+        return _ERR
+    batch, channel, h, w = d
+    if input1.stride(0) != gradinput1.stride(0) or input1.stride(1) != gradinput1.stride(1):
+        return _ERR
+    if input2.stride(0) != gradinput2.stride(0) or input2.stride(1) != gradinput2.stride(1):
+        return _ERR
+    if input3.stride(0) != gradinput3.stride(0) or input3.stride(1) != gradinput3.stride(1):
+        return _ERR
+    return _go_tail("WeightLayer_gpu_backward_kernel", [gradoutput.numel(), w, h, channel, batch],
+                    [input1, input2, input3, output],
+                    [input1, input2, input3, output, gradoutput, gradinput1, gradinput2, gradinput3],
+                    [lambda_e, lambda_v, Nw])
 
 
 # ------------------------------------------------------------------ SeparableConvFlow

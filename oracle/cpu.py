@@ -179,6 +179,25 @@ def pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sigma_d
     return (gi1 if mode == "value" else None), gi3, (gfw if mode != "reliable" else None)
 
 
+def weight_layer_forward(in1, in2, flow, lambda_e, Nw=3.0, precision="f32"):
+    in1, in2, flow = _f32(in1), _f32(in2), _f32(flow)
+    B, C, H, W = in1.shape
+    out = np.zeros((B, 1, H, W), _real(precision))
+    _check(_lib(precision).oracle_weight_layer_forward(B, C, H, W, _p(in1), _p(in2), _p(flow), _p(out),
+                                                       ctypes.c_float(lambda_e), ctypes.c_float(Nw)), "weight_layer_forward")
+    return out
+
+
+def weight_layer_backward(in1, in2, flow, fout, gout, lambda_e, Nw=3.0, precision="f32"):
+    in1, in2, flow, fout, gout = _f32(in1), _f32(in2), _f32(flow), _f32(fout), _f32(gout)
+    B, C, H, W = in1.shape
+    r = _real(precision)
+    g1, g2, g3 = np.zeros(in1.shape, r), np.zeros(in2.shape, r), np.zeros(flow.shape, r)
+    _check(_lib(precision).oracle_weight_layer_backward(B, C, H, W, _p(in1), _p(in2), _p(flow), _p(fout), _p(gout), _p(g1), _p(g2),
+                                                        _p(g3), ctypes.c_float(lambda_e), ctypes.c_float(Nw)), "weight_layer_backward")
+    return g1, g2, g3
+
+
 def separable_conv_flow_forward(vert, horiz, precision="f32"):
     vert, horiz = _f32(vert), _f32(horiz)
     B, fs, Ho, Wo = vert.shape

@@ -649,6 +649,127 @@ ORACLE_API int oracle_pixel_splat_backward(int mode, int B, int C, int H, int W,
 }
 
 /* ------------------------------------------------------------------------------------
+ * WeightLayer: matching confidence (1 - err / lambda_e)^2, err = mean over the 3x3 neighbourhood and the channels of
+ * |input1 around the pixel - input2 bilinearly sampled around pixel + flow|; 1e-4 where the target leaves the frame.
+ *   forward  : my_lib.c:2297-2340 (CUDA: my_lib_kernel.cu:3048-3122)
+ *   backward : my_lib.c:2468-2532 (CUDA: :3208-3322): the sign of every difference steers +-g into gi1 / gi2 / gi3
+ * The float build follows the C source operation for operation (its `fabs` is the double function: the running sum is
+ * rounded through double, my_lib.c:2325); the sign decisions are fp32 decisions in both builds.
+ * ---------------------------------------------------------------------------------- */
+static inline int wl_geometry(int H, int W, const float *flow, size_t plane, int h, int w, int *L, int *T, int *R, int *Bm,
+                              float *alpha, float *beta)
+{
+    const float fx = flow[(size_t)h * W + w], fy = flow[plane + (size_t)h * W + w];
+    const float x2 = (float)w + fx, y2 = (float)h + fy;
+    if (!(x2 >= 0.0f && y2 >= 0.0f && x2 <= (float)(W - 1) && y2 <= (float)(H - 1))) return 0;
+    *L = (int)x2; *T = (int)y2;
+    *R = mini(*L + 1, W - 1); *Bm = mini(*T + 1, H - 1);
+    *alpha = x2 - (int)x2; *beta = y2 - (int)y2;
+    return 1;
+}
+/* the bilinear sample in fp32, as the reference evaluates it (drives the sign decisions in both builds) */
+static inline float wl_target(float a, float b, float tl, float tr, float bl, float br)
+{
+    return (1 - a) * (1 - b) * tl + a * (1 - b) * tr + (1 - a) * b * bl + a * b * br;
+}
+
+ORACLE_API int oracle_weight_layer_forward(int B, int C, int H, int W, const float *in1, const float *in2, const float *flow,
+                                           real *out, float lambda_e, float Nw)
+{
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                int L, T, R, Bm; float a, bt;
+                real *o = out + (size_t)b * plane + (size_t)h * W + w;
+                if (!wl_geometry(H, W, flow + (size_t)b * 2 * plane, plane, h, w, &L, &T, &R, &Bm, &a, &bt)) { *o = (real)1e-4f; continue; }
+                float err_f = 0.0f;
+                real err = (real)0;
+                for (int m = -1; m <= 1; ++m)
+                    for (int n = -1; n <= 1; ++n) {
+                        const int p1m = clampi(m + h, 0, H - 1), p1n = clampi(n + w, 0, W - 1);
+                        const int mT = clampi(m + T, 0, H - 1), mB = clampi(m + Bm, 0, H - 1);
+                        const int nL = clampi(n + L, 0, W - 1), nR = clampi(n + R, 0, W - 1);
+                        for (int c = 0; c < C; ++c) {
+                            const float *s = in2 + ((size_t)b * C + c) * plane;
+                            const float tl = s[(size_t)mT * W + nL], tr = s[(size_t)mT * W + nR];
+                            const float bl = s[(size_t)mB * W + nL], br = s[(size_t)mB * W + nR];
+                            const float i_data = in1[((size_t)b * C + c) * plane + (size_t)p1m * W + p1n];
+                            err_f = (float)((double)err_f + fabs((double)(i_data - wl_target(a, bt, tl, tr, bl, br))));
+                            const real t64 = ((real)1 - a) * ((real)1 - bt) * tl + (real)a * ((real)1 - bt) * tr +
+                                             ((real)1 - a) * (real)bt * bl + (real)a * (real)bt * br;
+                            err += (real)fabs((double)((real)i_data - t64));
+                        }
+                    }
+                if (sizeof(real) == sizeof(float)) {
+                    err_f /= ((float)C * Nw * Nw);
+                    *o = (real)((1 - err_f / lambda_e) * (1 - err_f / lambda_e));
+                } else {
+                    err /= ((real)C * Nw * Nw);
+                    *o = ((real)1 - err / lambda_e) * ((real)1 - err / lambda_e);
+                }
+            }
+    return 0;
+}
+
+/* fout = the forward's output; gi1 / gi2 / gi3 are added into */
+ORACLE_API int oracle_weight_layer_backward(int B, int C, int H, int W, const float *in1, const float *in2, const float *flow,
+                                            const float *fout, const float *gout, real *gi1, real *gi2, real *gi3,
+                                            float lambda_e, float Nw)
+{
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0) return -1;
+    const size_t plane = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                int L, T, R, Bm; float af, btf;
+                if (!wl_geometry(H, W, flow + (size_t)b * 2 * plane, plane, h, w, &L, &T, &R, &Bm, &af, &btf)) continue;
+                const size_t pix = (size_t)h * W + w;
+                const real a = (real)af, bt = (real)btf;
+                const real go = (real)gout[(size_t)b * plane + pix];
+                real ges;
+                if (sizeof(real) == sizeof(float))
+                    ges = (real)(-gout[(size_t)b * plane + pix] / (lambda_e * C * Nw * Nw) * 2 * sqrtf(fout[(size_t)b * plane + pix]));
+                else
+                    ges = -go / ((real)lambda_e * C * Nw * Nw) * 2 * (real)sqrt((double)fout[(size_t)b * plane + pix]);
+                real *gx = gi3 + (size_t)b * 2 * plane + pix, *gy = gx + plane;
+                for (int m = -1; m <= 1; ++m)
+                    for (int n = -1; n <= 1; ++n) {
+                        const int p1m = clampi(m + h, 0, H - 1), p1n = clampi(n + w, 0, W - 1);
+                        const int mT = clampi(m + T, 0, H - 1), mB = clampi(m + Bm, 0, H - 1);
+                        const int nL = clampi(n + L, 0, W - 1), nR = clampi(n + R, 0, W - 1);
+                        for (int c = 0; c < C; ++c) {
+                            const size_t ch = ((size_t)b * C + c) * plane;
+                            const float *s = in2 + ch;
+                            const float tl = s[(size_t)mT * W + nL], tr = s[(size_t)mT * W + nR];
+                            const float bl = s[(size_t)mB * W + nL], br = s[(size_t)mB * W + nR];
+                            const float i_data = in1[ch + (size_t)p1m * W + p1n];
+                            const int above = i_data > wl_target(af, btf, tl, tr, bl, br);
+                            const real s1 = above ? ges : -ges, s2 = above ? -ges : ges;
+                            gi1[ch + (size_t)p1m * W + p1n] += s1;
+                            gi2[ch + (size_t)mT * W + nL] += ((real)1 - a) * ((real)1 - bt) * s2;
+                            gi2[ch + (size_t)mT * W + nR] += a * ((real)1 - bt) * s2;
+                            gi2[ch + (size_t)mB * W + nL] += ((real)1 - a) * bt * s2;
+                            gi2[ch + (size_t)mB * W + nR] += a * bt * s2;
+                            real gamma = (real)1.0f - bt, t = (real)0;
+                            t += gamma * ((real)tr - (real)tl);
+                            t += ((real)1 - gamma) * ((real)br - (real)bl);
+                            t = t * s2;
+                            *gx += t;
+                            gamma = (real)1.0f - a;
+                            t = (real)0;
+                            t += gamma * ((real)bl - (real)tl);
+                            t += gamma * ((real)br - (real)tr);   /* gamma for both rows: my_lib.c:2524 / my_lib_kernel.cu:3310 */
+                            t = t * s2;
+                            *gy += t;
+                        }
+                    }
+            }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * SeparableConvFlow: the flow a pair of separable filters encodes (centroid of the taps minus (fs-1)/2) on the valid
  * region Ho x Wo = (H-fs+1) x (W-fs+1); -2000 where the taps sum to 0.  Follows the CUDA source my_lib_kernel.cu:52-80
  * (forward), :108-160 (backward); the CPU twin my_lib.c:53-66 divides by |sum| instead of the signed sum, so the two

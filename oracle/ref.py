@@ -205,6 +205,23 @@ def cpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sig
     return None, g3, None
 
 
+def cpu_weight_layer_forward(in1, in2, flow, lambda_e):
+    in1, in2, flow = _c(in1), _c(in2), _c(flow)
+    out = np.zeros((in1.shape[0], 1) + in1.shape[2:], np.float32)
+    rc = _cpu().WeightLayer_cpu_forward(_TH(in1).ref, _TH(in2).ref, _TH(flow).ref, _TH(out).ref, _f(lambda_e), _f(0), _f(3))
+    assert rc == 0, rc
+    return out
+
+
+def cpu_weight_layer_backward(in1, in2, flow, fout, gout, lambda_e):
+    in1, in2, flow, fout, gout = _c(in1), _c(in2), _c(flow), _c(fout), _c(gout)
+    g1, g2, g3 = np.zeros_like(in1), np.zeros_like(in2), np.zeros_like(flow)
+    rc = _cpu().WeightLayer_cpu_backward(_TH(in1).ref, _TH(in2).ref, _TH(flow).ref, _TH(fout).ref, _TH(gout).ref,
+                                         _TH(g1).ref, _TH(g2).ref, _TH(g3).ref, _f(lambda_e), _f(0), _f(3))
+    assert rc == 0, rc
+    return g1, g2, g3
+
+
 def cpu_separable_conv_flow_forward(in1, vert, horiz):
     in1, vert, horiz = _c(in1), _c(vert), _c(horiz)
     flow = np.zeros((vert.shape[0], 2) + vert.shape[2:], np.float32)
@@ -436,6 +453,28 @@ def gpu_pixel_splat_backward(mode, flow, gout, in1=None, fw=None, fout=None, sig
         _d(flow), _d(fout), _d(gout), _d(g3), _f(threshold), *f3)
     assert rc == 0, rc
     return None, g3, None
+
+
+def gpu_weight_layer_forward(in1, in2, flow, lambda_e):
+    import torch
+    B, C, H, W = in1.shape
+    out = torch.zeros(B, 1, H, W, device=in1.device)
+    rc = _gpu().WeightLayer_gpu_forward_kernel(
+        _stream(), _i(out.numel()), _i(W), _i(H), _i(C), _i(B), *_s(in1), *_s(in2), *_s(flow), *_s(out),
+        _d(in1), _d(in2), _d(flow), _d(out), _f(lambda_e), _f(0), _f(3))
+    assert rc == 0, rc
+    return out
+
+
+def gpu_weight_layer_backward(in1, in2, flow, fout, gout, lambda_e):
+    import torch
+    B, C, H, W = in1.shape
+    g1, g2, g3 = torch.zeros_like(in1), torch.zeros_like(in2), torch.zeros_like(flow)
+    rc = _gpu().WeightLayer_gpu_backward_kernel(
+        _stream(), _i(gout.numel()), _i(W), _i(H), _i(C), _i(B), *_s(in1), *_s(in2), *_s(flow), *_s(fout),
+        _d(in1), _d(in2), _d(flow), _d(fout), _d(gout), _d(g1), _d(g2), _d(g3), _f(lambda_e), _f(0), _f(3))
+    assert rc == 0, rc
+    return g1, g2, g3
 
 
 def gpu_separable_conv_flow_forward(in1, vert, horiz):

@@ -899,6 +899,61 @@ def test_weighted_flow_projection_vs_reference_cuda_kernels(L, fillhole):
               what="WeightedFlowProjection bwd vs reference CUDA")
 
 
+# ------------------------------------------------------------------------------------- WeightLayer
+def _mostly_close(got, exp, what, frac=5e-4):
+    """The backward takes 27 x C sign decisions per pixel on fp32 values whose last bit depends on FMA contraction; a near-tie
+    flips one contribution.  All but a fraction `frac` of the elements must agree to TOL; none may be off by more than a
+    few flipped contributions."""
+    got = host(got) if isinstance(got, torch.Tensor) else got
+    exp = np.asarray(exp, np.float64)
+    scale = max(1.0, float(np.abs(exp).max()))
+    d = np.abs(got.astype(np.float64) - exp)
+    off = float((d > TOL * scale).mean())
+    assert off <= frac, "%s: %.2e of the elements differ by more than %.1e" % (what, off, TOL * scale)
+    return off
+
+
+@pytest.mark.parametrize("shape", FP_SHAPES)
+def test_weight_layer_vs_oracle_and_reference_cuda(L, shape):
+    import my_package._ext.my_lib as my_lib
+    S, P = L.strides_of, L.ptr
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=79)
+    rng = np.random.default_rng(81)
+    in1, in2 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+    lam = 0.9
+    t1, t2, t3 = dev(in1), dev(in2), dev(flow)
+    e = cpu.weight_layer_forward(in1, in2, flow, lam, 3.0, "f64")
+    out = torch.full((B, 1, H, W), 7.0, device="cuda")
+    assert my_lib.WeightLayer_gpu_forward(t1, t2, t3, out, lam, 0.0, 3.0) == 0
+    close(out, e, what="WeightLayer forward")
+    assert my_lib.WeightLayer_gpu_forward(t1, t2, t3, out, lam, 0.0, 5.0) == -1   # Nw must be 3
+    o2 = torch.empty_like(out)
+    L.call("memc_b200_weight_layer_forward", L.stream_ptr(t1), B, 3, H, W, lam, 3.0, S(t1), S(t2), S(t3), S(o2),
+           P(t1), P(t2), P(t3), P(o2), L.OVERWRITE)
+    assert torch.equal(o2, out)
+    fout = host(out)
+    gout = rng.standard_normal(fout.shape).astype(np.float32)
+    tg = dev(gout)
+    e1, e2, e3 = cpu.weight_layer_backward(in1, in2, flow, fout, gout, lam, 3.0, "f64")
+    g1, g2, g3 = torch.full_like(t1, 7.0), torch.full_like(t2, 7.0), torch.full_like(t3, 7.0)
+    L.call("memc_b200_weight_layer_backward", L.stream_ptr(t1), B, 3, H, W, lam, 3.0, S(t1), S(t2), S(t3), S(out),
+           P(t1), P(t2), P(t3), P(out), P(tg), P(g1), P(g2), P(g3), L.OVERWRITE)
+    _mostly_close(g1, e1, "WeightLayer gi1"), _mostly_close(g2, e2, "WeightLayer gi2"), _mostly_close(g3, e3, "WeightLayer gi3")
+    h1, h2, h3 = torch.ones_like(t1), torch.ones_like(t2), torch.ones_like(t3)   # reference contract: accumulated into
+    assert my_lib.WeightLayer_gpu_backward(t1, t2, t3, out, tg, h1, h2, h3, lam, 0.0, 3.0) == 0
+    _mostly_close(h1, e1 + 1.0, "WeightLayer gi1 (named, +=)"), _mostly_close(h2, e2 + 1.0, "WeightLayer gi2 (named, +=)")
+    _mostly_close(h3, e3 + 1.0, "WeightLayer gi3 (named, +=)")
+    if ref.available_gpu():
+        r = ref.gpu_weight_layer_forward(t1, t2, t3, lam)
+        close(out, host(r), what="WeightLayer forward vs reference CUDA")
+        r1, r2, r3 = ref.gpu_weight_layer_backward(t1, t2, t3, r, tg, lam)
+        g1, g2, g3 = torch.zeros_like(t1), torch.zeros_like(t2), torch.zeros_like(t3)
+        assert my_lib.WeightLayer_gpu_backward(t1, t2, t3, r, tg, g1, g2, g3, lam, 0.0, 3.0) == 0
+        _mostly_close(g1, host(r1), "WeightLayer gi1 vs reference CUDA"), _mostly_close(g2, host(r2), "WeightLayer gi2 vs reference CUDA")
+        _mostly_close(g3, host(r3), "WeightLayer gi3 vs reference CUDA")
+
+
 # ------------------------------------------------------------------------------- SeparableConvFlow
 @pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3), (1, 3, 4, 4, 4), (2, 3, 64, 96, 4)])
 def test_separable_conv_flow_vs_oracle_and_reference_cuda(L, shape):

@@ -122,6 +122,23 @@ def test_pixel_splat_family_bit_exact(shape, mode):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 64, 3.0), (2, 37, 53, 8.0), (1, 24, 24, 40.0), (1, 1, 1, 0.0)])
+def test_weight_layer_bit_exact(shape):
+    """WeightLayer against my_lib.c:2251-2614, forward and backward (sign decisions included: same fp32 expressions)."""
+    B, H, W, sigma = shape
+    flow = flow_case(B, H, W, sigma, seed=41)
+    rng = np.random.default_rng(43)
+    in1, in2 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+    lam = 0.9
+    out = cpu.weight_layer_forward(in1, in2, flow, lam)
+    assert np.array_equal(out, ref.cpu_weight_layer_forward(in1, in2, flow, lam))
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    for a, b in zip(cpu.weight_layer_backward(in1, in2, flow, out, gout, lam),
+                    ref.cpu_weight_layer_backward(in1, in2, flow, out, gout, lam)):
+        assert np.array_equal(a, b)
+
+
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 3, 32, 32, 4), (2, 3, 21, 35, 5), (1, 3, 9, 9, 3), (1, 3, 4, 4, 4)])
 def test_separable_conv_flow_bit_exact(shape):
     """SeparableConvFlow against my_lib.c:13-249 on filters with a positive tap sum (the reference's C source divides by
