@@ -75,6 +75,25 @@ def main():
                             sigma_d=np.float32(sd), threshold=np.float32(thr), out=out, gout=gout,
                             g1=g1 if g1 is not None else np.zeros(0, np.float32), g3=g3,
                             gw=gw if gw is not None else np.zeros(0, np.float32))
+    for name, (B, H, W, sigma, seed) in {"wl_small": (2, 12, 16, 3.0, 119), "wl_wild": (1, 10, 10, 15.0, 120)}.items():
+        flow = flow_case(B, H, W, sigma, seed)
+        rng = np.random.default_rng(seed)
+        in1, in2 = rng.random((B, 3, H, W), dtype=np.float32), rng.random((B, 3, H, W), dtype=np.float32)
+        lam = 0.9
+        out = ref.cpu_weight_layer_forward(in1, in2, flow, lam)
+        gout = rng.standard_normal(out.shape).astype(np.float32)
+        g1, g2, g3 = ref.cpu_weight_layer_backward(in1, in2, flow, out, gout, lam)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="weight_layer", in1=in1, in2=in2, flow=flow, lambda_e=np.float32(lam),
+                            out=out, gout=gout, g1=g1, g2=g2, g3=g3)
+    for name, (B, C, H, W, fs, seed) in {"scf_fs4": (2, 3, 12, 15, 4, 121)}.items():
+        in1, v, hz, _ = sepconv_case(B, C, H, W, fs, seed)
+        v, hz = np.abs(v) + np.float32(0.01), np.abs(hz) + np.float32(0.01)   # positive sums: the C and CUDA sources agree
+        v[0, :, 0, 0] = 0.0
+        flow = ref.cpu_separable_conv_flow_forward(in1, v, hz)
+        gflow = np.random.default_rng(seed).standard_normal(flow.shape).astype(np.float32)
+        gv, gh = ref.cpu_separable_conv_flow_backward(in1, v, hz, gflow)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), op="separable_conv_flow", in1=in1, vert=v, horiz=hz, flow=flow,
+                            gflow=gflow, gv=gv, gh=gh)
     for name, (B, C, H, W, sigma, seed) in {"ip_rgb": (2, 3, 12, 16, 3.0, 120), "ip_c7": (1, 7, 9, 13, 2.0, 121)}.items():
         in1, flow, _, gout = fi_case(B, C, H, W, 4, sigma, seed)
         out = ref.cpu_interpolation_forward(in1, flow)

@@ -1309,6 +1309,24 @@ def test_cuda_path_matches_golden_fixtures(L):
                 assert my_lib.ReliableWeightLayer_gpu_forward(t, out, sd, 0.0, 2.0) == 0
                 assert my_lib.ReliableWeightLayer_gpu_backward(t, dev(z["out"]), go, g3, thr, sd, 0.0, 2.0) == 0
             close(out, z["out"], what=path), close(g3, z["g3"], what=path)
+        elif op == "weight_layer":
+            t1, t2, t3, lam = dev(z["in1"]), dev(z["in2"]), dev(z["flow"]), float(z["lambda_e"])
+            out = torch.zeros(*z["out"].shape, device="cuda")
+            assert my_lib.WeightLayer_gpu_forward(t1, t2, t3, out, lam, 0.0, 3.0) == 0
+            close(out, z["out"], what=path)
+            g1, g2, g3 = torch.zeros_like(t1), torch.zeros_like(t2), torch.zeros_like(t3)
+            assert my_lib.WeightLayer_gpu_backward(t1, t2, t3, dev(z["out"]), dev(z["gout"]), g1, g2, g3, lam, 0.0, 3.0) == 0
+            for got, k in ((g1, "g1"), (g2, "g2"), (g3, "g3")):   # a near-tie may flip a sign: all but a few elements
+                d = np.abs(host(got) - z[k])
+                assert float((d > 1e-5 * max(1.0, np.abs(z[k]).max())).mean()) <= 5e-3, (path, k)
+        elif op == "separable_conv_flow":
+            t1, tv, th = dev(z["in1"]), dev(z["vert"]), dev(z["horiz"])
+            flow = torch.zeros(*z["flow"].shape, device="cuda")
+            assert my_lib.SeparableConvFlowLayer_gpu_forward(t1, tv, th, flow) == 0
+            close(flow, z["flow"], what=path)
+            g1, gv, gh = torch.zeros_like(t1), torch.zeros_like(tv), torch.zeros_like(th)
+            assert my_lib.SeparableConvFlowLayer_gpu_backward(t1, tv, th, dev(z["gflow"]), g1, gv, gh) == 0
+            close(gv, z["gv"], what=path), close(gh, z["gh"], what=path)
         elif op == "interpolation":
             t1, t2 = dev(z["in1"]), dev(z["flow"])
             out = torch.zeros_like(t1)
