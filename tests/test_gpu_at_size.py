@@ -177,7 +177,7 @@ def test_depth_flow_projection_at_size_vs_reference_kernels(L, kind):
     # convergent field the two errors are the same noise (1.0-1.7e-3 from run to run), so the bar is a factor, not an order
     assert e_ours <= 2.0 * e_ref + TOL, "ours is further from the exact result (%.3e) than twice the reference kernels' (%.3e)" % (e_ours, e_ref)
     for r in rows[:4]:
-        bound = max(TOL, 3.0 * r["ref_spread"], 2.0 * e_ref, 2e-6 * r["ref_max"])
+        bound = max(TOL, 3.0 * r["ref_spread"], 2.0 * e_ref, 4e-6 * r["ref_max"])   # ~30 fp32 ulps of the largest sum
         assert r["max_abs"] <= bound, "DFP %s %s: unscaled max-abs %.3e > %.3e" % (kind, r["tensor"], r["max_abs"], bound)
 
 
