@@ -375,6 +375,37 @@ def other_ops_and_legacy(torch, lib, synth, dev, st, peak, main_tensors):
         entry("%s forward 1920x1080, batch 4" % name, PB * H * W, bpp_f, tf, tlf)
         entry("%s backward 1920x1080, batch 4" % name, PB * H * W, bpp_b, tb, tlb)
         del po, pg, g1_, g3_, gw_
+    # --- WeightLayer (matching confidence) and SeparableConvFlow (the flow two separable filters encode), B = 4
+    pim2 = torch.rand(PB, 3, H, W, device=dev)
+    wo, wg = torch.empty(PB, 1, H, W, device=dev), torch.randn(PB, 1, H, W, device=dev)
+    wg1, wg2, wg3 = torch.empty_like(pim), torch.empty_like(pim2), torch.empty_like(pfl)
+    lam = 0.9
+    tf = _timed(torch, lambda: lib.call("memc_b200_weight_layer_forward", st, PB, 3, H, W, lam, 3.0, S(pim), S(pim2), S(pfl), S(wo),
+                                        P(pim), P(pim2), P(pfl), P(wo), lib.OVERWRITE))
+    tb = _timed(torch, lambda: lib.call("memc_b200_weight_layer_backward", st, PB, 3, H, W, lam, 3.0, S(pim), S(pim2), S(pfl), S(wo),
+                                        P(pim), P(pim2), P(pfl), P(wo), P(wg), P(wg1), P(wg2), P(wg3), lib.OVERWRITE), 5)
+    tlf = tlb = None
+    if have_ref:
+        tlf = _timed(torch, lambda: ref.gpu_weight_layer_forward(pim, pim2, pfl, lam), 3)
+        tlb = _timed(torch, lambda: ref.gpu_weight_layer_backward(pim, pim2, pfl, wo, wg, lam), 3)  # incl. its zero fills
+    entry("WeightLayer forward 1920x1080, batch 4", PB * H * W, (3 + 3 + 2 + 1) * 4, tf, tlf)
+    entry("WeightLayer backward 1920x1080, batch 4", PB * H * W, (3 + 3 + 2 + 1 + 1 + 3 + 3 + 2) * 4, tb, tlb)
+    del pim2, wo, wg, wg1, wg2, wg3
+    Ho, Wo = H - FS + 1, W - FS + 1
+    sv, sh = torch.rand(PB, FS, Ho, Wo, device=dev) + 0.01, torch.rand(PB, FS, Ho, Wo, device=dev) + 0.01
+    sf, sg = torch.empty(PB, 2, Ho, Wo, device=dev), torch.randn(PB, 2, Ho, Wo, device=dev)
+    sgv, sgh = torch.empty_like(sv), torch.empty_like(sh)
+    tf = _timed(torch, lambda: lib.call("memc_b200_separable_conv_flow_forward", st, PB, H, W, FS, S(sv), S(sh), S(sf), P(sv), P(sh),
+                                        P(sf), lib.OVERWRITE))
+    tb = _timed(torch, lambda: lib.call("memc_b200_separable_conv_flow_backward", st, PB, H, W, FS, S(sv), S(sh), S(sg), S(sgv), S(sgh),
+                                        P(sv), P(sh), P(sg), P(sgv), P(sgh), lib.OVERWRITE))
+    tlf = tlb = None
+    if have_ref:
+        tlf = _timed(torch, lambda: ref.gpu_separable_conv_flow_forward(pim, sv, sh), 3)
+        tlb = _timed(torch, lambda: ref.gpu_separable_conv_flow_backward(pim, sv, sh, sg), 3)
+    entry("SeparableConvFlow forward 1920x1080, fs=4, batch 4", PB * H * W, (2 * FS + 2) * 4, tf, tlf)
+    entry("SeparableConvFlow backward 1920x1080, fs=4, batch 4", PB * H * W, (2 * FS + 2 + 2 * FS) * 4, tb, tlb)
+    del sv, sh, sf, sg, sgv, sgh
     del pfl, pim, pfw
     torch.cuda.empty_cache()
 
