@@ -345,7 +345,7 @@ int dfp_forward(cudaStream_t stream, const DfpArgs& a_in, int flags) {
     // the weighted shared-memory splat, average + occupancy masks, mask-based fill-hole (O(1) per hole where the walks of
     // the generic kernel are O(W): 29 ms -> under 1 ms per 16 frames when the flow converges and most of the frame is a hole)
     if (!(flags & MEMC_B200_NO_FAST) && ensure_dynamic_smem(dfp_splat_kernel, sizeof(DSmem))) {
-        const int r = fp_frames_fast(stream, f, ow, no_zero, true, dfp_splat_frame, &a);
+        const int r = fp_frames_fast(stream, f, ow, no_zero, true, dfp_splat_frame, &a, nullptr, 0);
         if (r != 0) return r < 0 ? -1 : 0;
     }
     if (ow && !no_zero) {

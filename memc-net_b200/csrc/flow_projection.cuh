@@ -23,8 +23,9 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
 // signed_counts: count is an accumulated weight that may be <= 0 / NaN where something landed (DepthFlowProjection).
 // 1 = handled, 0 = layout preconditions not met, -1 = error
 typedef int (*FpSplatFn)(cudaStream_t stream, const void* ctx, int b);
+// extra: one more dense [B,1,H,W] plane (batch stride extra_b) that the average pass divides by count as well, or null
 int fp_frames_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, bool signed_counts, FpSplatFn splat,
-                   const void* ctx);
+                   const void* ctx, float* extra, int64_t extra_b);
 // average (+ fill-hole) over frames [b0, b0 + nb) with the generic kernels (flow_projection.cu)
 int fp_average_fill(cudaStream_t stream, const FpArgs& a, int b0, int nb, bool do_average);
 

@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(NT, 4) fp_splat_kernel(const FpArgs p, const i
 template <bool SIGNED>
 __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict__ out, const float* __restrict__ count,
                                                               unsigned* __restrict__ rowmask, unsigned* __restrict__ colmask,
-                                                              int W, int H, int Wt, int Ht, int64_t out_c) {
+                                                              int W, int H, int Wt, int Ht, int64_t out_c,
+                                                              float* __restrict__ extra) {  // extra: one more plane to divide, or null
     // CTA = 128 x 32 pixels: warp w handles rows w, w+8, w+16, w+24; a lane owns 4 consecutive
     // pixels (128-bit accesses; W % 4 == 0 is a precondition of the fast path)
     __shared__ unsigned rw[32][4];
@@ -323,6 +324,14 @@ __global__ void __launch_bounds__(256) fp_average_mask_kernel(float* __restrict_
                 if (c.w > 0.f) { vx.w /= c.w; vy.w /= c.w; }
                 *reinterpret_cast<float4*>(out + o) = vx;
                 *reinterpret_cast<float4*>(out + out_c + o) = vy;
+                if (extra) {  // WeightedFlowProjection's weight plane (my_lib_kernel.cu:2653), dense like count
+                    float4 e = *reinterpret_cast<float4*>(extra + o);
+                    if (c.x > 0.f) e.x /= c.x;
+                    if (c.y > 0.f) e.y /= c.y;
+                    if (c.z > 0.f) e.z /= c.z;
+                    if (c.w > 0.f) e.w /= c.w;
+                    *reinterpret_cast<float4*>(extra + o) = e;
+                }
             }
         }
         // nibble of this lane -> the 32-pixel word of its 8-lane group (bit = pixel x % 32)
@@ -867,14 +876,15 @@ int fp_forward_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool n
         if (r != 0) return r;
     }
     if (!ensure_dynamic_smem(fp_splat_kernel, sizeof(Smem))) return 0;
-    return fp_frames_fast(stream, a, overwrite, no_zero, false, fp_splat_frame, &a);
+    return fp_frames_fast(stream, a, overwrite, no_zero, false, fp_splat_frame, &a, nullptr, 0);
 }
 
 // frame by frame: [zero fills] -> splat(b) (the caller's kernel) -> average + occupancy masks, then ONE mask-based fill-hole
 // launch over the batch.  A frame's count + output planes (25 MB at 1080p) stay L2-resident between its passes.
 int fp_frames_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no_zero, bool signed_counts, FpSplatFn splat,
-                   const void* ctx) {
+                   const void* ctx, float* extra, int64_t extra_b) {
     if (!fp_fast_layout_ok(a)) return 0;
+    if (extra && ((reinterpret_cast<uintptr_t>(extra) & 15u) || extra_b % 4)) return 0;
     const int64_t plane = (int64_t)a.H * a.W;
     // occupancy masks: stream-ordered scratch (1 bit per pixel, twice), freed on the same stream
     const int Wt = (a.W + 31) / 32, Ht = (a.H + 31) / 32;
@@ -896,10 +906,12 @@ int fp_frames_fast(cudaStream_t stream, const FpArgs& a, bool overwrite, bool no
         if (splat(stream, ctx, b) != 0) rc = -1;
         if (signed_counts)
             fp_average_mask_kernel<true><<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
-                                                                     colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
+                                                                     colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c,
+                                                                     extra ? extra + (int64_t)b * extra_b : nullptr);
         else
             fp_average_mask_kernel<false><<<mgrid, 256, 0, stream>>>(outb, cntb, rowmask + (size_t)b * a.H * Wt,
-                                                                      colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c);
+                                                                      colmask + (size_t)b * Ht * a.W, a.W, a.H, Wt, Ht, a.out.c,
+                                                                      extra ? extra + (int64_t)b * extra_b : nullptr);
         count_launch(2);
         if (check_launch("FlowProjection splat/average (fast)")) rc = -1;
     }

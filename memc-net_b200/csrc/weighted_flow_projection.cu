@@ -156,8 +156,11 @@ int wfp_forward(cudaStream_t stream, const WfpArgs& a, int flags) {
     int r = 0;
     if (!(flags & MEMC_B200_NO_FAST)) {
         // FlowProjection's frame-by-frame driver: zero fills, this file's splat, average + occupancy masks, mask fill-hole
-        r = fp_frames_fast(stream, f, ow, no_zero, false, wfp_splat_frame, &a);
+        // (the weight plane rides along in the average pass when it is dense like count: h-stride == W)
+        const bool dense_w = a.wgt.h == f.W;
+        r = fp_frames_fast(stream, f, ow, no_zero, false, wfp_splat_frame, &a, dense_w ? a.wgtp : nullptr, a.wgt.b);
         if (r < 0) return -1;
+        if (r == 1 && dense_w) return 0;
     }
     if (r == 0) {
         if (ow && !no_zero) {
