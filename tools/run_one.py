@@ -72,3 +72,23 @@ if op in ("ip_bwd", "sc_bwd", "sc_fwd"):
                 lib.call("memc_b200_separable_conv_backward", st, B, 3, H, W, fs, S(in1), S(v), S(hz), S(go), S(g1), S(g2),
                          S(g3), P(in1), P(v), P(hz), P(go), P(g1), P(g2), P(g3), flags)
     torch.cuda.synchronize()
+if op in ("dfp_fwd", "wfp_fwd"):
+    H, W = 1080, 1920
+    fl = synth.smooth_flow(B, H, W, 6.0, seed=1, device="cuda")
+    cnt, prj = torch.empty(B, 1, H, W, device="cuda"), torch.empty_like(fl)
+    st = lib.stream_ptr(fl)
+    if op == "dfp_fwd":
+        dw = synth.inverse_depth(B, H, W, seed=7, device="cuda")
+        for _ in range(3):
+            lib.call("memc_b200_depth_flow_projection_forward", st, B, H, W, 1, S(fl), S(dw), S(cnt), S(prj), P(fl), P(dw), P(cnt),
+                     P(prj), flags)
+    else:
+        g = torch.Generator(device="cuda").manual_seed(9)
+        f0 = torch.nn.functional.interpolate(torch.rand(B, 3, H // 30, W // 30, device="cuda", generator=g), size=(H, W),
+                                             mode="bilinear", align_corners=True).contiguous()
+        f2 = (f0 + 0.2 * torch.randn(B, 3, H, W, device="cuda", generator=g)).contiguous()
+        wgt = torch.empty(B, 1, H, W, device="cuda")
+        for _ in range(3):
+            lib.call("memc_b200_weighted_flow_projection_forward", st, B, H, W, 1, 0.16, S(fl), S(f0), S(f2), S(cnt), S(wgt), S(prj),
+                     P(fl), P(f0), P(f2), P(cnt), P(wgt), P(prj), flags)
+    torch.cuda.synchronize()
